@@ -1,0 +1,199 @@
+/*
+ * wld.h — C ABI of libwld.so, the B200-native (sm_100a) implementation of WeightedLD's hot path:
+ *   encode + site filter  ->  Henikoff weights  ->  all-pairs weighted LD + r2 filter.
+ *
+ * The reference (ojcharles/WeightedLD) has no FFI; its seam is the Rust crate's `pub` API that
+ * rust/weighted_ld/src/main.rs:12 consumes (`use weighted_ld::*`).  Every entry point below names
+ * the reference item (file:line under the reference root) it replaces.  The header is plain C
+ * (C types only, opaque context, POD structs, int status codes) so that `bindgen` can bind it
+ * from a Rust `weighted_ld-sys` crate (INTEGRATION.md shows the stub).
+ *
+ * Contract
+ *  - One context per run and per GPU.  A context is not thread-safe; calls block until done.
+ *  - The caller owns every host buffer it passes; the library owns all device memory.  Results
+ *    are copied into caller buffers; no pointer into device or pinned memory is ever returned.
+ *  - Every function returns a wld_status.  On failure wld_last_error(ctx) holds a message.
+ *    There is NO CPU fallback: a CUDA failure is an error, never a silent downgrade.
+ *  - Stage order (main.rs:129-190): load -> filter (or keep_all) -> henikoff | set_weights ->
+ *    ld_pairs -> fetch_pairs.  Calling out of order returns WLD_ERR_STATE.
+ */
+#ifndef WLD_H
+#define WLD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WLD_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define WLD_API __attribute__((visibility("default")))
+#else
+#define WLD_API
+#endif
+
+typedef struct wld_ctx wld_ctx;
+
+typedef enum wld_status {
+  WLD_OK = 0,
+  WLD_ERR_INVALID = 1,     /* bad argument */
+  WLD_ERR_STATE = 2,       /* stage called out of order */
+  WLD_ERR_CUDA = 3,        /* CUDA runtime / driver failure, device missing, wrong architecture */
+  WLD_ERR_NOMEM = 4,       /* host or device allocation failed */
+  WLD_ERR_UNSUPPORTED = 5, /* size beyond the stated limits of the exact-accumulation scheme */
+  WLD_ERR_PANIC = 6        /* the reference would panic here (lib.rs:180-182 unequal lengths) */
+} wld_status;
+
+/* Symbol codes, lib.rs:20-29: A=0 C=1 G=2 T=3 Missing('-')=4 Unknown(anything else)=5. */
+enum { WLD_SYM_A = 0, WLD_SYM_C = 1, WLD_SYM_G = 2, WLD_SYM_T = 3, WLD_SYM_MISSING = 4, WLD_SYM_UNKNOWN = 5 };
+
+/* One surviving site pair: lib.rs:523-527 (PairData{first_idx, second_idx, data}) with
+ * lib.rs:382-387 (LdStats).  20 bytes, little-endian, no padding. */
+typedef struct wld_pair {
+  uint32_t site_a;  /* first_idx  (lib.rs:662) */
+  uint32_t site_b;  /* second_idx (lib.rs:663) */
+  float d;          /* lib.rs:502 */
+  float d_prime;    /* lib.rs:516 */
+  float r2;         /* lib.rs:518 */
+} wld_pair;
+
+/* wld_load_alignment flags */
+enum {
+  WLD_INPUT_ASCII = 0,   /* bytes are characters; encoded by lib.rs:53-64 on the GPU */
+  WLD_INPUT_CODES = 1,   /* bytes are already 0..5 codes (values > 5 are read as 5 = Unknown);
+                            the VCF path of WeightedLD.py:311-379 produces these */
+  WLD_INPUT_DEVICE = 2   /* `data` is a device pointer on the context's GPU (borrowed until the
+                            next load/destroy); otherwise a host pointer (copied) */
+};
+
+/* wld_fetch_pairs flags */
+enum {
+  WLD_FETCH_PARENT_INDEX = 0, /* site_a/site_b are raw alignment columns (lib.rs:662-663) */
+  WLD_FETCH_KEPT_INDEX = 1,   /* site_a/site_b index the filtered site set (for merging shards) */
+  WLD_FETCH_UNORDERED = 2     /* skip the sort into the reference's output order */
+};
+
+/* pair-kernel selection for wld_set_pair_kernel */
+enum {
+  WLD_PAIR_KERNEL_UMMA = 0, /* tcgen05/TMEM Gram tiles fed by TMA, fused epilogue (default) */
+  WLD_PAIR_KERNEL_SIMT = 1  /* CUDA-core FP64 kernel, same exact sums and epilogue; verification path */
+};
+
+/* stage ids for wld_stage_ms */
+enum {
+  WLD_STAGE_LOAD = 0,      /* H2D copy of the alignment (0 for device input) */
+  WLD_STAGE_HISTOGRAM = 1, /* per-column 6-bin histogram (part of wld_load_alignment) */
+  WLD_STAGE_FILTER = 2,    /* site decision + ordered compaction + encode/transpose of kept sites */
+  WLD_STAGE_HENIKOFF = 3,
+  WLD_STAGE_PAIR_PREP = 4, /* weight quantisation + indicator / limb operand expansion */
+  WLD_STAGE_PAIR = 5,      /* Gram + epilogue + compaction kernel(s) */
+  WLD_STAGE_COUNT = 6
+};
+
+/* Progress callback of all_weighted_ld_pairs (lib.rs:582): receives the number of site pairs
+ * finished so far; first call is 0 on the caller's thread (lib.rs:584); counts never decrease. */
+typedef void (*wld_progress_fn)(uint64_t pairs_computed, void* user);
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+/* Creates a context on CUDA device `device`.  Fails with WLD_ERR_CUDA when no sm_100 GPU is
+ * present.  (The reference has no setup step; this replaces process start in main.rs:121.) */
+WLD_API int wld_create(int device, wld_ctx** out);
+WLD_API void wld_destroy(wld_ctx* ctx);
+WLD_API const char* wld_last_error(const wld_ctx* ctx);
+WLD_API int wld_abi_version(void);
+
+/* Run all work on this CUDA stream (a cudaStream_t passed as void*); NULL = the context's own. */
+WLD_API int wld_set_stream(wld_ctx* ctx, void* cuda_stream);
+
+/* Shard the pair stage: this context computes part `part` of `nparts` of the upper-triangular
+ * tile grid (load-balanced, no collective).  Replaces rayon's tile fan-out, lib.rs:635-637. */
+WLD_API int wld_set_partition(wld_ctx* ctx, int part, int nparts);
+
+/* Weight limbs of the exact split-bf16 Gram (1..4, default 3 = 24-bit fixed-point weights;
+ * limbs are 8 bits wide, or narrower when n_seqs is so large that fp32 accumulation of 8-bit
+ * limbs could round — see DESIGN.md "precision contract"). */
+WLD_API int wld_set_limbs(wld_ctx* ctx, int n_limbs);
+WLD_API int wld_set_pair_kernel(wld_ctx* ctx, int kind);
+/* Initial capacity (in pairs) of the device survivor buffer; it grows automatically. */
+WLD_API int wld_set_pair_capacity(wld_ctx* ctx, uint64_t pairs);
+
+/* ---- stage 1: encode + histogram + filter -------------------------------------------------- */
+/* SiteSet::from_multiseq (lib.rs:176-206) for an alignment given as n_seqs rows of n_cols bytes,
+ * row pitch row_stride bytes (sequence-major, as read_fasta lib.rs:277-307 produces it,
+ * newline column included if the caller follows lib.rs:297).  Computes the 6-bin histogram of
+ * every column (lib.rs:98-104).  flags: WLD_INPUT_*. */
+WLD_API int wld_load_alignment(wld_ctx* ctx, const uint8_t* data, int64_t n_seqs, int64_t n_cols,
+                       int64_t row_stride, int flags);
+
+/* SiteSet::filter_by (lib.rs:230-251) with is_site_of_interest (lib.rs:310-338) and the
+ * threshold of main.rs:139: keep a site iff acgt > ceil(f32(min_acgt)*f32(n_seqs)) and a major
+ * and a minor symbol exist and min_minor <= minor/(minor+major) <= max_minor (f32).  Builds the
+ * kept, site-major 0..5 code matrix on the device. */
+WLD_API int wld_filter_sites(wld_ctx* ctx, float min_acgt, float min_minor, float max_minor, int64_t* n_kept);
+/* Use every column unfiltered (the reference's unit tests call henikoff_weights and
+ * single_weighted_ld_pair on unfiltered SiteSets, lib.rs:731-801). */
+WLD_API int wld_keep_all_sites(wld_ctx* ctx, int64_t* n_kept);
+
+WLD_API int64_t wld_n_seqs(const wld_ctx* ctx);   /* SiteSet::n_seqs  lib.rs:259 */
+WLD_API int64_t wld_n_cols(const wld_ctx* ctx);   /* SiteSet::n_sites lib.rs:254 of the unfiltered set */
+WLD_API int64_t wld_n_kept(const wld_ctx* ctx);   /* SiteSet::n_sites lib.rs:254 of the filtered set */
+/* site_map, lib.rs:169 / parent_site_index lib.rs:263: out[k] = raw column of kept site k. */
+WLD_API int wld_get_site_map(wld_ctx* ctx, int64_t* out, int64_t cap);
+/* Histograms of ALL raw columns, out[col*6 + sym] (SymbolHistogram, lib.rs:72-104). */
+WLD_API int wld_get_histograms(wld_ctx* ctx, uint32_t* out, int64_t cap_cols);
+/* major_minor_symbols (lib.rs:126-140) of the kept sites; -1 = None. */
+WLD_API int wld_get_major_minor(wld_ctx* ctx, int8_t* major, int8_t* minor, int64_t cap);
+/* Kept code matrix, site-major: out[k*n_seqs + seq] (SiteSet::site_symbols, lib.rs:267). */
+WLD_API int wld_get_codes(wld_ctx* ctx, uint8_t* out, int64_t cap_bytes);
+
+/* ---- stage 2: sequence weights ------------------------------------------------------------- */
+/* henikoff_weights (lib.rs:340-358) + henikoff_site_contributions (lib.rs:360-380) over the
+ * kept sites; f64 accumulation on the GPU, results held as f64 and as f32 (the reference type). */
+WLD_API int wld_henikoff(wld_ctx* ctx);
+/* Caller-supplied weights (main.rs:150-153 passes all-ones for --unweighted). Finite, >= 0, max > 0. */
+WLD_API int wld_set_weights(wld_ctx* ctx, const float* weights, int64_t n);
+WLD_API int wld_get_weights(wld_ctx* ctx, float* out, int64_t cap);
+WLD_API int wld_get_weights_f64(wld_ctx* ctx, double* out, int64_t cap);
+
+/* ---- stage 3: all-pairs weighted LD -------------------------------------------------------- */
+/* all_weighted_ld_pairs (lib.rs:578-684) with single_weighted_ld_pair (lib.rs:390-521): every
+ * pair b > a of kept sites (of this context's partition), D / D' / r2, keep r2 > r2_threshold
+ * (strict, NaN dropped, lib.rs:660).  Survivors stay on the device until fetched.
+ * n_survivors receives their count; pairs_computed (may be NULL) the number of pairs evaluated. */
+WLD_API int wld_ld_pairs(wld_ctx* ctx, float r2_threshold, wld_progress_fn progress, void* user,
+                 uint64_t* n_survivors, uint64_t* pairs_computed);
+/* PairStore::iter (lib.rs:533-575): copies the survivors into out[0..cap) in the reference's
+ * output order (tile rows bottom-up, columns ascending, then a, then b — lib.rs:623-679).
+ * flags: WLD_FETCH_*. */
+WLD_API int wld_fetch_pairs(wld_ctx* ctx, wld_pair* out, uint64_t cap, int flags, uint64_t* n_written);
+/* Sort key of the reference's output order for a pair of KEPT indices (for merging shards):
+ * lexicographic (key, a, b) ascending == reference order. */
+WLD_API uint64_t wld_pair_order_key(int64_t n_kept, uint32_t kept_a, uint32_t kept_b);
+
+/* ---- introspection ------------------------------------------------------------------------- */
+/* Device time of the last run of a stage in milliseconds (CUDA events on the context's stream). */
+WLD_API int wld_stage_ms(wld_ctx* ctx, int stage, float* ms);
+/* Kernel launches issued by the last run of a stage. */
+WLD_API int wld_stage_launches(wld_ctx* ctx, int stage, int* launches);
+/* Geometry of the last pair stage: limbs used, bits per limb, total weight bits, K padding,
+ * tiles computed, executed tensor flop. */
+typedef struct wld_pair_info {
+  int32_t kernel;          /* WLD_PAIR_KERNEL_* actually run */
+  int32_t n_limbs;
+  int32_t limb_bits;
+  int32_t weight_bits;     /* n_limbs * limb_bits */
+  int64_t k_padded;        /* sequences padded to the MMA K block */
+  int64_t tiles;           /* output tiles computed by this partition */
+  int64_t tile_sites_m;    /* kept sites per tile along a */
+  int64_t tile_sites_n;    /* kept sites per tile along b */
+  double executed_flop;    /* 2*M*N*K summed over MMA instructions issued */
+} wld_pair_info;
+WLD_API int wld_get_pair_info(wld_ctx* ctx, wld_pair_info* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WLD_H */

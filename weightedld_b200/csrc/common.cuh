@@ -1,0 +1,174 @@
+// common.cuh — context, error plumbing and launch declarations shared by the libwld.so sources.
+// Product code: never includes or links anything under oracle/.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/wld.h"
+
+namespace wld {
+
+constexpr int kNumSMsB200 = 148;
+
+// ---------------------------------------------------------------------------------------------
+// device buffer with explicit ownership
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= bytes && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&p, n ? n : 1);
+    if (e == cudaSuccess) bytes = n ? n : 1;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+enum class Stage : int { Created = 0, Loaded = 1, Filtered = 2, Weighted = 3, Paired = 4 };
+
+struct StageTimer {
+  cudaEvent_t beg = nullptr, end = nullptr;
+  bool valid = false;
+  int launches = 0;
+};
+
+// Pair-stage operand geometry (see DESIGN.md "data layout in HBM").
+struct PairGeom {
+  int n_limbs = 3;       // NL
+  int limb_bits = 8;     // b
+  int rows_per_site = 6; // RPS = 2*NL   rows of the limb operand per kept site
+  int sites_per_group = 21; // SPG = floor(128 / RPS) kept sites per 128-row group of the limb operand
+  int64_t k_padded = 0;  // sequences rounded up to 64
+  int64_t a_rows = 0;    // indicator operand rows, padded to 128 (2 rows per site)
+  int64_t b_groups = 0;  // 128-row groups of the limb operand
+};
+
+}  // namespace wld
+
+struct wld_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  wld::Stage stage = wld::Stage::Created;
+  std::string err;
+
+  // options
+  int part = 0, nparts = 1;
+  int n_limbs_opt = 3;
+  int pair_kernel = WLD_PAIR_KERNEL_UMMA;
+  uint64_t pair_cap_opt = 0;
+
+  // stage 1
+  int64_t n_seqs = 0, n_cols = 0, row_stride = 0;
+  int input_flags = 0;
+  const uint8_t* d_raw = nullptr;  // borrowed or = raw_own.p
+  wld::DevBuf raw_own;
+  int64_t cols_padded = 0;         // n_cols rounded up to 16
+  wld::DevBuf hist;                // u32 [6][cols_padded]
+  wld::DevBuf keep;                // u8  [cols_padded]
+  wld::DevBuf rank;                // i32 [cols_padded]  exclusive prefix of keep
+  wld::DevBuf maj_raw, min_raw;    // i8  [cols_padded]
+  wld::DevBuf site_map;            // i32 [n_kept]
+  wld::DevBuf maj, mnr;            // i8  [n_kept]
+  wld::DevBuf kept_count;          // i32 [1]
+  int64_t n_kept = 0;
+  int64_t ldc = 0;                 // code row pitch: n_seqs rounded up to 128
+  wld::DevBuf codes;               // u8 [n_kept][ldc], site-major, pad = 5
+
+  // stage 2
+  wld::DevBuf table;               // f64 [n_kept][8]  per-site contribution per code (6 used)
+  wld::DevBuf partial;             // f64 [site_chunks][n_seqs]
+  wld::DevBuf w64;                 // f64 [n_seqs]
+  wld::DevBuf w32;                 // f32 [n_seqs]
+  wld::DevBuf scalars;             // f64 [8] scratch (max etc.)
+
+  // stage 3
+  wld::PairGeom geom;
+  wld::DevBuf q;                   // u32 [ldc]      fixed-point weights
+  wld::DevBuf limbs;               // u16 [NL][ldc]  bf16 bit patterns of the limbs
+  wld::DevBuf opA;                 // bf16 [a_rows][k_padded]
+  wld::DevBuf opB;                 // bf16 [b_groups*128][k_padded]
+  wld::DevBuf tiles;               // uint2 [n_tiles]
+  wld::DevBuf pairs;               // wld_pair [pair_cap]
+  wld::DevBuf counters;            // u64 [4]: survivors, pairs_done, ...
+  uint64_t pair_cap = 0;
+  uint64_t n_survivors = 0;
+  uint64_t pairs_computed = 0;
+  wld_pair_info info{};
+  float last_thr = 0.f;
+
+  wld::StageTimer timers[WLD_STAGE_COUNT];
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+};
+
+#define WLD_CUDA(ctx, expr)                                                                      \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      return (ctx)->fail(_e == cudaErrorMemoryAllocation ? WLD_ERR_NOMEM : WLD_ERR_CUDA,         \
+                         "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+namespace wld {
+
+struct ScopedStageTimer {
+  wld_ctx* c;
+  int id;
+  ScopedStageTimer(wld_ctx* ctx, int stage) : c(ctx), id(stage) {
+    StageTimer& t = c->timers[id];
+    if (!t.beg) {
+      cudaEventCreate(&t.beg);
+      cudaEventCreate(&t.end);
+    }
+    t.valid = false;
+    t.launches = 0;
+    cudaEventRecord(t.beg, c->stream);
+  }
+  void launched(int n = 1) { c->timers[id].launches += n; }
+  ~ScopedStageTimer() {
+    StageTimer& t = c->timers[id];
+    cudaEventRecord(t.end, c->stream);
+    t.valid = true;
+  }
+};
+
+// ---- stage launchers (each in its own .cu) ------------------------------------------------------
+int run_histogram(wld_ctx* c, ScopedStageTimer& tm);                       // encode_filter.cu
+int run_filter(wld_ctx* c, bool keep_all, float min_acgt, float min_minor, float max_minor,
+               ScopedStageTimer& tm);                                      // encode_filter.cu
+int run_henikoff(wld_ctx* c, ScopedStageTimer& tm);                        // henikoff.cu
+int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm);                       // pair_prep.cu
+int run_pair_simt(wld_ctx* c, float thr, ScopedStageTimer& tm);            // pair_simt.cu
+int run_pair_umma(wld_ctx* c, float thr, ScopedStageTimer& tm);            // pair_umma.cu
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+}  // namespace wld

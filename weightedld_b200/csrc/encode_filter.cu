@@ -1,0 +1,440 @@
+// encode_filter.cu — stage 1: alphabet encoding, per-site histograms, site filter, and the
+// transposing gather that builds the kept, site-major 0..5 code matrix.
+//
+// Reference semantics restated on the GPU (bit-exact, integer + three f32 operations):
+//   Symbol::from(char)                       lib.rs:53-64
+//   SymbolHistogram::from_slice / acgt       lib.rs:98-109
+//   major_minor_symbols                      lib.rs:126-140
+//   is_site_of_interest + threshold          lib.rs:310-338, main.rs:139
+//   SiteSet::from_multiseq / filter_by       lib.rs:176-206, 230-251
+//
+// All three kernels are HBM-bound byte kernels.  Algorithmic bytes: n_seqs*n_cols read for the
+// histogram; n_seqs*n_cols read + n_seqs*n_kept written for the gather (tiles without a kept
+// column are skipped, so the second read shrinks with the keep ratio).
+#include "common.cuh"
+
+namespace wld {
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// SWAR alphabet: four bytes at a time.  lib.rs:53-64: aA->0 cC->1 gG->2 tT->3 '-'->4 else->5.
+// Lower-casing with |0x20 is only applied for the letter tests ('\r'|0x20 == '-', so '-' is
+// tested on the raw byte).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t encode4_ascii(uint32_t x) {
+  const uint32_t y = x | 0x20202020u;
+  uint32_t code = 0x05050505u;
+  code -= __vcmpeq4(y, 0x61616161u) & 0x05050505u;  // a -> 0
+  code -= __vcmpeq4(y, 0x63636363u) & 0x04040404u;  // c -> 1
+  code -= __vcmpeq4(y, 0x67676767u) & 0x03030303u;  // g -> 2
+  code -= __vcmpeq4(y, 0x74747474u) & 0x02020202u;  // t -> 3
+  code -= __vcmpeq4(x, 0x2d2d2d2du) & 0x01010101u;  // - -> 4
+  return code;
+}
+// Already-encoded input: values above 5 read as 5 (Unknown).
+__device__ __forceinline__ uint32_t encode4_codes(uint32_t x) { return __vminu4(x, 0x05050505u); }
+
+__device__ __forceinline__ uint32_t encode1(uint32_t c, bool ascii) {
+  return (ascii ? encode4_ascii(c) : encode4_codes(c)) & 0xffu;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 1a: per-column histogram, vectorised path (base and pitch 16-byte aligned).
+// A warp owns 512 consecutive columns (16 per lane, one 16-byte load per row); the 8 warps of a
+// block take interleaved rows of the block's row chunk.  Counts live in byte lanes of 32-bit
+// registers (5 symbols x 4 words) and are flushed to a block-shared histogram before any byte
+// lane can exceed 255; one global atomicAdd per (symbol, column) per block follows.
+// ---------------------------------------------------------------------------------------------
+constexpr int kHistThreads = 256;
+constexpr int kHistColsPerBlock = 512;
+
+template <bool kAscii>
+__global__ void __launch_bounds__(kHistThreads) hist_vec16_kernel(const uint8_t* __restrict__ raw,
+                                                                  int64_t n_seqs, int64_t n_cols,
+                                                                  int64_t row_stride, int rows_per_block,
+                                                                  uint32_t* __restrict__ hist,
+                                                                  int64_t cols_padded) {
+  __shared__ uint32_t s_hist[5][kHistColsPerBlock];
+  for (int i = threadIdx.x; i < 5 * kHistColsPerBlock; i += kHistThreads) (&s_hist[0][0])[i] = 0;
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t col0 = (int64_t)blockIdx.x * kHistColsPerBlock + lane * 16;
+  const int64_t row_begin = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t row_end = min(row_begin + rows_per_block, n_seqs);
+  const bool active = col0 < cols_padded;  // cols_padded is a multiple of 16 and <= row_stride
+
+  uint32_t cnt[5][4];
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cnt[k][j] = 0;
+  int since_flush = 0;
+
+  auto flush = [&]() {
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t v = cnt[k][j];
+        if (v) {
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            uint32_t c = (v >> (8 * b)) & 0xffu;
+            if (c) atomicAdd(&s_hist[k][lane * 16 + j * 4 + b], c);
+          }
+        }
+        cnt[k][j] = 0;
+      }
+    since_flush = 0;
+  };
+
+  if (active) {
+    for (int64_t r = row_begin + warp; r < row_end; r += kHistThreads / 32) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(raw + r * row_stride + col0));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (kAscii) {
+          const uint32_t y = w[j] | 0x20202020u;
+          cnt[0][j] += __vcmpeq4(y, 0x61616161u) & 0x01010101u;
+          cnt[1][j] += __vcmpeq4(y, 0x63636363u) & 0x01010101u;
+          cnt[2][j] += __vcmpeq4(y, 0x67676767u) & 0x01010101u;
+          cnt[3][j] += __vcmpeq4(y, 0x74747474u) & 0x01010101u;
+          cnt[4][j] += __vcmpeq4(w[j], 0x2d2d2d2du) & 0x01010101u;
+        } else {
+          cnt[0][j] += __vcmpeq4(w[j], 0x00000000u) & 0x01010101u;
+          cnt[1][j] += __vcmpeq4(w[j], 0x01010101u) & 0x01010101u;
+          cnt[2][j] += __vcmpeq4(w[j], 0x02020202u) & 0x01010101u;
+          cnt[3][j] += __vcmpeq4(w[j], 0x03030303u) & 0x01010101u;
+          cnt[4][j] += __vcmpeq4(w[j], 0x04040404u) & 0x01010101u;
+        }
+      }
+      if (++since_flush == 255) flush();
+    }
+    flush();
+  }
+  __syncthreads();
+  const int64_t cb = (int64_t)blockIdx.x * kHistColsPerBlock;
+  for (int i = threadIdx.x; i < 5 * kHistColsPerBlock; i += kHistThreads) {
+    const int k = i / kHistColsPerBlock, c = i % kHistColsPerBlock;
+    const uint32_t v = s_hist[k][c];
+    if (v && cb + c < cols_padded) atomicAdd(&hist[(int64_t)k * cols_padded + cb + c], v);
+  }
+}
+
+// Kernel 1a', generic path for unaligned input: one column per thread, byte loads.
+__global__ void __launch_bounds__(256) hist_generic_kernel(const uint8_t* __restrict__ raw, int64_t n_seqs,
+                                                           int64_t n_cols, int64_t row_stride,
+                                                           int rows_per_block, bool ascii,
+                                                           uint32_t* __restrict__ hist, int64_t cols_padded) {
+  const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= n_cols) return;
+  const int64_t row_begin = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t row_end = min(row_begin + rows_per_block, n_seqs);
+  uint32_t h[5] = {0, 0, 0, 0, 0};
+  for (int64_t r = row_begin; r < row_end; ++r) {
+    const uint32_t c = encode1(raw[r * row_stride + col], ascii);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) h[k] += (c == (uint32_t)k);
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+    if (h[k]) atomicAdd(&hist[(int64_t)k * cols_padded + col], h[k]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 1b: per-site decision.  Completes bin 5 (Unknown = n_seqs - sum of the others), runs the
+// major/minor scan of lib.rs:126-140 and the filter of lib.rs:310-338.
+// ---------------------------------------------------------------------------------------------
+__global__ void decide_kernel(uint32_t* __restrict__ hist, int64_t cols_padded, int64_t n_cols,
+                              int64_t n_seqs, bool keep_all, unsigned long long min_acgt, float min_minor,
+                              float max_minor, uint8_t* __restrict__ keep, int8_t* __restrict__ maj_raw,
+                              int8_t* __restrict__ min_raw) {
+  const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= cols_padded) return;
+  if (col >= n_cols) {
+    keep[col] = 0;
+    maj_raw[col] = -1;
+    min_raw[col] = -1;
+    return;
+  }
+  uint32_t h[5];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    h[k] = hist[(int64_t)k * cols_padded + col];
+    sum += h[k];
+  }
+  hist[5 * cols_padded + col] = (uint32_t)n_seqs - sum;
+
+  int maj = -1, mnr = -1;  // lib.rs:126-140
+#pragma unroll
+  for (int sym = 0; sym < 5; ++sym) {
+    const uint32_t majc = maj >= 0 ? h[maj] : 0u;
+    const uint32_t minc = mnr >= 0 ? h[mnr] : 0u;
+    if (h[sym] > majc) {
+      mnr = maj;
+      maj = sym;
+    } else if (h[sym] > minc) {
+      mnr = sym;
+    }
+  }
+  maj_raw[col] = (int8_t)maj;
+  min_raw[col] = (int8_t)mnr;
+
+  bool k = true;
+  if (!keep_all) {
+    const unsigned long long acgt = (unsigned long long)h[0] + h[1] + h[2] + h[3];  // lib.rs:106-109
+    if (acgt <= min_acgt) {                                                        // lib.rs:315
+      k = false;
+    } else if (maj < 0 || mnr < 0) {                                               // lib.rs:319-322
+      k = false;
+    } else {
+      const float maj_count = (float)h[maj];                                       // lib.rs:324
+      const float min_count = (float)h[mnr];                                       // lib.rs:325
+      const float minor_frac = __fdiv_rn(min_count, __fadd_rn(min_count, maj_count));  // lib.rs:328
+      if (minor_frac < min_minor || minor_frac > max_minor) k = false;             // lib.rs:331
+    }
+  }
+  keep[col] = k ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 1c: ordered compaction of the keep flags (single block; L_raw is at most a few million).
+// rank[col] = number of kept columns before col (rank[cols_padded] = total), site_map, and the
+// kept sites' major/minor symbols.
+// ---------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads) scan_kernel(const uint8_t* __restrict__ keep,
+                                                            int64_t cols_padded, int32_t* __restrict__ rank,
+                                                            int32_t* __restrict__ kept_count) {
+  __shared__ int32_t s_warp[kScanThreads / 32];
+  __shared__ int32_t s_base;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t base = 0; base < cols_padded; base += kScanThreads) {
+    const int64_t col = base + threadIdx.x;
+    const int flag = col < cols_padded ? keep[col] : 0;
+    int incl = flag;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int v = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+      }
+      s_warp[lane] = v;  // inclusive over warps
+    }
+    __syncthreads();
+    const int warp_off = warp ? s_warp[warp - 1] : 0;
+    const int excl = s_base + warp_off + incl - flag;
+    if (col < cols_padded) rank[col] = excl;
+    __syncthreads();
+    if (threadIdx.x == 0) s_base += s_warp[kScanThreads / 32 - 1];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    rank[cols_padded] = s_base;
+    *kept_count = s_base;
+  }
+}
+
+__global__ void site_map_kernel(const uint8_t* __restrict__ keep, const int32_t* __restrict__ rank,
+                                const int8_t* __restrict__ maj_raw, const int8_t* __restrict__ min_raw,
+                                int64_t n_cols, int32_t* __restrict__ site_map, int8_t* __restrict__ maj,
+                                int8_t* __restrict__ mnr) {
+  const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= n_cols || !keep[col]) return;
+  const int32_t k = rank[col];
+  site_map[k] = (int32_t)col;
+  maj[k] = maj_raw[col];
+  mnr[k] = min_raw[col];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 1d: encode + transpose + gather of the kept columns.
+// Tile = 128 sequences x 128 raw columns.  Global reads are 4-byte words arranged so that a warp
+// request covers four 32-byte sectors (8 lanes x 4 columns, 4 row groups); a 4x4 byte block is
+// transposed in registers with PRMT and stored conflict-free into a [128 cols][33 words] tile;
+// kept columns are then written as 128-byte rows of the site-major code matrix.  Rows beyond
+// n_seqs are padded with 5 (Unknown) so the pair operands see zeros there.
+// ---------------------------------------------------------------------------------------------
+constexpr int kGatherThreads = 256;
+
+template <bool kAscii, bool kAligned4>
+__global__ void __launch_bounds__(kGatherThreads) gather_kernel(const uint8_t* __restrict__ raw, int64_t n_seqs,
+                                                                int64_t n_cols, int64_t row_stride,
+                                                                const uint8_t* __restrict__ keep,
+                                                                const int32_t* __restrict__ rank,
+                                                                uint8_t* __restrict__ codes, int64_t ldc) {
+  __shared__ uint32_t tile[128][33];
+  const int64_t col_tile = (int64_t)blockIdx.x * 128;
+  const int64_t seq_tile = (int64_t)blockIdx.y * 128;
+  const int64_t col_hi = min(col_tile + 128, n_cols);
+  // rank is an exclusive prefix, rank[x] for x in [0, cols_padded]; cols_padded >= n_cols.
+  if (rank[col_hi] == rank[col_tile]) return;  // nothing kept in this column tile
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cs = warp & 3, rh = warp >> 2;
+  const int c8 = lane & 7, g = lane >> 3;
+  const int64_t col = col_tile + 32 * cs + 4 * c8;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int s_local = 64 * rh + 16 * t + 4 * g;
+    uint32_t r[4];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int64_t seq = seq_tile + s_local + rr;
+      uint32_t w = 0x05050505u;  // pad rows: Unknown
+      if (seq < n_seqs) {
+        const uint8_t* p = raw + seq * row_stride + col;
+        uint32_t x;
+        if (kAligned4 && col + 3 < row_stride) {
+          // bytes between n_cols and the pitch are junk, but those columns are never kept
+          x = __ldg(reinterpret_cast<const uint32_t*>(p));
+        } else {
+          x = 0;
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            if (col + b < n_cols) x |= (uint32_t)p[b] << (8 * b);
+        }
+        w = kAscii ? encode4_ascii(x) : encode4_codes(x);
+      }
+      r[rr] = w;
+    }
+    const uint32_t t0 = __byte_perm(r[0], r[1], 0x5140), t1 = __byte_perm(r[0], r[1], 0x7362);
+    const uint32_t t2 = __byte_perm(r[2], r[3], 0x5140), t3 = __byte_perm(r[2], r[3], 0x7362);
+    const int word = s_local >> 2;
+    const int cl = 32 * cs + 4 * c8;
+    tile[cl + 0][word] = __byte_perm(t0, t2, 0x5410);
+    tile[cl + 1][word] = __byte_perm(t0, t2, 0x7632);
+    tile[cl + 2][word] = __byte_perm(t1, t3, 0x5410);
+    tile[cl + 3][word] = __byte_perm(t1, t3, 0x7632);
+  }
+  __syncthreads();
+  for (int cl = warp; cl < 128; cl += kGatherThreads / 32) {
+    const int64_t c = col_tile + cl;
+    if (c < n_cols && keep[c]) {
+      const int64_t k = rank[c];
+      *reinterpret_cast<uint32_t*>(codes + k * ldc + seq_tile + 4 * lane) = tile[cl][lane];
+    }
+  }
+}
+
+}  // namespace
+
+// =============================================================================================
+// host launchers
+// =============================================================================================
+int run_histogram(wld_ctx* c, ScopedStageTimer& tm) {
+  const bool ascii = !(c->input_flags & WLD_INPUT_CODES);
+  c->cols_padded = round_up(c->n_cols, 16);
+  WLD_CUDA(c, c->hist.ensure(sizeof(uint32_t) * 6 * (size_t)c->cols_padded));
+  WLD_CUDA(c, cudaMemsetAsync(c->hist.p, 0, sizeof(uint32_t) * 6 * (size_t)c->cols_padded, c->stream));
+  if (c->n_seqs == 0 || c->n_cols == 0) return WLD_OK;
+
+  const bool vec16 = (reinterpret_cast<uintptr_t>(c->d_raw) % 16 == 0) && (c->row_stride % 16 == 0) &&
+                     (c->cols_padded <= c->row_stride);
+  // Row chunk per block: enough blocks for several waves, at most 2040 rows (8 warps x 255).
+  const int64_t col_blocks = vec16 ? (c->cols_padded + kHistColsPerBlock - 1) / kHistColsPerBlock
+                                   : (c->n_cols + 255) / 256;
+  int64_t want_blocks = (int64_t)c->sm_count * 16;
+  int64_t row_chunks = (want_blocks + col_blocks - 1) / col_blocks;
+  int64_t rows_per_block = (c->n_seqs + row_chunks - 1) / row_chunks;
+  rows_per_block = std::max<int64_t>(64, std::min<int64_t>(rows_per_block, 2040));
+  rows_per_block = round_up(rows_per_block, 8);
+  row_chunks = (c->n_seqs + rows_per_block - 1) / rows_per_block;
+  if (row_chunks > 65535) {
+    rows_per_block = round_up((c->n_seqs + 65534) / 65535, 8);
+    row_chunks = (c->n_seqs + rows_per_block - 1) / rows_per_block;
+  }
+  dim3 grid((unsigned)col_blocks, (unsigned)row_chunks);
+  if (vec16) {
+    if (ascii)
+      hist_vec16_kernel<true><<<grid, kHistThreads, 0, c->stream>>>(c->d_raw, c->n_seqs, c->n_cols, c->row_stride,
+                                                                   (int)rows_per_block, c->hist.as<uint32_t>(),
+                                                                   c->cols_padded);
+    else
+      hist_vec16_kernel<false><<<grid, kHistThreads, 0, c->stream>>>(c->d_raw, c->n_seqs, c->n_cols, c->row_stride,
+                                                                    (int)rows_per_block, c->hist.as<uint32_t>(),
+                                                                    c->cols_padded);
+  } else {
+    hist_generic_kernel<<<grid, 256, 0, c->stream>>>(c->d_raw, c->n_seqs, c->n_cols, c->row_stride,
+                                                     (int)rows_per_block, ascii, c->hist.as<uint32_t>(),
+                                                     c->cols_padded);
+  }
+  tm.launched();
+  WLD_CUDA(c, cudaGetLastError());
+  return WLD_OK;
+}
+
+int run_filter(wld_ctx* c, bool keep_all, float min_acgt, float min_minor, float max_minor,
+               ScopedStageTimer& tm) {
+  const bool ascii = !(c->input_flags & WLD_INPUT_CODES);
+  const int64_t cp = c->cols_padded;
+  WLD_CUDA(c, c->keep.ensure((size_t)cp + 16));
+  WLD_CUDA(c, c->rank.ensure(sizeof(int32_t) * ((size_t)cp + 1)));
+  WLD_CUDA(c, c->maj_raw.ensure((size_t)cp + 16));
+  WLD_CUDA(c, c->min_raw.ensure((size_t)cp + 16));
+  WLD_CUDA(c, c->kept_count.ensure(sizeof(int32_t)));
+
+  // main.rs:139: (min_acgt * n_seqs as f32).ceil() as usize  (f32 arithmetic; `as` saturates)
+  unsigned long long min_count = 0;
+  {
+    const float v = ceilf(min_acgt * (float)c->n_seqs);
+    if (v > 0.0f) min_count = v >= 18446744073709551616.0f ? ~0ull : (unsigned long long)v;
+  }
+  if (cp > 0) {
+    decide_kernel<<<(unsigned)((cp + 255) / 256), 256, 0, c->stream>>>(
+        c->hist.as<uint32_t>(), cp, c->n_cols, c->n_seqs, keep_all, min_count, min_minor, max_minor,
+        c->keep.as<uint8_t>(), c->maj_raw.as<int8_t>(), c->min_raw.as<int8_t>());
+    tm.launched();
+  }
+  scan_kernel<<<1, kScanThreads, 0, c->stream>>>(c->keep.as<uint8_t>(), cp, c->rank.as<int32_t>(),
+                                                 c->kept_count.as<int32_t>());
+  tm.launched();
+  WLD_CUDA(c, cudaGetLastError());
+  int32_t kept = 0;
+  WLD_CUDA(c, cudaMemcpyAsync(&kept, c->kept_count.p, sizeof kept, cudaMemcpyDeviceToHost, c->stream));
+  WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->n_kept = kept;
+  c->ldc = round_up(std::max<int64_t>(c->n_seqs, 1), 128);
+
+  WLD_CUDA(c, c->site_map.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(kept, 1)));
+  WLD_CUDA(c, c->maj.ensure((size_t)std::max<int64_t>(kept, 1)));
+  WLD_CUDA(c, c->mnr.ensure((size_t)std::max<int64_t>(kept, 1)));
+  WLD_CUDA(c, c->codes.ensure((size_t)std::max<int64_t>(kept, 1) * (size_t)c->ldc));
+  if (kept == 0 || c->n_seqs == 0) return WLD_OK;
+
+  site_map_kernel<<<(unsigned)((c->n_cols + 255) / 256), 256, 0, c->stream>>>(
+      c->keep.as<uint8_t>(), c->rank.as<int32_t>(), c->maj_raw.as<int8_t>(), c->min_raw.as<int8_t>(), c->n_cols,
+      c->site_map.as<int32_t>(), c->maj.as<int8_t>(), c->mnr.as<int8_t>());
+  tm.launched();
+
+  const bool aligned4 = (reinterpret_cast<uintptr_t>(c->d_raw) % 4 == 0) && (c->row_stride % 4 == 0);
+  dim3 grid((unsigned)((c->n_cols + 127) / 128), (unsigned)(c->ldc / 128));
+  if (grid.y > 65535) return c->fail(WLD_ERR_UNSUPPORTED, "n_seqs %lld too large for the gather grid", (long long)c->n_seqs);
+#define WLD_LAUNCH_GATHER(A, B)                                                                              \
+  gather_kernel<A, B><<<grid, kGatherThreads, 0, c->stream>>>(c->d_raw, c->n_seqs, c->n_cols, c->row_stride, \
+                                                             c->keep.as<uint8_t>(), c->rank.as<int32_t>(),   \
+                                                             c->codes.as<uint8_t>(), c->ldc)
+  if (ascii && aligned4) WLD_LAUNCH_GATHER(true, true);
+  else if (ascii) WLD_LAUNCH_GATHER(true, false);
+  else if (aligned4) WLD_LAUNCH_GATHER(false, true);
+  else WLD_LAUNCH_GATHER(false, false);
+#undef WLD_LAUNCH_GATHER
+  tm.launched();
+  WLD_CUDA(c, cudaGetLastError());
+  return WLD_OK;
+}
+
+}  // namespace wld

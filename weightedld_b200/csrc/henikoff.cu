@@ -1,0 +1,145 @@
+// henikoff.cu — stage 2: Henikoff position-based sequence weights over the kept sites.
+//
+// Reference: henikoff_site_contributions lib.rs:360-380, henikoff_weights lib.rs:340-358.
+//   per site:  k = #{x in A,C,G,T,-: count>0}            lib.rs:363 (116-124)
+//              code<=4 -> 1/(k*count[code])              lib.rs:366-370
+//              code 5  -> (sum of the above over the known sequences)/k   lib.rs:373-378
+//   per sequence: sum over sites, then divide by the maximum  lib.rs:354-355
+//
+// The reference materialises an L x N f32 matrix (lib.rs:341); here the per-site contribution is
+// a 6-entry table and the per-sequence sum is a segmented reduction over the site-major code
+// matrix: column-histogram pass (already done in stage 1) + per-sequence gather-sum.
+// Accumulation is f64 in a fixed order (site chunks of 256 in ascending order, then chunk
+// partials in ascending order), so results are deterministic; tolerance vs the f64 oracle 1e-9.
+// HBM-bound: reads n_kept*ldc code bytes once, writes 4*n_seqs (+ chunk partials).
+#include "common.cuh"
+
+namespace wld {
+namespace {
+
+constexpr int kSiteChunk = 256;
+constexpr int kAccThreads = 256;
+
+__global__ void table_kernel(const uint32_t* __restrict__ hist, int64_t cols_padded,
+                             const int32_t* __restrict__ site_map, int64_t n_kept, double* __restrict__ table) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_kept) return;
+  const int64_t col = site_map[k];
+  uint32_t n[5];
+  int distinct = 0;
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    n[c] = hist[(int64_t)c * cols_padded + col];
+    distinct += n[c] > 0;  // lib.rs:116-124
+  }
+  const double kd = (double)distinct;
+  double total = 0.0;  // lib.rs:364-371: sum of the contributions of the known sequences
+  double t[8];
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    t[c] = n[c] > 0 ? __ddiv_rn(1.0, __dmul_rn(kd, (double)n[c])) : 0.0;  // lib.rs:368
+    if (n[c] > 0) total = __dadd_rn(total, __dmul_rn((double)n[c], t[c]));
+  }
+  t[5] = __ddiv_rn(total, kd);  // lib.rs:373 (0/0 = NaN when the site has no known symbol)
+  t[6] = 0.0;
+  t[7] = 0.0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) table[k * 8 + c] = t[c];
+}
+
+// grid (seq blocks of 1024, site chunks of 256); each thread owns four consecutive sequences.
+__global__ void __launch_bounds__(kAccThreads) accumulate_kernel(const uint8_t* __restrict__ codes, int64_t ldc,
+                                                                 int64_t n_kept, int64_t n_seqs,
+                                                                 const double* __restrict__ table,
+                                                                 double* __restrict__ partial) {
+  __shared__ double s_tab[kSiteChunk][8];
+  const int64_t k0 = (int64_t)blockIdx.y * kSiteChunk;
+  const int nk = (int)min((int64_t)kSiteChunk, n_kept - k0);
+  for (int i = threadIdx.x; i < nk * 8; i += kAccThreads) (&s_tab[0][0])[i] = table[k0 * 8 + i];
+  __syncthreads();
+  const int64_t s0 = ((int64_t)blockIdx.x * kAccThreads + threadIdx.x) * 4;
+  if (s0 >= ldc) return;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  const uint8_t* p = codes + k0 * ldc + s0;
+  int k = 0;
+  for (; k + 4 <= nk; k += 4) {
+    uint32_t w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) w[u] = __ldg(reinterpret_cast<const uint32_t*>(p + (int64_t)(k + u) * ldc));
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[b] = __dadd_rn(acc[b], s_tab[k + u][(w[u] >> (8 * b)) & 7u]);
+  }
+  for (; k < nk; ++k) {
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p + (int64_t)k * ldc));
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[b] = __dadd_rn(acc[b], s_tab[k][(w >> (8 * b)) & 7u]);
+  }
+#pragma unroll
+  for (int b = 0; b < 4; ++b)
+    if (s0 + b < n_seqs) partial[(int64_t)blockIdx.y * n_seqs + s0 + b] = acc[b];
+}
+
+// Sum chunk partials in ascending chunk order; track the maximum (NaN ignored like f32::max).
+__global__ void reduce_kernel(const double* __restrict__ partial, int64_t n_chunks, int64_t n_seqs,
+                              double* __restrict__ w64, unsigned long long* __restrict__ max_bits) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  if (s < n_seqs) {
+    for (int64_t ch = 0; ch < n_chunks; ++ch) v = __dadd_rn(v, partial[ch * n_seqs + s]);
+    w64[s] = v;
+  }
+  // lib.rs:355 fold(0.0, max): sums are >= 0 or NaN; for non-negative doubles the bit pattern is
+  // monotone, so an integer atomicMax implements it.
+  unsigned long long bits = (s < n_seqs && v == v && v > 0.0) ? (unsigned long long)__double_as_longlong(v) : 0ull;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, o));
+  if ((threadIdx.x & 31) == 0 && bits) atomicMax(max_bits, bits);
+}
+
+__global__ void normalize_kernel(double* __restrict__ w64, float* __restrict__ w32, int64_t n_seqs,
+                                 const unsigned long long* __restrict__ max_bits) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_seqs) return;
+  const double mx = __longlong_as_double((long long)*max_bits);
+  const double v = __ddiv_rn(w64[s], mx);  // lib.rs:355
+  w64[s] = v;
+  w32[s] = (float)v;  // the reference's weight type is f32 (lib.rs:340)
+}
+
+}  // namespace
+
+int run_henikoff(wld_ctx* c, ScopedStageTimer& tm) {
+  const int64_t n = c->n_seqs, L = c->n_kept;
+  WLD_CUDA(c, c->w64.ensure(sizeof(double) * (size_t)std::max<int64_t>(n, 1)));
+  WLD_CUDA(c, c->w32.ensure(sizeof(float) * (size_t)std::max<int64_t>(n, 1)));
+  WLD_CUDA(c, c->scalars.ensure(sizeof(double) * 8));
+  WLD_CUDA(c, cudaMemsetAsync(c->scalars.p, 0, sizeof(double) * 8, c->stream));
+  if (n == 0) return WLD_OK;
+  const int64_t n_chunks = (L + kSiteChunk - 1) / kSiteChunk;
+  WLD_CUDA(c, c->table.ensure(sizeof(double) * 8 * (size_t)std::max<int64_t>(L, 1)));
+  WLD_CUDA(c, c->partial.ensure(sizeof(double) * (size_t)std::max<int64_t>(n_chunks, 1) * (size_t)n));
+  if (L > 0) {
+    table_kernel<<<(unsigned)((L + 255) / 256), 256, 0, c->stream>>>(c->hist.as<uint32_t>(), c->cols_padded,
+                                                                    c->site_map.as<int32_t>(), L,
+                                                                    c->table.as<double>());
+    tm.launched();
+    dim3 grid((unsigned)((c->ldc / 4 + kAccThreads - 1) / kAccThreads), (unsigned)n_chunks);
+    if (grid.y > 65535) return c->fail(WLD_ERR_UNSUPPORTED, "too many kept sites for the Henikoff grid");
+    accumulate_kernel<<<grid, kAccThreads, 0, c->stream>>>(c->codes.as<uint8_t>(), c->ldc, L, n,
+                                                           c->table.as<double>(), c->partial.as<double>());
+    tm.launched();
+  }
+  reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->partial.as<double>(), n_chunks, n,
+                                                                   c->w64.as<double>(),
+                                                                   c->scalars.as<unsigned long long>());
+  tm.launched();
+  normalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->w64.as<double>(), c->w32.as<float>(), n,
+                                                                      c->scalars.as<unsigned long long>());
+  tm.launched();
+  WLD_CUDA(c, cudaGetLastError());
+  return WLD_OK;
+}
+
+}  // namespace wld

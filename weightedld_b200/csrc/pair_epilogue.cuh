@@ -1,0 +1,123 @@
+// pair_epilogue.cuh — fused epilogue of the pair stage, shared by the tcgen05 and the SIMT kernel.
+//
+// Input: the four EXACT weighted haplotype sums of one site pair (integers held in f64):
+//   AB = sum w [a=maj_a][b=maj_b]   (ld_obs[3], lib.rs:477-479)
+//   Ab = sum w [a=maj_a][b=min_b]   (ld_obs[2])
+//   aB = sum w [a=min_a][b=maj_b]   (ld_obs[1])
+//   ab = sum w [a=min_a][b=min_b]   (ld_obs[0])
+// over sequences that are major-or-minor at both sites (lib.rs:462-467).
+//
+// Output: D, D', r2 by lib.rs:482-518 evaluated operation for operation in f64 (no FMA
+// contraction: explicit _rn intrinsics), rounded to f32 (the reference's LdStats type,
+// lib.rs:382-387), then the reference's filter `r2 > threshold` in f32 (lib.rs:660).
+//
+// Because the sums are exact and scaling by 2^bits is exact, the result is bit-identical to the
+// f64 restatement of lib.rs:455-521 run on the same fixed-point weights — that is what the parity
+// tests assert (tests/test_gpu_parity.py).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/wld.h"
+
+namespace wld {
+
+struct PairOut {
+  wld_pair* pairs;              // survivor buffer
+  unsigned long long* count;    // survivors so far (may exceed cap: overflow protocol)
+  unsigned long long cap;
+};
+
+// Division-free conservative pre-filter.  r2 = d^2/(PA Pa PB Pb) with d = PA*PB - AB/T, so in raw
+// sums r2 = (A*B - AB*T)^2 / (A (T-A) B (T-B)).  A pair can only pass `(float)r2 > thr` if
+// num >= thr_lo * den with thr_lo = thr - |thr|*1e-6 - 1e-24 (slack >> f64/f32 rounding of the
+// exact path).  den == 0 (a marginal is empty, or no common valid sequence) is NaN in the
+// reference (d is exactly 0 there, 0/0) and is dropped by lib.rs:660.
+__device__ __forceinline__ bool ld_prefilter(double AB, double Ab, double aB, double ab, double thr_lo) {
+  const double A = AB + Ab;
+  const double B = AB + aB;
+  const double T = A + (aB + ab);
+  const double a = T - A;
+  const double b = T - B;
+  double num = A * B - AB * T;
+  num = num * num;
+  const double den = (A * a) * (B * b);
+  return den > 0.0 && num >= thr_lo * den;
+}
+
+__host__ __device__ inline double ld_thr_lo(float thr) {
+  const double t = (double)thr;
+  return t - (t < 0 ? -t : t) * 1e-6 - 1e-24;
+}
+
+// lib.rs:482-518 in f64.  Returns true when the pair survives `r2 > thr` (f32 compare).
+__device__ __forceinline__ bool ld_stats_exact(double AB, double Ab, double aB, double ab, float thr, float& d_out,
+                                               float& dprime_out, float& r2_out) {
+  // total_weight, PA, PB, ld_obs[3] as the reference accumulates them (lib.rs:469-479); exact here.
+  const double total = __dadd_rn(__dadd_rn(AB, Ab), __dadd_rn(aB, ab));
+  double PA = __dadd_rn(AB, Ab);
+  double PB = __dadd_rn(AB, aB);
+  double o3 = AB;
+  double Pa = __dsub_rn(total, PA);  // lib.rs:482
+  double Pb = __dsub_rn(total, PB);  // lib.rs:483
+  double o2 = __dsub_rn(PA, o3);     // lib.rs:484
+  double o1 = __dsub_rn(PB, o3);     // lib.rs:485
+  double o0 = __dsub_rn(Pa, o1);     // lib.rs:486
+  PA = __ddiv_rn(PA, total);         // lib.rs:488-495
+  PB = __ddiv_rn(PB, total);
+  Pa = __ddiv_rn(Pa, total);
+  Pb = __ddiv_rn(Pb, total);
+  o0 = __ddiv_rn(o0, total);
+  o1 = __ddiv_rn(o1, total);
+  o2 = __ddiv_rn(o2, total);
+  o3 = __ddiv_rn(o3, total);
+  const double PAB = __dmul_rn(PA, PB);  // lib.rs:497-500
+  const double PAb = __dmul_rn(PA, Pb);
+  const double PaB = __dmul_rn(Pa, PB);
+  const double Pab = __dmul_rn(Pa, Pb);
+  const double d = __ddiv_rn(
+      __dadd_rn(__dadd_rn(__dadd_rn(__dsub_rn(PAB, o3), __dsub_rn(Pab, o0)), __dsub_rn(o2, PAb)), __dsub_rn(o1, PaB)),
+      4.0);  // lib.rs:502
+  double den;  // lib.rs:504-515
+  if (d < 0.0) {
+    den = fmax(-o0, -o3);
+    if (den == 0.0) den = fmin(-o0, -o3);
+  } else {
+    den = fmin(o1, o2);
+    if (den == 0.0) den = fmax(o1, o2);
+  }
+  const double dprime = __ddiv_rn(d, den);  // lib.rs:516
+  const double r2 =
+      __ddiv_rn(__dmul_rn(d, d), __dmul_rn(__dmul_rn(__dmul_rn(PA, Pa), PB), Pb));  // lib.rs:518
+  d_out = (float)d;
+  dprime_out = (float)dprime;
+  r2_out = (float)r2;
+  return r2_out > thr;  // lib.rs:660 (NaN fails)
+}
+
+// Warp-aggregated compaction: one atomicAdd per warp, survivors written to consecutive slots.
+// Must be called by all 32 lanes of a converged warp.
+__device__ __forceinline__ void emit_pairs_warp(bool keep, uint32_t site_a, uint32_t site_b, float d, float dprime,
+                                                float r2, const PairOut& out) {
+  const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+  if (ballot == 0) return;
+  const int lane = threadIdx.x & 31;
+  unsigned long long base = 0;
+  if (lane == __ffs(ballot) - 1) base = atomicAdd(out.count, (unsigned long long)__popc(ballot));
+  base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
+  if (keep) {
+    const unsigned long long slot = base + __popc(ballot & ((1u << lane) - 1u));
+    if (slot < out.cap) {
+      wld_pair p;
+      p.site_a = site_a;
+      p.site_b = site_b;
+      p.d = d;
+      p.d_prime = dprime;
+      p.r2 = r2;
+      out.pairs[slot] = p;
+    }
+  }
+}
+
+}  // namespace wld

@@ -1,0 +1,480 @@
+// pair_umma.cu — stage 3b: all-pairs weighted LD as a dense Gram on the 5th-generation tensor
+// cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA), with the D / D' / r2 /
+// threshold / compaction epilogue fused behind it.  sm_100a only.
+//
+// Reference: all_weighted_ld_pairs lib.rs:578-684 (tile fan-out, b>a, r2 > thr) and
+// single_weighted_ld_pair lib.rs:390-521 (the four weighted sums + statistics).
+//
+// Math.  opA rows (2i+alpha) are the 0/1 indicators of site i's major (alpha=0) / minor (alpha=1)
+// symbol, opB rows (site j, beta, limb l) are indicator_beta(j) * limb_l(weight); see
+// pair_prep.cu.  One output tile is
+//     D[128 x 256] = opA[mi*128 .. +128, :] * opB[nj*256 .. +256, :]^T        (K = sequences)
+// i.e. 64 sites i  x  2*SPG sites j.  D[(i,alpha)][(j,beta,l)] is an exact integer in fp32; the
+// epilogue recombines limbs in f64:  S = sum_l D_l * 2^(b*(NL-1-l))  and gets
+//     AB = S[i,0][j,0]  Ab = S[i,0][j,1]  aB = S[i,1][j,0]  ab = S[i,1][j,1].
+//
+// Kernel shape (persistent, one CTA per SM, 384 threads, 1 CTA/SM because TMEM is fully used):
+//   warp 0      TMA producer: 4-stage ring of {A 128x64, B 256x64} bf16 tiles (48 KB/stage),
+//               128B-swizzled, completion on `full[stage]` mbarriers
+//   warp 1      MMA issuer: one lane issues 4 x tcgen05.mma (M128 N256 K16) per stage into one of
+//               two 256-column TMEM accumulators; tcgen05.commit frees the stage / publishes the tile
+//   warp 2      TMEM allocator (512 columns)
+//   warps 4-11  epilogue: warp w reads TMEM lanes 32*(w%4).. (tcgen05.ld 32x32b) and the column
+//               half (w-4)/4 (= one 128-row group of opB); adjacent lanes (alpha=0/1 of a site)
+//               swap halves of the 2x2 table by shuffle; division-free pre-filter; exact f64
+//               statistics only for candidates; warp-aggregated atomic compaction.
+//   The accumulator is double-buffered, so the epilogue of tile t overlaps the MMAs of tile t+1.
+//
+// Roofline: tensor pipe.  Algorithmic flop per site pair per launch = 8*N*NL (4 weighted dot
+// products of length N per limb); executed = 2*128*256*Kp per tile.
+#include "common.cuh"
+#include "pair_epilogue.cuh"
+
+namespace wld {
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockN = 256;
+constexpr int kBlockK = 64;  // bf16 elements = 128 bytes = one swizzle atom
+constexpr int kUmmaK = 16;
+constexpr int kStages = 4;
+constexpr int kAStageBytes = kBlockM * kBlockK * 2;  // 16 KB
+constexpr int kBStageBytes = kBlockN * kBlockK * 2;  // 32 KB
+constexpr int kStageBytes = kAStageBytes + kBStageBytes;
+constexpr int kNumThreads = 384;
+constexpr int kEpiWarp0 = 4;
+constexpr int kNumEpiWarps = 8;
+constexpr int kTmemCols = 512;
+constexpr int kSmemBytes = 1024 /*alignment slack*/ + kStages * kStageBytes + 256 /*barriers*/;
+
+struct UmmaParams {
+  const uint2* tiles;
+  int n_tiles;
+  int k_blocks;
+  int n_kept;
+  int limb_bits;
+  float thr;
+  double thr_lo;
+  PairOut out;
+  unsigned long long* pairs_done;
+  int* error_flag;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as an error, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 20000000000ll) {  // ~10 s at 2 GHz
+      if (error_flag) atomicExch(error_flag, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle (canonical layout
+// ((8,n),2):((8,SBO),1) in 16-byte units): start address, LBO = 1 (ignored for swizzled K-major),
+// SBO = 1024 B between 8-row groups, descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor, kind::f16: D=F32 (bits 4-5 = 1), A=B=BF16 (bits 7-9, 10-12 = 1), both
+// K-major (bits 15, 16 = 0), N>>3 at bits 17-22, M>>4 at bits 24-28.
+constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBlockN >> 3) << 17) |
+                                ((uint32_t)(kBlockM >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* v) {
+  static_assert(N == 2 || N == 4 || N == 6 || N == 8 || N == 12 || N == 16, "unsupported column count");
+  if constexpr (N == 2) {
+    tmem_ld2(taddr, v);
+  } else if constexpr (N == 4) {
+    tmem_ld4(taddr, v);
+  } else if constexpr (N == 6) {
+    tmem_ld4(taddr, v);
+    tmem_ld2(taddr + 4, v + 4);
+  } else if constexpr (N == 8) {
+    tmem_ld8(taddr, v);
+  } else if constexpr (N == 12) {
+    tmem_ld8(taddr, v);
+    tmem_ld4(taddr + 8, v + 8);
+  } else {
+    tmem_ld8(taddr, v);
+    tmem_ld8(taddr + 8, v + 8);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <int NL>
+__global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                   const __grid_constant__ CUtensorMap tmB,
+                                                                   const UmmaParams p) {
+  constexpr int RPS = 2 * NL;      // opB rows per site
+  constexpr int SPG = 128 / RPS;   // sites per 128-row group
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sA = smem_u32(smem);
+  const uint32_t sB = sA + kStages * kAStageBytes;
+  const uint32_t bars = sB + kStages * kBStageBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+  auto tfull_bar = [&](int b) { return bars + 8u * (2 * kStages + b); };
+  auto tempty_bar = [&](int b) { return bars + 8u * (2 * kStages + 2 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kStages * kStageBytes + 8 * (2 * kStages + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), kNumEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const uint2 tile = p.tiles[t];
+        const int m_row = (int)tile.x * kBlockM, n_row = (int)tile.y * kBlockN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, p.error_flag, 1);
+          mbar_expect_tx(full_bar(stage), kStageBytes);
+          tma_load_2d(sA + stage * kAStageBytes, &tmA, kb * kBlockK, m_row, full_bar(stage));
+          tma_load_2d(sB + stage * kBStageBytes, &tmB, kb * kBlockK, n_row, full_bar(stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t tcount = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++tcount) {
+        const uint32_t buf = tcount & 1u, bphase = (tcount >> 1) & 1u;
+        mbar_wait(tempty_bar(buf), bphase ^ 1u, p.error_flag, 2);  // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * kBlockN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase, p.error_flag, 3);  // TMA bytes landed
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(sA + stage * kAStageBytes);
+          const uint64_t bdesc = make_smem_desc(sB + stage * kBStageBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in 16-byte units
+            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, kInstrDesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(buf));  // accumulator complete -> epilogue
+      }
+    }
+    __syncwarp();
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue =====================
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+    const int half = (warp - kEpiWarp0) >> 2; // which 128-column group of the accumulator
+    const int alpha = lane & 1;
+    double scale[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) scale[l] = (double)(1ull << (p.limb_bits * (NL - 1 - l)));
+    unsigned long long done = 0;
+    uint32_t tcount = 0;
+    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++tcount) {
+      const uint2 tile = p.tiles[t];
+      const uint32_t buf = tcount & 1u, bphase = (tcount >> 1) & 1u;
+      const int site_i = (int)tile.x * (kBlockM / 2) + quarter * 16 + (lane >> 1);
+      const int site_j0 = (int)tile.y * (2 * SPG) + half * SPG;
+      mbar_wait(tfull_bar(buf), bphase, p.error_flag, 4);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * kBlockN + half * 128;
+      // whole tile below the diagonal band for this warp?  (i >= every j) -> nothing to do
+      const int i_min = (int)tile.x * (kBlockM / 2) + quarter * 16;
+      const bool any_work = i_min < min(site_j0 + SPG, p.n_kept) - 0 && site_j0 < p.n_kept;
+      if (any_work) {
+#pragma unroll 1
+        for (int jp = 0; jp < (SPG + 1) / 2; ++jp) {
+          uint32_t v[2 * RPS];
+          const bool has2 = (2 * jp + 1) < SPG;
+          if (has2) {
+            tmem_ld_cols<2 * RPS>(taddr + jp * 2 * RPS, v);
+          } else {
+            tmem_ld_cols<RPS>(taddr + jp * 2 * RPS, v);
+#pragma unroll
+            for (int x = RPS; x < 2 * RPS; ++x) v[x] = 0u;
+          }
+          tmem_ld_wait();
+          double S[2][2];
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+            for (int beta = 0; beta < 2; ++beta) {
+              double s = 0.0;
+#pragma unroll
+              for (int l = 0; l < NL; ++l)
+                s = fma((double)__uint_as_float(v[jj * RPS + beta * NL + l]), scale[l], s);  // exact
+              S[jj][beta] = s;
+            }
+          // lane alpha=0 finishes site j0 = 2jp, lane alpha=1 finishes j1 = 2jp+1; swap the other halves
+          const double send0 = alpha ? S[0][0] : S[1][0];
+          const double send1 = alpha ? S[0][1] : S[1][1];
+          const double recv0 = __shfl_xor_sync(0xffffffffu, send0, 1);
+          const double recv1 = __shfl_xor_sync(0xffffffffu, send1, 1);
+          const double own0 = alpha ? S[1][0] : S[0][0];
+          const double own1 = alpha ? S[1][1] : S[0][1];
+          const double AB = alpha ? recv0 : own0;
+          const double Ab = alpha ? recv1 : own1;
+          const double aB = alpha ? own0 : recv0;
+          const double ab = alpha ? own1 : recv1;
+          const int j_local = 2 * jp + alpha;
+          const int site_j = site_j0 + j_local;
+          const bool valid = j_local < SPG && site_i < site_j && site_j < p.n_kept;  // lib.rs:651
+          done += valid;
+          bool keep = valid && ld_prefilter(AB, Ab, aB, ab, p.thr_lo);
+          if (__any_sync(0xffffffffu, keep)) {
+            float d = 0.f, dp = 0.f, r2 = 0.f;
+            if (keep) keep = ld_stats_exact(AB, Ab, aB, ab, p.thr, d, dp, r2);
+            emit_pairs_warp(keep, (uint32_t)site_i, (uint32_t)site_j, d, dp, r2, p.out);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) done += __shfl_xor_sync(0xffffffffu, done, o);
+    if (lane == 0 && done) atomicAdd(p.pairs_done, done);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+bool make_tensor_map(CUtensorMap* map, void* base, uint64_t rows, uint64_t kp, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  const cuuint64_t gdim[2] = {kp, rows};
+  const cuuint64_t gstride[1] = {kp * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int NL>
+cudaError_t launch(int grid, cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                   const UmmaParams& prm) {
+  cudaError_t e = cudaFuncSetAttribute(pair_umma_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e != cudaSuccess) return e;
+  pair_umma_kernel<NL><<<grid, kNumThreads, kSmemBytes, stream>>>(tmA, tmB, prm);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+int run_pair_umma(wld_ctx* c, float thr, ScopedStageTimer& tm) {
+  const PairGeom& gm = c->geom;
+  const int64_t L = c->n_kept;
+  const int64_t tile_m = kBlockM / 2;             // sites per tile along a
+  const int64_t tile_n = 2 * gm.sites_per_group;  // sites per tile along b
+  const int64_t n_mt = (L + tile_m - 1) / tile_m, n_nt = (L + tile_n - 1) / tile_n;
+
+  // Upper-triangular tile list, rasterised in strips of 8 N tiles so that the ~148 tiles in flight
+  // share operand panels through L2 (about 18 A panels x 8 B panels).
+  std::vector<uint2> all;
+  constexpr int64_t kStrip = 8;
+  for (int64_t ns = 0; ns < n_nt; ns += kStrip) {
+    const int64_t ne = std::min(ns + kStrip, n_nt);
+    for (int64_t mi = 0; mi < n_mt; ++mi) {
+      for (int64_t nj = ns; nj < ne; ++nj) {
+        const int64_t j_last = std::min(L, (nj + 1) * tile_n) - 1;
+        if (mi * tile_m < j_last) all.push_back(make_uint2((unsigned)mi, (unsigned)nj));
+      }
+    }
+  }
+  // Load-balanced partition for multi-GPU runs: blocks of 2*SM tiles dealt round-robin.
+  std::vector<uint2> list;
+  if (c->nparts == 1) {
+    list.swap(all);
+  } else {
+    const size_t blk = (size_t)std::max(c->sm_count, 1) * 2;
+    for (size_t b0 = 0, bi = 0; b0 < all.size(); b0 += blk, ++bi)
+      if ((int)(bi % (size_t)c->nparts) == c->part)
+        list.insert(list.end(), all.begin() + b0, all.begin() + std::min(all.size(), b0 + blk));
+  }
+  c->info.tiles = (int64_t)list.size();
+  c->info.tile_sites_m = tile_m;
+  c->info.tile_sites_n = tile_n;
+  c->info.executed_flop = (double)list.size() * 2.0 * kBlockM * kBlockN * (double)gm.k_padded;
+  if (list.empty()) return WLD_OK;
+
+  WLD_CUDA(c, c->tiles.ensure(sizeof(uint2) * list.size()));
+  WLD_CUDA(c, cudaMemcpyAsync(c->tiles.p, list.data(), sizeof(uint2) * list.size(), cudaMemcpyHostToDevice, c->stream));
+  WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+
+  CUtensorMap tmA, tmB;
+  if (!make_tensor_map(&tmA, c->opA.p, (uint64_t)gm.a_rows, (uint64_t)gm.k_padded, kBlockM) ||
+      !make_tensor_map(&tmB, c->opB.p, (uint64_t)gm.b_groups * 128, (uint64_t)gm.k_padded, kBlockN))
+    return c->fail(WLD_ERR_CUDA, "cuTensorMapEncodeTiled failed (driver without TMA support?)");
+
+  UmmaParams prm;
+  prm.tiles = c->tiles.as<uint2>();
+  prm.n_tiles = (int)list.size();
+  prm.k_blocks = (int)(gm.k_padded / kBlockK);
+  prm.n_kept = (int)L;
+  prm.limb_bits = gm.limb_bits;
+  prm.thr = thr;
+  prm.thr_lo = ld_thr_lo(thr);
+  prm.out = PairOut{c->pairs.as<wld_pair>(), c->counters.as<unsigned long long>(), c->pair_cap};
+  prm.pairs_done = c->counters.as<unsigned long long>() + 1;
+  prm.error_flag = reinterpret_cast<int*>(c->counters.as<unsigned long long>() + 2);
+
+  const int grid = (int)std::min<size_t>(list.size(), (size_t)c->sm_count);
+  cudaError_t e;
+  switch (gm.n_limbs) {
+    case 1: e = launch<1>(grid, c->stream, tmA, tmB, prm); break;
+    case 2: e = launch<2>(grid, c->stream, tmA, tmB, prm); break;
+    case 3: e = launch<3>(grid, c->stream, tmA, tmB, prm); break;
+    case 4: e = launch<4>(grid, c->stream, tmA, tmB, prm); break;
+    default: return c->fail(WLD_ERR_INVALID, "n_limbs must be 1..4");
+  }
+  tm.launched();
+  if (e != cudaSuccess) return c->fail(WLD_ERR_CUDA, "pair_umma launch failed: %s", cudaGetErrorString(e));
+  return WLD_OK;
+}
+
+}  // namespace wld

@@ -1,0 +1,407 @@
+// wld_api.cu — the C ABI declared in include/wld.h (stage orchestration, ownership, errors,
+// result ordering).  No torch types, no CPU fallback: every stage is a CUDA kernel in this library
+// and every failure is reported through wld_status + wld_last_error.
+#include <algorithm>
+#include <cmath>
+#include <new>
+
+#include "common.cuh"
+
+using namespace wld;
+
+namespace {
+#define WLD_CHECK_CTX(c)        \
+  if (!(c)) return WLD_ERR_INVALID; \
+  cudaSetDevice((c)->device)
+
+struct HostPairKey {
+  uint64_t tile;
+  uint32_t a, b;
+  uint32_t idx;
+};
+}  // namespace
+
+extern "C" {
+
+int wld_abi_version(void) { return WLD_ABI_VERSION; }
+
+int wld_create(int device, wld_ctx** out) {
+  if (!out) return WLD_ERR_INVALID;
+  *out = nullptr;
+  wld_ctx* c = new (std::nothrow) wld_ctx();
+  if (!c) return WLD_ERR_NOMEM;
+  *out = c;  // returned even on failure so that wld_last_error works; caller destroys it
+  c->device = device;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return c->fail(WLD_ERR_CUDA, "no CUDA device available (%s); libwld has no CPU fallback",
+                   e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return c->fail(WLD_ERR_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+  WLD_CUDA(c, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  WLD_CUDA(c, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return c->fail(WLD_ERR_CUDA, "device %d is sm_%d%d; libwld is built for sm_100a (B200) only", device, prop.major,
+                   prop.minor);
+  c->sm_count = prop.multiProcessorCount;
+  WLD_CUDA(c, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  return WLD_OK;
+}
+
+void wld_destroy(wld_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  DevBuf* bufs[] = {&c->raw_own, &c->hist, &c->keep, &c->rank, &c->maj_raw, &c->min_raw, &c->site_map, &c->maj,
+                    &c->mnr, &c->kept_count, &c->codes, &c->table, &c->partial, &c->w64, &c->w32, &c->scalars,
+                    &c->q, &c->limbs, &c->opA, &c->opB, &c->tiles, &c->pairs, &c->counters};
+  for (DevBuf* b : bufs) b->release();
+  for (auto& t : c->timers) {
+    if (t.beg) cudaEventDestroy(t.beg);
+    if (t.end) cudaEventDestroy(t.end);
+  }
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+const char* wld_last_error(const wld_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int wld_set_stream(wld_ctx* c, void* cuda_stream) {
+  WLD_CHECK_CTX(c);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  c->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+  return WLD_OK;
+}
+
+int wld_set_partition(wld_ctx* c, int part, int nparts) {
+  WLD_CHECK_CTX(c);
+  if (nparts < 1 || part < 0 || part >= nparts) return c->fail(WLD_ERR_INVALID, "bad partition %d/%d", part, nparts);
+  c->part = part;
+  c->nparts = nparts;
+  return WLD_OK;
+}
+
+int wld_set_limbs(wld_ctx* c, int n_limbs) {
+  WLD_CHECK_CTX(c);
+  if (n_limbs < 1 || n_limbs > 4) return c->fail(WLD_ERR_INVALID, "n_limbs must be 1..4");
+  c->n_limbs_opt = n_limbs;
+  return WLD_OK;
+}
+
+int wld_set_pair_kernel(wld_ctx* c, int kind) {
+  WLD_CHECK_CTX(c);
+  if (kind != WLD_PAIR_KERNEL_UMMA && kind != WLD_PAIR_KERNEL_SIMT) return c->fail(WLD_ERR_INVALID, "unknown pair kernel %d", kind);
+  c->pair_kernel = kind;
+  return WLD_OK;
+}
+
+int wld_set_pair_capacity(wld_ctx* c, uint64_t pairs) {
+  WLD_CHECK_CTX(c);
+  c->pair_cap_opt = pairs;
+  return WLD_OK;
+}
+
+// ---- stage 1 -----------------------------------------------------------------------------------
+int wld_load_alignment(wld_ctx* c, const uint8_t* data, int64_t n_seqs, int64_t n_cols, int64_t row_stride, int flags) {
+  WLD_CHECK_CTX(c);
+  if (n_seqs < 0 || n_cols < 0 || row_stride < n_cols || (!data && n_seqs * n_cols > 0))
+    return c->fail(WLD_ERR_INVALID, "bad alignment shape %lld x %lld (stride %lld)", (long long)n_seqs, (long long)n_cols,
+                   (long long)row_stride);
+  if (n_seqs >= (1ll << 31) || n_cols >= (1ll << 31) - 64)
+    return c->fail(WLD_ERR_UNSUPPORTED, "alignment dimensions must be below 2^31");
+  c->stage = Stage::Created;
+  c->n_seqs = n_seqs;
+  c->n_cols = n_cols;
+  c->input_flags = flags;
+  c->n_kept = 0;
+  {
+    ScopedStageTimer tm(c, WLD_STAGE_LOAD);
+    if (flags & WLD_INPUT_DEVICE) {
+      c->d_raw = data;
+      c->row_stride = row_stride;
+    } else {
+      const int64_t pitch = round_up(std::max<int64_t>(n_cols, 1), 16);
+      const size_t bytes = (size_t)pitch * (size_t)std::max<int64_t>(n_seqs, 1);
+      WLD_CUDA(c, c->raw_own.ensure(bytes));
+      if (pitch != n_cols) WLD_CUDA(c, cudaMemsetAsync(c->raw_own.p, 0, bytes, c->stream));
+      if (n_seqs > 0 && n_cols > 0)
+        WLD_CUDA(c, cudaMemcpy2DAsync(c->raw_own.p, (size_t)pitch, data, (size_t)row_stride, (size_t)n_cols,
+                                      (size_t)n_seqs, cudaMemcpyHostToDevice, c->stream));
+      c->d_raw = c->raw_own.as<uint8_t>();
+      c->row_stride = pitch;
+    }
+  }
+  {
+    ScopedStageTimer tm(c, WLD_STAGE_HISTOGRAM);
+    int rc = run_histogram(c, tm);
+    if (rc != WLD_OK) return rc;
+  }
+  // The host buffer may be reused by the caller as soon as we return.
+  WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->stage = Stage::Loaded;
+  return WLD_OK;
+}
+
+static int filter_common(wld_ctx* c, bool keep_all, float min_acgt, float min_minor, float max_minor, int64_t* n_kept) {
+  if (c->stage < Stage::Loaded) return c->fail(WLD_ERR_STATE, "wld_filter_sites before wld_load_alignment");
+  {
+    ScopedStageTimer tm(c, WLD_STAGE_FILTER);
+    int rc = run_filter(c, keep_all, min_acgt, min_minor, max_minor, tm);
+    if (rc != WLD_OK) return rc;
+  }
+  WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (n_kept) *n_kept = c->n_kept;
+  c->stage = Stage::Filtered;
+  return WLD_OK;
+}
+
+int wld_filter_sites(wld_ctx* c, float min_acgt, float min_minor, float max_minor, int64_t* n_kept) {
+  WLD_CHECK_CTX(c);
+  return filter_common(c, false, min_acgt, min_minor, max_minor, n_kept);
+}
+
+int wld_keep_all_sites(wld_ctx* c, int64_t* n_kept) {
+  WLD_CHECK_CTX(c);
+  return filter_common(c, true, 0.f, 0.f, 0.f, n_kept);
+}
+
+int64_t wld_n_seqs(const wld_ctx* c) { return c ? c->n_seqs : -1; }
+int64_t wld_n_cols(const wld_ctx* c) { return c ? c->n_cols : -1; }
+int64_t wld_n_kept(const wld_ctx* c) { return c ? c->n_kept : -1; }
+
+int wld_get_site_map(wld_ctx* c, int64_t* out, int64_t cap) {
+  WLD_CHECK_CTX(c);
+  if (c->stage < Stage::Filtered) return c->fail(WLD_ERR_STATE, "site map requested before filtering");
+  if (cap < c->n_kept || (!out && c->n_kept)) return c->fail(WLD_ERR_INVALID, "site map buffer too small");
+  std::vector<int32_t> tmp((size_t)c->n_kept);
+  if (c->n_kept)
+    WLD_CUDA(c, cudaMemcpyAsync(tmp.data(), c->site_map.p, sizeof(int32_t) * tmp.size(), cudaMemcpyDeviceToHost, c->stream));
+  WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int64_t k = 0; k < c->n_kept; ++k) out[k] = tmp[(size_t)k];
+  return WLD_OK;
+}
+
+int wld_get_histograms(wld_ctx* c, uint32_t* out, int64_t cap_cols) {
+  WLD_CHECK_CTX(c);
+  // bin 5 is completed by the decision kernel, so histograms are readable after filtering
+  if (c->stage < Stage::Filtered) return c->fail(WLD_ERR_STATE, "histograms requested before filtering");
+  if (cap_cols < c->n_cols || (!out && c->n_cols)) return c->fail(WLD_ERR_INVALID, "histogram buffer too small");
+  std::vector<uint32_t> tmp((size_t)(6 * c->cols_padded));
+  if (!tmp.empty())
+    WLD_CUDA(c, cudaMemcpyAsync(tmp.data(), c->hist.p, sizeof(uint32_t) * tmp.size(), cudaMemcpyDeviceToHost, c->stream));
+  WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int64_t col = 0; col < c->n_cols; ++col)
+    for (int k = 0; k < 6; ++k) out[col * 6 + k] = tmp[(size_t)(k * c->cols_padded + col)];
+  return WLD_OK;
+}
+
+int wld_get_major_minor(wld_ctx* c, int8_t* major, int8_t* minor, int64_t cap) {
+  WLD_CHECK_CTX(c);
+  if (c->stage < Stage::Filtered) return c->fail(WLD_ERR_STATE, "major/minor requested before filtering");
+  if (cap < c->n_kept) return c->fail(WLD_ERR_INVALID, "major/minor buffer too small");
+  if (c->n_kept) {
+    WLD_CUDA(c, cudaMemcpyAsync(major, c->maj.p, (size_t)c->n_kept, cudaMemcpyDeviceToHost, c->stream));
+    WLD_CUDA(c, cudaMemcpyAsync(minor, c->mnr.p, (size_t)c->n_kept, cudaMemcpyDeviceToHost, c->stream));
+  }
+  WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+  return WLD_OK;
+}
+
+int wld_get_codes(wld_ctx* c, uint8_t* out, int64_t cap_bytes) {
+  WLD_CHECK_CTX(c);
+  if (c->stage < Stage::Filtered) return c->fail(WLD_ERR_STATE, "codes requested before filtering");
+  if (cap_bytes < c->n_kept * c->n_seqs) return c->fail(WLD_ERR_INVALID, "code buffer too small");
+  if (c->n_kept && c->n_seqs)
+    WLD_CUDA(c, cudaMemcpy2DAsync(out, (size_t)c->n_seqs, c->codes.p, (size_t)c->ldc, (size_t)c->n_seqs,
+                                  (size_t)c->n_kept, cudaMemcpyDeviceToHost, c->stream));
+  WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+  return WLD_OK;
+}
+
+// ---- stage 2 -----------------------------------------------------------------------------------
+int wld_henikoff(wld_ctx* c) {
+  WLD_CHECK_CTX(c);
+  if (c->stage < Stage::Filtered) return c->fail(WLD_ERR_STATE, "wld_henikoff before wld_filter_sites");
+  {
+    ScopedStageTimer tm(c, WLD_STAGE_HENIKOFF);
+    int rc = run_henikoff(c, tm);
+    if (rc != WLD_OK) return rc;
+  }
+  WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->stage = Stage::Weighted;
+  return WLD_OK;
+}
+
+int wld_set_weights(wld_ctx* c, const float* weights, int64_t n) {
+  WLD_CHECK_CTX(c);
+  if (c->stage < Stage::Filtered) return c->fail(WLD_ERR_STATE, "wld_set_weights before wld_filter_sites");
+  if (n != c->n_seqs || (!weights && n)) return c->fail(WLD_ERR_INVALID, "expected %lld weights", (long long)c->n_seqs);
+  WLD_CUDA(c, c->w32.ensure(sizeof(float) * (size_t)std::max<int64_t>(n, 1)));
+  WLD_CUDA(c, c->w64.ensure(sizeof(double) * (size_t)std::max<int64_t>(n, 1)));
+  std::vector<double> w64((size_t)n);
+  for (int64_t i = 0; i < n; ++i) w64[(size_t)i] = (double)weights[i];
+  if (n) {
+    WLD_CUDA(c, cudaMemcpyAsync(c->w32.p, weights, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    WLD_CUDA(c, cudaMemcpyAsync(c->w64.p, w64.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  }
+  WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->stage = Stage::Weighted;
+  return WLD_OK;
+}
+
+int wld_get_weights(wld_ctx* c, float* out, int64_t cap) {
+  WLD_CHECK_CTX(c);
+  if (c->stage < Stage::Weighted) return c->fail(WLD_ERR_STATE, "weights requested before wld_henikoff / wld_set_weights");
+  if (cap < c->n_seqs) return c->fail(WLD_ERR_INVALID, "weight buffer too small");
+  if (c->n_seqs) WLD_CUDA(c, cudaMemcpyAsync(out, c->w32.p, sizeof(float) * (size_t)c->n_seqs, cudaMemcpyDeviceToHost, c->stream));
+  WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+  return WLD_OK;
+}
+
+int wld_get_weights_f64(wld_ctx* c, double* out, int64_t cap) {
+  WLD_CHECK_CTX(c);
+  if (c->stage < Stage::Weighted) return c->fail(WLD_ERR_STATE, "weights requested before wld_henikoff / wld_set_weights");
+  if (cap < c->n_seqs) return c->fail(WLD_ERR_INVALID, "weight buffer too small");
+  if (c->n_seqs) WLD_CUDA(c, cudaMemcpyAsync(out, c->w64.p, sizeof(double) * (size_t)c->n_seqs, cudaMemcpyDeviceToHost, c->stream));
+  WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+  return WLD_OK;
+}
+
+// ---- stage 3 -----------------------------------------------------------------------------------
+int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void* user, uint64_t* n_survivors,
+                 uint64_t* pairs_computed) {
+  WLD_CHECK_CTX(c);
+  if (c->stage < Stage::Weighted) return c->fail(WLD_ERR_STATE, "wld_ld_pairs before weights are set");
+  if (progress) progress(0, user);  // lib.rs:584
+  c->n_survivors = 0;
+  c->pairs_computed = 0;
+  c->last_thr = r2_threshold;
+  c->info = wld_pair_info{};
+  const int64_t L = c->n_kept;
+  if (L >= 2 && c->n_seqs > 0) {
+    {
+      ScopedStageTimer tm(c, WLD_STAGE_PAIR_PREP);
+      int rc = run_pair_prep(c, tm);
+      if (rc != WLD_OK) return rc;
+    }
+    const uint64_t total_pairs = (uint64_t)L * (uint64_t)(L - 1) / 2;
+    uint64_t cap = c->pair_cap_opt ? c->pair_cap_opt : std::min<uint64_t>(total_pairs, 1ull << 24);
+    cap = std::max<uint64_t>(cap, 1024);
+    if (c->pair_cap < cap) {
+      WLD_CUDA(c, c->pairs.ensure(sizeof(wld_pair) * (size_t)cap));
+      c->pair_cap = cap;
+    }
+    for (int attempt = 0; attempt < 3; ++attempt) {
+      WLD_CUDA(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 8, c->stream));
+      {
+        ScopedStageTimer tm(c, WLD_STAGE_PAIR);
+        int rc = c->pair_kernel == WLD_PAIR_KERNEL_SIMT ? run_pair_simt(c, r2_threshold, tm)
+                                                        : run_pair_umma(c, r2_threshold, tm);
+        if (rc != WLD_OK) return rc;
+      }
+      unsigned long long cnt[4] = {0, 0, 0, 0};
+      cudaError_t e = cudaMemcpyAsync(cnt, c->counters.p, sizeof cnt, cudaMemcpyDeviceToHost, c->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+      if (e != cudaSuccess)
+        return c->fail(WLD_ERR_CUDA, "pair kernel failed: %s (pipeline watchdog code %d)", cudaGetErrorString(e),
+                       (int)cnt[2]);
+      c->pairs_computed = cnt[1];
+      if (cnt[0] <= c->pair_cap) {
+        c->n_survivors = cnt[0];
+        break;
+      }
+      // overflow protocol: the count is exact, the buffer was not written past its end -> grow, rerun
+      const uint64_t want = cnt[0] + cnt[0] / 16 + 1024;
+      WLD_CUDA(c, c->pairs.ensure(sizeof(wld_pair) * (size_t)want));
+      c->pair_cap = want;
+      if (attempt == 2) return c->fail(WLD_ERR_NOMEM, "survivor buffer kept overflowing");
+    }
+    c->info.kernel = c->pair_kernel;
+    c->info.n_limbs = c->geom.n_limbs;
+    c->info.limb_bits = c->geom.limb_bits;
+    c->info.weight_bits = c->geom.n_limbs * c->geom.limb_bits;
+    c->info.k_padded = c->geom.k_padded;
+  }
+  if (progress) progress(c->pairs_computed, user);
+  if (n_survivors) *n_survivors = c->n_survivors;
+  if (pairs_computed) *pairs_computed = c->pairs_computed;
+  c->stage = Stage::Paired;
+  return WLD_OK;
+}
+
+uint64_t wld_pair_order_key(int64_t n_kept, uint32_t kept_a, uint32_t kept_b) {
+  // lib.rs:615-632: n tiles of 256 per edge; linear tile index i -> row = n-1-root(i), col ascending:
+  // tile rows bottom-up, columns left to right.  (n-1-row)*n + col is monotone in that order.
+  const uint64_t n = (uint64_t)((n_kept + 255) / 256);
+  const uint64_t tr = kept_a / 256, tc = kept_b / 256;
+  return (n - 1 - tr) * n + tc;
+}
+
+int wld_fetch_pairs(wld_ctx* c, wld_pair* out, uint64_t cap, int flags, uint64_t* n_written) {
+  WLD_CHECK_CTX(c);
+  if (c->stage < Stage::Paired) return c->fail(WLD_ERR_STATE, "wld_fetch_pairs before wld_ld_pairs");
+  const uint64_t n = c->n_survivors;
+  if (n_written) *n_written = 0;
+  if (cap < n) return c->fail(WLD_ERR_INVALID, "pair buffer holds %llu, need %llu", (unsigned long long)cap, (unsigned long long)n);
+  if (n == 0) return WLD_OK;
+  std::vector<wld_pair> host((size_t)n);
+  WLD_CUDA(c, cudaMemcpyAsync(host.data(), c->pairs.p, sizeof(wld_pair) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  std::vector<int32_t> smap;
+  if (!(flags & WLD_FETCH_KEPT_INDEX)) {
+    smap.resize((size_t)c->n_kept);
+    WLD_CUDA(c, cudaMemcpyAsync(smap.data(), c->site_map.p, sizeof(int32_t) * smap.size(), cudaMemcpyDeviceToHost, c->stream));
+  }
+  WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+  std::vector<HostPairKey> keys;
+  if (!(flags & WLD_FETCH_UNORDERED)) {
+    keys.resize((size_t)n);
+    for (uint64_t i = 0; i < n; ++i)
+      keys[(size_t)i] = HostPairKey{wld_pair_order_key(c->n_kept, host[(size_t)i].site_a, host[(size_t)i].site_b),
+                                    host[(size_t)i].site_a, host[(size_t)i].site_b, (uint32_t)i};
+    std::sort(keys.begin(), keys.end(), [](const HostPairKey& x, const HostPairKey& y) {
+      if (x.tile != y.tile) return x.tile < y.tile;
+      if (x.a != y.a) return x.a < y.a;
+      return x.b < y.b;
+    });
+  }
+  for (uint64_t i = 0; i < n; ++i) {
+    wld_pair p = host[(size_t)(keys.empty() ? i : keys[(size_t)i].idx)];
+    if (!smap.empty()) {
+      p.site_a = (uint32_t)smap[p.site_a];  // lib.rs:662-663
+      p.site_b = (uint32_t)smap[p.site_b];
+    }
+    out[i] = p;
+  }
+  if (n_written) *n_written = n;
+  return WLD_OK;
+}
+
+// ---- introspection -----------------------------------------------------------------------------
+int wld_stage_ms(wld_ctx* c, int stage, float* ms) {
+  WLD_CHECK_CTX(c);
+  if (stage < 0 || stage >= WLD_STAGE_COUNT || !ms) return c->fail(WLD_ERR_INVALID, "bad stage id");
+  *ms = 0.f;
+  StageTimer& t = c->timers[stage];
+  if (!t.valid) return WLD_OK;
+  WLD_CUDA(c, cudaEventSynchronize(t.end));
+  WLD_CUDA(c, cudaEventElapsedTime(ms, t.beg, t.end));
+  return WLD_OK;
+}
+
+int wld_stage_launches(wld_ctx* c, int stage, int* launches) {
+  WLD_CHECK_CTX(c);
+  if (stage < 0 || stage >= WLD_STAGE_COUNT || !launches) return c->fail(WLD_ERR_INVALID, "bad stage id");
+  *launches = c->timers[stage].valid ? c->timers[stage].launches : 0;
+  return WLD_OK;
+}
+
+int wld_get_pair_info(wld_ctx* c, wld_pair_info* out) {
+  WLD_CHECK_CTX(c);
+  if (!out) return c->fail(WLD_ERR_INVALID, "null output");
+  *out = c->info;
+  return WLD_OK;
+}
+
+}  // extern "C"
