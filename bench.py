@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py — weighted-LD site-pairs/sec of the WeightedLD hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c4|c3|tiny] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the whole hot path over one synthetic alignment: encode + histogram +
+site filter -> Henikoff weights -> operand expansion -> tcgen05 Gram + fused epilogue + compaction.
+`value` times it with the alignment already resident in HBM; `e2e` runs the same through the
+C ABI from pinned HOST memory (H2D of the alignment and D2H of the surviving pairs inside the timed
+region).  With N ranks the upper-triangular tile grid is partitioned (no collective on the data
+path); the alignment is replicated; value = all pairs / max-over-ranks time ("strong" scaling: the
+total work is fixed).  Inputs (0.5-3 GB of text, 8 GB of operands) are far larger than the 126 MB
+L2, so no explicit flush is needed between iterations.
+
+--impl reference times the reference's own CPU implementation of the path.  The Rust binary cannot
+be built in this image (no cargo/rustc), so this is the C restatement of the
+reference's fastest path (8-lane f32 `simd` build, 256x256 tiles, all host threads; oracle/),
+on a bounded sample of tiles of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (description, n_seqs, n_cols, generator kwargs)
+    "c5": ("synthetic 10,000 sequences x 50,000 variable sites (BASELINE.json configs[4])", 10_000, 50_000, {}),
+    "c4": ("synthetic SARS-CoV-2-like 100,000 sequences x 30 kb, ~1/3 variable (configs[3])", 100_000, 30_000, {"sars": True}),
+    "c3": ("synthetic 2,000 sequences x 20,000 variable sites (configs[2])", 2_000, 20_000, {}),
+    "tiny": ("synthetic 512 sequences x 3,000 sites (smoke)", 512, 3_000, {}),
+}
+R2_THRESHOLD = 0.1
+FILTER = (0.8, 0.02, 0.5)  # main.rs defaults
+
+
+def make_input(name: str) -> np.ndarray:
+    from weightedld_b200.synth import make_alignment, make_sarscov2_like
+    _, n, l, kw = WORKLOADS[name]
+    seed = 0xC0FFEE + list(WORKLOADS).index(name)
+    if kw.get("sars"):
+        return make_sarscov2_like(n, l, seed=seed)
+    return make_alignment(n, l, seed=seed)
+
+
+def peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"bf16_sustained": d.get("bf16_tflops_sustained"), "bf16_burst": d.get("bf16_tflops"),
+                "hbm": d.get("hbm_gbs"), "source": "MEASURED_PEAKS.json (of measured)"}
+    return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "source": "B200_PROFILING.md fallback (of fallback)"}
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, nm in names.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self._nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self) -> dict:
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port) — also the cpu_baseline leg of our own arm
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(chars: np.ndarray, steps: int, warmup: int, target_s: float):
+    """Times the C restatement of the reference's `simd` pair path on a bounded sample of tiles.
+    Returns (pairs_per_s, info dict)."""
+    from oracle import oracle as O
+    O.build(native=True, force=True)  # -O3 -march=native on THIS machine's cores (README.md:88-97 of the reference)
+    lib = O.lib(native=True)
+    threads = lib.wldo_max_threads()
+    ss = O.filter_sites(O.siteset_from_chars(chars), *FILTER)
+    w = O.henikoff_weights(ss)
+    n_tiles = int(lib.wldo_tile_count(ss.n_sites))
+    # calibrate on `threads` tiles, then size the sample for ~target_s per step
+    rng = np.random.Generator(np.random.PCG64(1))
+    start = int(rng.integers(0, max(1, n_tiles - threads)))
+    t0 = time.perf_counter()
+    _, done = O.all_weighted_ld_pairs(ss, w, R2_THRESHOLD, O.F32_SIMD8, tile_range=(start, start + threads), store=False, native=True)
+    dt = time.perf_counter() - t0
+    rate = done / dt
+    sample_tiles = int(min(n_tiles, max(threads, target_s * rate / max(done / threads, 1))))
+    sample_tiles = max(threads, sample_tiles // threads * threads)
+    start = int(rng.integers(0, max(1, n_tiles - sample_tiles)))
+    times, pairs = [], 0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, pairs = O.all_weighted_ld_pairs(ss, w, R2_THRESHOLD, O.F32_SIMD8, tile_range=(start, start + sample_tiles), store=False, native=True)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    dt = float(np.mean(times))
+    info = {"cores": threads, "kind": "port",
+            "sample": f"{sample_tiles} of {n_tiles} reference tiles (256x256 sites, {pairs} pairs) of the same workload, "
+                      f"8-lane f32 restatement of lib.rs:410-453, -O3 -march=native, OpenMP dynamic; "
+                      f"restated reference (C), not the Rust binary",
+            "n_kept": ss.n_sites, "ms_per_step": dt * 1e3}
+    return pairs / dt, info
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    desc, n, l, _ = WORKLOADS[args.workload]
+    chars = make_input(args.workload)
+    value, info = cpu_reference(chars, args.steps, max(args.warmup, 1), target_s=6.0)
+    line = {"impl": "reference", "metric": "weighted LD site-pairs/sec", "value": value, "unit": "site-pairs/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "n_seqs": n, "n_cols": l, "n_kept": info["n_kept"], "r2_threshold": R2_THRESHOLD},
+            "cpu_baseline": {"value": value, "unit": "site-pairs/s", "cores": info["cores"], "kind": info["kind"],
+                             "sample": info["sample"]},
+            "e2e": {"value": value, "unit": "site-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import weightedld_b200 as wld
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    desc, n_seqs, n_cols, _ = WORKLOADS[args.workload]
+    chars_np = make_input(args.workload)
+    host = torch.from_numpy(chars_np).pin_memory()
+    host_np = host.numpy()  # view of the pinned buffer
+    dev = host.cuda(non_blocking=False)
+
+    ctx = wld.Context(local)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.set_partition(rank, world)
+    if args.limbs:
+        ctx.set_limbs(args.limbs)
+    if args.kernel:
+        ctx.set_pair_kernel(args.kernel)
+
+    stages = {k: 0.0 for k in wld.STAGE_NAMES}
+    launches = {"n": 0}
+    state = {}
+
+    def step(src, fetch: bool, record: bool):
+        ctx.load_alignment(src)
+        n_kept = ctx.filter_sites(*FILTER)
+        ctx.henikoff()
+        n_surv, done = ctx.ld_pairs(R2_THRESHOLD)
+        out = ctx.fetch_pairs(n_surv, wld.FETCH_KEPT_INDEX | wld.FETCH_UNORDERED) if fetch else None
+        state.update(n_kept=n_kept, n_surv=n_surv, done=done)
+        if record:
+            for i, nm in enumerate(wld.STAGE_NAMES):
+                stages[nm] += ctx.stage_ms(i)
+                launches["n"] += ctx.stage_launches(i)
+        return out
+
+    def timed(src, fetch, steps, record):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(src, fetch, record)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        barrier()
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step(dev, False, False)
+    with ClockSampler(local) as clocks:
+        ms = timed(dev, False, args.steps, True)
+    for _ in range(1):
+        step(host_np, True, False)
+    ms_e2e = timed(host_np, True, args.steps, False)
+
+    n_kept = state["n_kept"]
+    total_pairs = n_kept * (n_kept - 1) // 2
+    done_all = state["done"]
+    surv_all = state["n_surv"]
+    if world > 1:
+        t = torch.tensor([done_all, surv_all], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        done_all, surv_all = int(t[0]), int(t[1])
+    assert done_all == total_pairs, (done_all, total_pairs)
+
+    info = ctx.pair_info()
+    pk = peaks()
+    pair_ms = stages["pair"] / args.steps
+    algo_flop = 8.0 * n_seqs * info.n_limbs * state["done"]      # 8*N flop per pair per limb pass
+    useful_flop = 8.0 * n_seqs * state["done"]
+    achieved = algo_flop / (pair_ms * 1e-3) / 1e12
+    roof = {"bound": "tensor", "kernel": "pair_umma_kernel" if info.kernel == 0 else "pair_simt_kernel",
+            "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
+            "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
+            "achieved_useful": useful_flop / (pair_ms * 1e-3) / 1e12,
+            "executed": info.executed_flop / (pair_ms * 1e-3) / 1e12,
+            "algorithmic_flop_per_pair": 8 * n_seqs * info.n_limbs, "n_limbs": info.n_limbs, "limb_bits": info.limb_bits,
+            "kernel_ms": pair_ms, "traffic": None}
+    prof = ROOT / "profiles" / "pair_umma_traffic.json"
+    if prof.exists():
+        try:
+            roof["traffic"] = json.loads(prof.read_text()).get(args.workload)
+        except Exception:
+            pass
+
+    if rank == 0:
+        line = {
+            "metric": "weighted LD site-pairs/sec", "value": total_pairs / (ms * 1e-3), "unit": "site-pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16 limbs x fp32 accumulate (exact), f64 epilogue",
+            "data": "synthetic",
+            "config": {"workload": desc, "n_seqs": n_seqs, "n_cols": n_cols, "n_kept": n_kept, "site_pairs": total_pairs,
+                       "survivors": surv_all, "r2_threshold": R2_THRESHOLD, "filter": list(FILTER),
+                       "parallelism": f"triangle-partition x{world}", "l2": "inputs larger than L2 (no flush needed)"},
+            "stages_ms": {k: v / args.steps for k, v in stages.items()},
+            "roofline": roof,
+            "e2e": {"value": total_pairs / (ms_e2e * 1e-3), "unit": "site-pairs/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(chars_np.nbytes), "d2h_bytes_per_step": int(20 * state["n_surv"] + 64)},
+            "gpu_launches": launches["n"],
+            "clocks": clocks.summary(),
+        }
+        if world == 1 and not args.no_cpu:
+            v, ci = cpu_reference(chars_np, 1, 1, target_s=12.0)
+            line["cpu_baseline"] = {"value": v, "unit": "site-pairs/s", "cores": ci["cores"], "kind": ci["kind"], "sample": ci["sample"]}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c5", choices=list(WORKLOADS))
+    ap.add_argument("--limbs", type=int, default=0)
+    ap.add_argument("--kernel", default="", choices=["", "umma", "simt"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

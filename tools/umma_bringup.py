@@ -28,7 +28,7 @@ ok = True
 for (n, l, limbs) in [(64, 100, 1), (64, 100, 3), (200, 300, 3), (1000, 900, 3), (1000, 900, 2), (1000, 900, 4), (3000, 3000, 3)]:
     chars = make_alignment(n, l, seed=n + l, block=60, clonal=True)
     w = np.ones(n, np.float32) if limbs == 1 else None
-    k, s, sd, sms, _ = run(chars, "simt", weights=w)
+    k, s, sd, sms, _ = run(chars, "simt", limbs=limbs, weights=w)
     try:
         k2, u, ud, ums, info = run(chars, "umma", limbs=limbs, weights=w)
     except Exception as e:  # noqa

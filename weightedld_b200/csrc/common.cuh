@@ -103,7 +103,7 @@ struct wld_ctx {
 
   // stage 3
   wld::PairGeom geom;
-  wld::DevBuf q;                   // u32 [ldc]      fixed-point weights
+  wld::DevBuf q;                   // f64 [ldc]      fixed-point weights (integers <= 2^32)
   wld::DevBuf limbs;               // u16 [NL][ldc]  bf16 bit patterns of the limbs
   wld::DevBuf opA;                 // bf16 [a_rows][k_padded]
   wld::DevBuf opB;                 // bf16 [b_groups*128][k_padded]

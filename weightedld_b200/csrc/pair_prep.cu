@@ -29,7 +29,7 @@ __device__ __forceinline__ uint16_t bf16_bits_of_small_int(uint32_t v) {
 // One block.  flags: bit0 = invalid weight seen, bit1 = all weights equal.
 // limb_sums[l] = sum over sequences of limb l (u64) — an upper bound of every Gram entry of that limb.
 __global__ void __launch_bounds__(1024) quantize_kernel(const float* __restrict__ w, int64_t n_seqs, int64_t ldc,
-                                                        int n_limbs, int limb_bits, uint32_t* __restrict__ q,
+                                                        int n_limbs, int limb_bits, double* __restrict__ q,
                                                         uint16_t* __restrict__ limbs,
                                                         unsigned long long* __restrict__ limb_sums,
                                                         int* __restrict__ flags) {
@@ -74,12 +74,12 @@ __global__ void __launch_bounds__(1024) quantize_kernel(const float* __restrict_
   const uint32_t limb_mask = (1u << limb_bits) - 1u;
   unsigned long long sums[4] = {0, 0, 0, 0};
   for (int64_t s = threadIdx.x; s < ldc; s += blockDim.x) {
-    uint32_t qi = 0;
-    if (s < n_seqs) qi = (uint32_t)rint(__dmul_rn(__ddiv_rn((double)w[s], (double)mx), scale));
-    q[s] = qi;
+    unsigned long long qi = 0;  // may equal 2^total_bits (up to 2^32) for the largest weight
+    if (s < n_seqs) qi = (unsigned long long)rint(__dmul_rn(__ddiv_rn((double)w[s], (double)mx), scale));
+    q[s] = (double)qi;
     for (int l = 0; l < n_limbs; ++l) {
       const int shift = limb_bits * (n_limbs - 1 - l);
-      uint32_t v = qi >> shift;
+      uint32_t v = (uint32_t)(qi >> shift);
       if (l > 0) v &= limb_mask;  // the top limb keeps the carry (q may equal 2^total_bits)
       limbs[(int64_t)l * ldc + s] = bf16_bits_of_small_int(v);
       sums[l] += v;
@@ -172,7 +172,7 @@ int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm) {
   const int64_t n = c->n_seqs, L = c->n_kept;
   gm.n_limbs = c->n_limbs_opt;
 
-  WLD_CUDA(c, c->q.ensure(sizeof(uint32_t) * (size_t)c->ldc));
+  WLD_CUDA(c, c->q.ensure(sizeof(double) * (size_t)c->ldc));
   WLD_CUDA(c, c->limbs.ensure(sizeof(uint16_t) * 4 * (size_t)c->ldc));
   WLD_CUDA(c, c->counters.ensure(sizeof(unsigned long long) * 16));
   WLD_CUDA(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream));
@@ -184,7 +184,7 @@ int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm) {
   int bits = 8;
   for (;;) {
     quantize_kernel<<<1, 1024, 0, c->stream>>>(c->w32.as<float>(), n, c->ldc, gm.n_limbs, bits,
-                                               c->q.as<uint32_t>(), c->limbs.as<uint16_t>(),
+                                               c->q.as<double>(), c->limbs.as<uint16_t>(),
                                                c->counters.as<unsigned long long>() + 8,
                                                reinterpret_cast<int*>(c->counters.as<unsigned long long>() + 12));
     tm.launched();

@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(256) pair_simt_kernel(const uint8_t* __restric
                                                         int64_t n_kept, int64_t n_seqs,
                                                         const int8_t* __restrict__ maj,
                                                         const int8_t* __restrict__ mnr,
-                                                        const uint32_t* __restrict__ q,
+                                                        const double* __restrict__ q,
                                                         const uint2* __restrict__ tiles, float thr, double thr_lo,
                                                         PairOut out, unsigned long long* __restrict__ pairs_done) {
   __shared__ double sAM[kKC][kTile], sAm[kKC][kTile], sBM[kKC][kTile], sBm[kKC][kTile];
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) pair_simt_kernel(const uint8_t* __restric
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       const int64_t s = s0 + ls + b;
-      const double w = s < n_seqs ? (double)q[s] : 0.0;  // ldc padding holds code 5 anyway
+      const double w = s < n_seqs ? q[s] : 0.0;  // ldc padding holds code 5 anyway
       const int xa = (ca >> (8 * b)) & 0xff, xb = (cb >> (8 * b)) & 0xff;
       sAM[ls + b][lt] = xa == a_maj ? w : 0.0;
       sAm[ls + b][lt] = xa == a_min ? w : 0.0;
@@ -119,7 +119,7 @@ int run_pair_simt(wld_ctx* c, float thr, ScopedStageTimer& tm) {
   WLD_CUDA(c, cudaStreamSynchronize(c->stream));  // `list` is pageable and dies at return
   PairOut out{c->pairs.as<wld_pair>(), c->counters.as<unsigned long long>(), c->pair_cap};
   pair_simt_kernel<<<(unsigned)list.size(), 256, 0, c->stream>>>(
-      c->codes.as<uint8_t>(), c->ldc, L, c->n_seqs, c->maj.as<int8_t>(), c->mnr.as<int8_t>(), c->q.as<uint32_t>(),
+      c->codes.as<uint8_t>(), c->ldc, L, c->n_seqs, c->maj.as<int8_t>(), c->mnr.as<int8_t>(), c->q.as<double>(),
       c->tiles.as<uint2>(), thr, ld_thr_lo(thr), out, c->counters.as<unsigned long long>() + 1);
   tm.launched();
   WLD_CUDA(c, cudaGetLastError());

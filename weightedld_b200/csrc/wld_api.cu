@@ -38,6 +38,7 @@ int wld_create(int device, wld_ctx** out) {
     return c->fail(WLD_ERR_CUDA, "no CUDA device available (%s); libwld has no CPU fallback",
                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
   if (device < 0 || device >= ndev) return c->fail(WLD_ERR_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+  cudaGetLastError();  // do not inherit a stale error from unrelated earlier calls
   WLD_CUDA(c, cudaSetDevice(device));
   cudaDeviceProp prop;
   WLD_CUDA(c, cudaGetDeviceProperties(&prop, device));
@@ -52,6 +53,10 @@ int wld_create(int device, wld_ctx** out) {
 
 void wld_destroy(wld_ctx* c) {
   if (!c) return;
+  if (!c->own_stream) {  // creation failed before any device state existed
+    delete c;
+    return;
+  }
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->raw_own, &c->hist, &c->keep, &c->rank, &c->maj_raw, &c->min_raw, &c->site_map, &c->maj,
