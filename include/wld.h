@@ -172,6 +172,14 @@ WLD_API int wld_fetch_pairs(wld_ctx* ctx, wld_pair* out, uint64_t cap, int flags
 /* Sort key of the reference's output order for a pair of KEPT indices (for merging shards):
  * lexicographic (key, a, b) ascending == reference order. */
 WLD_API uint64_t wld_pair_order_key(int64_t n_kept, uint32_t kept_a, uint32_t kept_b);
+/* The pair-stage schedule, host only (no GPU needed): the upper-triangular tile list of partition
+ * `part` of `nparts` exactly as wld_ld_pairs runs it (replaces rayon's fan-out over triu_index,
+ * lib.rs:623-637).  A tile covers kept sites [tm*64, tm*64+64) x [tn*TN, tn*TN+TN), TN =
+ * 2*floor(128/(2*n_limbs)); only pairs a < b inside it are evaluated.  Writes 2 uint32 (tm, tn) per
+ * tile into tiles_mn (may be NULL to count), n_tiles = number of tiles, n_pairs = site pairs they
+ * cover.  sm_count sizes the round-robin blocks (148 on B200). */
+WLD_API int wld_plan_tiles(int64_t n_kept, int n_limbs, int part, int nparts, int sm_count, uint32_t* tiles_mn,
+                           uint64_t cap_tiles, uint64_t* n_tiles, uint64_t* n_pairs);
 
 /* ---- introspection ------------------------------------------------------------------------- */
 /* Device time of the last run of a stage in milliseconds (CUDA events on the context's stream). */

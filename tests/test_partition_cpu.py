@@ -1,0 +1,107 @@
+"""CPU tests of the multi-GPU host logic: the tile partition is a disjoint,
+balanced cover of the upper triangle, and shards merge into the reference's output order.
+The N>1 path runs as two real processes over torch.distributed (gloo), as bench.py does over NCCL:
+each rank plans its own part, 'computes' its shard (the oracle stands in for the GPU kernel,
+restricted to the rank's tiles), rank 0 gathers and merges, and the max-over-ranks reduction used
+for timing is exercised."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def tile_owner_mask(wld, n_kept, a, b, tiles, tile_m, tile_n):
+    own = np.zeros((n_kept // tile_m + 1, n_kept // tile_n + 1), bool)
+    own[tiles[:, 0], tiles[:, 1]] = True
+    return own[a // tile_m, b // tile_n]
+
+
+@pytest.mark.parametrize("n_limbs,tile_n", [(1, 128), (2, 64), (3, 42), (4, 32)])
+@pytest.mark.parametrize("n_kept", [1, 2, 63, 64, 65, 700, 5000])
+def test_plan_covers_each_pair_once(n_kept, n_limbs, tile_n):
+    import weightedld_b200 as wld
+    for nparts in (1, 2, 3, 8):
+        seen = np.zeros((n_kept // 64 + 1, n_kept // tile_n + 1), np.int32)
+        total = 0
+        for part in range(nparts):
+            tiles, pairs = wld.plan_tiles(n_kept, n_limbs, part, nparts, sm_count=4)
+            total += pairs
+            if len(tiles):
+                np.add.at(seen, (tiles[:, 0], tiles[:, 1]), 1)
+        assert total == n_kept * (n_kept - 1) // 2
+        assert seen.max() <= 1
+        # every tile that contains a pair a < b is present
+        for tm in range(seen.shape[0]):
+            for tn in range(seen.shape[1]):
+                j_last = min(n_kept, (tn + 1) * tile_n) - 1
+                needed = tm * 64 < j_last and tm * 64 < n_kept and tn * tile_n < n_kept
+                assert bool(seen[tm, tn]) == needed, (tm, tn)
+
+
+def test_plan_is_balanced_at_config5():
+    import weightedld_b200 as wld
+    for nparts in (2, 4, 8):
+        pairs = [wld.plan_tiles(48601, 3, p, nparts)[1] for p in range(nparts)]
+        assert max(pairs) / min(pairs) < 1.01
+
+
+def _worker(rank, world, port, n_kept, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    import torch
+    import torch.distributed as dist
+
+    import weightedld_b200 as wld
+    from oracle import oracle as O
+    from weightedld_b200.synth import make_alignment
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    chars = make_alignment(120, n_kept + 40, seed=5, block=50)
+    fs = O.filter_sites(O.siteset_from_chars(chars))
+    w = O.quantize_weights(O.henikoff_weights(fs), 24)
+    kept = O.SiteSet(fs.codes, fs.hists, None)  # kept indices, like WLD_FETCH_KEPT_INDEX
+    full, computed = O.all_weighted_ld_pairs(kept, w, 0.1, O.F64)
+    tiles, my_pairs = wld.plan_tiles(fs.n_sites, 3, rank, world, sm_count=2)
+    mine = full[tile_owner_mask(wld, fs.n_sites, full["a"], full["b"], tiles, 64, 42)]
+    rng = np.random.default_rng(rank)
+    shard = np.empty(len(mine), wld.PAIR_DTYPE)  # the GPU emits its survivors unordered
+    for src, dst in (("a", "site_a"), ("b", "site_b"), ("d", "d"), ("d_prime", "d_prime"), ("r2", "r2")):
+        shard[dst] = mine[src]
+    shard = shard[rng.permutation(len(shard))]
+
+    t = torch.tensor([my_pairs], dtype=torch.int64)
+    dist.all_reduce(t)
+    ms = torch.tensor([10.0 + rank])
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, shard)
+    if rank == 0:
+        merged = wld.merge_shards(fs.n_sites, gathered, fs.site_map)
+        ref, _ = O.all_weighted_ld_pairs(fs, w, 0.1, O.F64)  # parent indices, reference order
+        ok = (len(merged) == len(ref) and np.array_equal(merged["site_a"], ref["a"])
+              and np.array_equal(merged["site_b"], ref["b"]) and np.array_equal(merged["r2"], ref["r2"]))
+        q.put((int(t.item()), computed, float(ms.item()), ok, len(ref), [len(g) for g in gathered]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_partition_and_merge_gloo():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 600, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    total, computed, ms, ok, n_ref, sizes = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert total == computed            # the two parts cover every pair exactly once
+    assert ms == 11.0                   # max over ranks
+    assert ok and n_ref > 100 and min(sizes) > 0

@@ -8,10 +8,10 @@ from ._lib import (FETCH_KEPT_INDEX, FETCH_PARENT_INDEX, FETCH_UNORDERED, PAIR_D
                    PAIR_KERNEL_UMMA, STAGE_FILTER, STAGE_HENIKOFF, STAGE_HISTOGRAM, STAGE_LOAD, STAGE_NAMES,
                    STAGE_PAIR, STAGE_PAIR_PREP, WldError)
 from .api import (Context, MultiSequence, PairStore, SiteSet, all_weighted_ld_pairs, format_f3, henikoff_weights,
-                  pair_order_key, read_fasta, single_weighted_ld_pair, write_henikoff_weights, write_pair_stats)
+                  merge_shards, pair_order_key, plan_tiles, read_fasta, single_weighted_ld_pair, write_henikoff_weights, write_pair_stats)
 
 __all__ = [
     "Context", "MultiSequence", "PairStore", "SiteSet", "WldError", "all_weighted_ld_pairs", "format_f3",
-    "henikoff_weights", "pair_order_key", "read_fasta", "single_weighted_ld_pair", "write_henikoff_weights",
+    "henikoff_weights", "merge_shards", "pair_order_key", "plan_tiles", "read_fasta", "single_weighted_ld_pair", "write_henikoff_weights",
     "write_pair_stats", "PAIR_DTYPE",
 ]

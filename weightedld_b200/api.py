@@ -217,6 +217,33 @@ def pair_order_key(n_kept: int, kept_a, kept_b) -> np.ndarray:
     return (np.uint64(n - 1) - tr) * np.uint64(n) + tc
 
 
+def plan_tiles(n_kept: int, n_limbs: int = 3, part: int = 0, nparts: int = 1, sm_count: int = 148):
+    """Host-only pair-stage schedule (wld_plan_tiles): ((n_tiles, 2) uint32 tile coordinates,
+    site pairs covered).  Needs no GPU."""
+    lib = L.load()
+    n, pairs = C.c_uint64(), C.c_uint64()
+    rc = lib.wld_plan_tiles(n_kept, n_limbs, part, nparts, sm_count, None, 0, C.byref(n), C.byref(pairs))
+    if rc != L.WLD_OK:
+        raise WldError(rc, "bad tile plan arguments")
+    tiles = np.empty((n.value, 2), np.uint32)
+    rc = lib.wld_plan_tiles(n_kept, n_limbs, part, nparts, sm_count, _ptr(tiles), n.value, C.byref(n), C.byref(pairs))
+    if rc != L.WLD_OK:
+        raise WldError(rc, "bad tile plan arguments")
+    return tiles, pairs.value
+
+
+def merge_shards(n_kept: int, shards: list[np.ndarray], site_map: np.ndarray | None = None) -> np.ndarray:
+    """Host merge of per-GPU survivor shards (records with KEPT indices) into the reference's
+    output order (lib.rs:623-679); maps to raw columns when site_map is given (lib.rs:662-663)."""
+    allp = np.concatenate(shards) if shards else np.empty(0, PAIR_DTYPE)
+    order = np.lexsort((allp["site_b"], allp["site_a"], pair_order_key(n_kept, allp["site_a"], allp["site_b"])))
+    out = allp[order]
+    if site_map is not None and len(out):
+        out["site_a"] = np.asarray(site_map)[out["site_a"]]
+        out["site_b"] = np.asarray(site_map)[out["site_b"]]
+    return out
+
+
 # =================================================================================================
 # Mirror of the reference's Rust API
 # =================================================================================================

@@ -171,4 +171,12 @@ int run_pair_umma(wld_ctx* c, float thr, ScopedStageTimer& tm);            // pa
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// Upper-triangular tile schedule of the tcgen05 pair kernel (pair_plan.cpp part of wld_api.cu).
+struct TilePlan {
+  std::vector<uint2> tiles;
+  uint64_t pairs = 0;
+  int64_t tile_m = 64, tile_n = 42;
+};
+TilePlan plan_tiles(int64_t n_kept, int n_limbs, int part, int nparts, int sm_count);
+
 }  // namespace wld

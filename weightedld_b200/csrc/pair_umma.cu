@@ -406,36 +406,48 @@ cudaError_t launch(int grid, cudaStream_t stream, const CUtensorMap& tmA, const 
 
 }  // namespace
 
-int run_pair_umma(wld_ctx* c, float thr, ScopedStageTimer& tm) {
-  const PairGeom& gm = c->geom;
-  const int64_t L = c->n_kept;
-  const int64_t tile_m = kBlockM / 2;             // sites per tile along a
-  const int64_t tile_n = 2 * gm.sites_per_group;  // sites per tile along b
+// Upper-triangular tile list, rasterised in strips of 8 N tiles so that the ~148 tiles in flight
+// share operand panels through L2 (about 18 A panels x 8 B panels); for multi-GPU runs blocks of
+// 2*SM consecutive tiles are dealt round-robin (load-balanced, no collective; replaces rayon's
+// fan-out over triu_index, lib.rs:623-637).
+TilePlan plan_tiles(int64_t L, int n_limbs, int part, int nparts, int sm_count) {
+  TilePlan plan;
+  plan.tile_m = kBlockM / 2;
+  plan.tile_n = 2 * (128 / (2 * n_limbs));
+  const int64_t tile_m = plan.tile_m, tile_n = plan.tile_n;
   const int64_t n_mt = (L + tile_m - 1) / tile_m, n_nt = (L + tile_n - 1) / tile_n;
-
-  // Upper-triangular tile list, rasterised in strips of 8 N tiles so that the ~148 tiles in flight
-  // share operand panels through L2 (about 18 A panels x 8 B panels).
   std::vector<uint2> all;
   constexpr int64_t kStrip = 8;
   for (int64_t ns = 0; ns < n_nt; ns += kStrip) {
     const int64_t ne = std::min(ns + kStrip, n_nt);
-    for (int64_t mi = 0; mi < n_mt; ++mi) {
+    for (int64_t mi = 0; mi < n_mt; ++mi)
       for (int64_t nj = ns; nj < ne; ++nj) {
         const int64_t j_last = std::min(L, (nj + 1) * tile_n) - 1;
         if (mi * tile_m < j_last) all.push_back(make_uint2((unsigned)mi, (unsigned)nj));
       }
-    }
   }
-  // Load-balanced partition for multi-GPU runs: blocks of 2*SM tiles dealt round-robin.
-  std::vector<uint2> list;
-  if (c->nparts == 1) {
-    list.swap(all);
+  if (nparts <= 1) {
+    plan.tiles.swap(all);
   } else {
-    const size_t blk = (size_t)std::max(c->sm_count, 1) * 2;
+    const size_t blk = (size_t)std::max(sm_count, 1) * 2;
     for (size_t b0 = 0, bi = 0; b0 < all.size(); b0 += blk, ++bi)
-      if ((int)(bi % (size_t)c->nparts) == c->part)
-        list.insert(list.end(), all.begin() + b0, all.begin() + std::min(all.size(), b0 + blk));
+      if ((int)(bi % (size_t)nparts) == part)
+        plan.tiles.insert(plan.tiles.end(), all.begin() + b0, all.begin() + std::min(all.size(), b0 + blk));
   }
+  for (const uint2& t : plan.tiles) {  // pairs a < b inside the tile
+    const int64_t i0 = (int64_t)t.x * tile_m, i1 = std::min(L, i0 + tile_m);
+    const int64_t j0 = (int64_t)t.y * tile_n, j1 = std::min(L, j0 + tile_n);
+    for (int64_t i = i0; i < i1; ++i) plan.pairs += (uint64_t)std::max<int64_t>(0, j1 - std::max(j0, i + 1));
+  }
+  return plan;
+}
+
+int run_pair_umma(wld_ctx* c, float thr, ScopedStageTimer& tm) {
+  const PairGeom& gm = c->geom;
+  const int64_t L = c->n_kept;
+  TilePlan plan = plan_tiles(L, gm.n_limbs, c->part, c->nparts, c->sm_count);
+  std::vector<uint2>& list = plan.tiles;
+  const int64_t tile_m = plan.tile_m, tile_n = plan.tile_n;
   c->info.tiles = (int64_t)list.size();
   c->info.tile_sites_m = tile_m;
   c->info.tile_sites_n = tile_n;

@@ -344,6 +344,22 @@ uint64_t wld_pair_order_key(int64_t n_kept, uint32_t kept_a, uint32_t kept_b) {
   return (n - 1 - tr) * n + tc;
 }
 
+int wld_plan_tiles(int64_t n_kept, int n_limbs, int part, int nparts, int sm_count, uint32_t* tiles_mn,
+                   uint64_t cap_tiles, uint64_t* n_tiles, uint64_t* n_pairs) {
+  if (n_kept < 0 || n_limbs < 1 || n_limbs > 4 || nparts < 1 || part < 0 || part >= nparts) return WLD_ERR_INVALID;
+  TilePlan plan = plan_tiles(n_kept, n_limbs, part, nparts, sm_count > 0 ? sm_count : kNumSMsB200);
+  if (n_tiles) *n_tiles = plan.tiles.size();
+  if (n_pairs) *n_pairs = plan.pairs;
+  if (tiles_mn) {
+    if (cap_tiles < plan.tiles.size()) return WLD_ERR_INVALID;
+    for (size_t i = 0; i < plan.tiles.size(); ++i) {
+      tiles_mn[2 * i] = plan.tiles[i].x;
+      tiles_mn[2 * i + 1] = plan.tiles[i].y;
+    }
+  }
+  return WLD_OK;
+}
+
 int wld_fetch_pairs(wld_ctx* c, wld_pair* out, uint64_t cap, int flags, uint64_t* n_written) {
   WLD_CHECK_CTX(c);
   if (c->stage < Stage::Paired) return c->fail(WLD_ERR_STATE, "wld_fetch_pairs before wld_ld_pairs");

@@ -1,0 +1,194 @@
+// main.cpp — the `weighted_ld` command-line tool on the B200 library: same long flags, defaults,
+// stage order, stderr log lines and TSV outputs as the reference binary
+// (rust/weighted_ld/src/main.rs:14-213).  Extension: --gpus N (tile-partitioned pair stage).
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <iostream>
+#include <string>
+
+#include "weighted_ld.hpp"
+
+using namespace weighted_ld;
+using Clock = std::chrono::steady_clock;
+
+namespace {
+int g_level = 3;  // 0 off, 1 error, 2 warn, 3 info, 4 debug  (env_logger default "info", main.rs:122)
+
+void init_logger() {
+  const char* e = std::getenv("RUST_LOG");
+  if (!e) return;
+  std::string s(e);
+  for (auto& ch : s) ch = (char)std::tolower(ch);
+  if (s == "off") g_level = 0;
+  else if (s == "error") g_level = 1;
+  else if (s == "warn") g_level = 2;
+  else if (s == "info") g_level = 3;
+  else if (s == "debug" || s == "trace") g_level = 4;
+}
+void log_line(int level, const char* name, const std::string& msg) {
+  if (level > g_level) return;
+  char ts[32];
+  std::time_t t = std::time(nullptr);
+  std::strftime(ts, sizeof ts, "%Y-%m-%dT%H:%M:%SZ", std::gmtime(&t));
+  std::fprintf(stderr, "[%s %-5s weighted_ld] %s\n", ts, name, msg.c_str());
+}
+#define INFO(msg) log_line(3, "INFO", msg)
+#define DEBUG(msg) log_line(4, "DEBUG", msg)
+
+// Rust `{:?}` of a Duration: largest unit with a non-zero integer part, fraction trimmed.
+std::string fmt_duration(Clock::duration d) {
+  const double ns = (double)std::chrono::duration_cast<std::chrono::nanoseconds>(d).count();
+  char b[64];
+  auto trim = [&](double v, const char* unit) {
+    std::snprintf(b, sizeof b, "%.9f", v);
+    std::string s(b);
+    while (!s.empty() && s.back() == '0') s.pop_back();
+    if (!s.empty() && s.back() == '.') s.pop_back();
+    return s + unit;
+  };
+  if (ns >= 1e9) return trim(ns / 1e9, "s");
+  if (ns >= 1e6) return trim(ns / 1e6, "ms");
+  if (ns >= 1e3) return trim(ns / 1e3, "\xc2\xb5s");
+  return trim(ns, "ns");
+}
+// human_format::Formatter (1.0.3) defaults: 2 decimals, separator " ", SI suffixes, optional units.
+std::string human(double v, const char* units = "") {
+  static const char* suf[] = {"", "k", "M", "G", "T", "P", "E", "Z", "Y"};
+  int i = 0;
+  while (std::fabs(v) >= 1000.0 && i < 8) {
+    v /= 1000.0;
+    ++i;
+  }
+  char b[64];
+  std::snprintf(b, sizeof b, "%.2f %s%s", v, suf[i], units);
+  return b;
+}
+
+struct Opt {  // main.rs:19-68
+  std::string fasta_input, weights_output, pair_output;
+  float min_acgt = 0.8f, min_minor = 0.02f, max_minor = 0.5f, r2_threshold = 0.1f;
+  bool unweighted = false;
+  int gpus = 1;
+};
+
+void usage(FILE* f) {
+  std::fputs(
+      "weighted_ld 0.1.0\nA tool for computing sequence weighted linkage disequilibrium\n\n"
+      "USAGE:\n    weighted_ld [FLAGS] [OPTIONS] --fasta-input <fasta-input> --pair-output <pair-output>\n\n"
+      "FLAGS:\n    -h, --help          Prints help information\n"
+      "        --unweighted    Use unit weights instead of Henikoff weights\n"
+      "    -V, --version       Prints version information\n\n"
+      "OPTIONS:\n        --fasta-input <fasta-input>          The source file to load\n"
+      "        --max-minor <max-minor>              Maximum fraction of minor symbols for a site to be considered [default: 0.5]\n"
+      "        --min-acgt <min-acgt>                Minimum fractions of ACTG for a site to be considered [default: 0.8]\n"
+      "        --min-minor <min-minor>              Minimum fraction of minor symbols for a site to be considered [default: 0.02]\n"
+      "        --pair-output <pair-output>          Filename to write the per-pair weighted LD figures to, in Tab Separated Value format\n"
+      "        --r2-threshold <r2-threshold>        Minimum value of R2 to be included in the output [default: 0.1]\n"
+      "        --weights-output <weights-output>    Filename to write the per-sequence weights to, in Tab Separated Value format\n"
+      "        --gpus <gpus>                        (B200 build) number of GPUs for the pair stage [default: 1]\n",
+      f);
+}
+
+bool parse(int argc, char** argv, Opt& o) {
+  auto need = [&](int& i, const char* flag) -> const char* {
+    const char* eq = std::strchr(argv[i], '=');
+    if (eq) return eq + 1;
+    if (i + 1 >= argc) {
+      std::fprintf(stderr, "error: The argument '%s <value>' requires a value but none was supplied\n", flag);
+      std::exit(1);
+    }
+    return argv[++i];
+  };
+  auto is = [&](const char* a, const char* flag) {
+    const size_t n = std::strlen(flag);
+    return std::strncmp(a, flag, n) == 0 && (a[n] == 0 || a[n] == '=');
+  };
+  for (int i = 1; i < argc; ++i) {
+    const char* a = argv[i];
+    if (!std::strcmp(a, "-h") || !std::strcmp(a, "--help")) { usage(stdout); std::exit(0); }
+    if (!std::strcmp(a, "-V") || !std::strcmp(a, "--version")) { std::puts("weighted_ld 0.1.0"); std::exit(0); }
+    if (!std::strcmp(a, "--unweighted")) o.unweighted = true;
+    else if (is(a, "--fasta-input")) o.fasta_input = need(i, "--fasta-input");
+    else if (is(a, "--pair-output")) o.pair_output = need(i, "--pair-output");
+    else if (is(a, "--weights-output")) o.weights_output = need(i, "--weights-output");
+    else if (is(a, "--min-acgt")) o.min_acgt = std::strtof(need(i, "--min-acgt"), nullptr);
+    else if (is(a, "--min-minor")) o.min_minor = std::strtof(need(i, "--min-minor"), nullptr);
+    else if (is(a, "--max-minor")) o.max_minor = std::strtof(need(i, "--max-minor"), nullptr);
+    else if (is(a, "--r2-threshold")) o.r2_threshold = std::strtof(need(i, "--r2-threshold"), nullptr);
+    else if (is(a, "--gpus")) o.gpus = std::atoi(need(i, "--gpus"));
+    else {
+      std::fprintf(stderr, "error: Found argument '%s' which wasn't expected, or isn't valid in this context\n\nUSAGE:\n    weighted_ld [FLAGS] [OPTIONS] --fasta-input <fasta-input> --pair-output <pair-output>\n\nFor more information try --help\n", a);
+      return false;
+    }
+  }
+  if (o.fasta_input.empty() || o.pair_output.empty()) {
+    std::fprintf(stderr, "error: The following required arguments were not provided:\n%s%s\nUSAGE:\n    weighted_ld [FLAGS] [OPTIONS] --fasta-input <fasta-input> --pair-output <pair-output>\n\nFor more information try --help\n",
+                 o.fasta_input.empty() ? "    --fasta-input <fasta-input>\n" : "", o.pair_output.empty() ? "    --pair-output <pair-output>\n" : "");
+    return false;
+  }
+  return true;
+}
+}  // namespace
+
+int main(int argc, char** argv) {
+  init_logger();
+  Opt opt;
+  if (!parse(argc, argv, opt)) return 1;
+  try {
+    std::vector<int> devices;
+    for (int g = 0; g < std::max(1, opt.gpus); ++g) devices.push_back(g);
+
+    auto sw = Clock::now();
+    MultiSequence multiseq = read_fasta(opt.fasta_input);                 // main.rs:129
+    SiteSet siteset = SiteSet::from_multiseq(multiseq, devices);          // main.rs:130
+    INFO("Loaded fasta file in " + fmt_duration(Clock::now() - sw));      // main.rs:131
+    INFO("    " + std::to_string(siteset.n_seqs()) + " sequences, " + std::to_string(siteset.n_sites()) + " sites");
+
+    sw = Clock::now();
+    SiteSet filtered = siteset.filter_by(opt.min_acgt, opt.min_minor, opt.max_minor);  // main.rs:139-143
+    INFO("Computed + filtered sites of interest in " + fmt_duration(Clock::now() - sw));
+    INFO("    Found " + std::to_string(filtered.n_sites()) + " sites of interest");
+
+    std::vector<float> weights;
+    if (opt.unweighted) {
+      weights.assign((size_t)siteset.n_seqs(), 1.0f);                     // main.rs:150-153
+    } else {
+      sw = Clock::now();
+      weights = henikoff_weights(filtered);                               // main.rs:156
+      INFO("Computed Henikoff weights in " + fmt_duration(Clock::now() - sw));
+    }
+    if (!opt.weights_output.empty()) {                                    // main.rs:161-164
+      INFO("Writing weights to \"" + opt.weights_output + "\"");
+      write_henikoff_weights(opt.weights_output, weights);
+    }
+
+    INFO("Beginning pairwise weighted LD computation");                   // main.rs:166
+    sw = Clock::now();
+    const int64_t L = filtered.n_sites();
+    const uint64_t total_pairs = (uint64_t)((L - 1) * (L - 2) / 2);       // main.rs:168 (sic)
+    PairStore store = all_weighted_ld_pairs(filtered, weights, opt.r2_threshold, [&](size_t computed) {
+      if (g_level >= 4) DEBUG("progress " + std::to_string(computed) + "/" + std::to_string(total_pairs));
+    });
+    const auto dur = Clock::now() - sw;
+    INFO("Finished computing pairwise weighted LD stats in " + fmt_duration(dur));
+    const double secs = std::chrono::duration<double>(dur).count();
+    INFO("    " + human((double)total_pairs) + " pairs computed at ~" + human((double)total_pairs / secs, "pairs/s") + ", " +
+         human((double)store.len()) + " passed threshold");               // main.rs:196-205
+
+    INFO("Writing output to \"" + opt.pair_output + "\"");                // main.rs:207
+    sw = Clock::now();
+    write_pair_stats(opt.pair_output, store);                             // main.rs:209
+    INFO("Finshed writing output in " + fmt_duration(Clock::now() - sw)); // main.rs:210 (sic)
+    return 0;
+  } catch (const Panic& p) {
+    std::fprintf(stderr, "thread 'main' panicked at '%s'\n", p.what());
+    return 101;  // Rust's panic exit code
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "Error: %s\n", e.what());                        // main.rs:121 (io::Error via `?`)
+    return 1;
+  }
+}

@@ -1,0 +1,77 @@
+// weighted_ld.hpp — C++ host-side mirror of the reference's Rust crate API (rust/weighted_ld/src/lib.rs)
+// on top of the C ABI (include/wld.h).  Same names, argument meaning and error behaviour:
+//   read_fasta                lib.rs:277-307     MultiSequence (rows keep their newline column)
+//   SiteSet::from_multiseq    lib.rs:176-206     throws where the reference panics (lib.rs:180-182)
+//   SiteSet::filter_by        lib.rs:230-251 + is_site_of_interest lib.rs:310-338 + main.rs:139
+//   henikoff_weights          lib.rs:340-358
+//   all_weighted_ld_pairs     lib.rs:578-684     -> PairStore (lib.rs:529-576), reference order
+// No CPU fallback: every stage below the text parser is a CUDA kernel in libwld.so.
+#pragma once
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/wld.h"
+
+namespace weighted_ld {
+
+struct WldError : std::runtime_error {
+  int status;
+  WldError(int s, const std::string& m) : std::runtime_error(m), status(s) {}
+};
+struct Panic : std::runtime_error {  // the reference's panic!() sites
+  using std::runtime_error::runtime_error;
+};
+
+struct MultiSequence {                 // lib.rs:153-156
+  std::string source;
+  int64_t n_seqs = 0, n_cols = 0, row_stride = 0;
+  std::vector<uint8_t> chars;          // n_seqs rows, pitch row_stride (16-byte multiple), newline column kept
+  std::vector<std::string> names;      // lib.rs:143-146 (empty = None)
+  bool ragged = false;                 // rows of unequal length: from_multiseq panics (lib.rs:180-182)
+};
+
+MultiSequence read_fasta(const std::string& path);  // throws std::ios_base::failure on I/O errors
+
+struct LdStats { float r2, d, d_prime; };          // lib.rs:382-387
+
+class PairStore {                                   // lib.rs:529-576
+ public:
+  std::vector<wld_pair> pairs;                      // reference order, parent indices
+  uint64_t pairs_computed = 0;
+  size_t len() const { return pairs.size(); }
+};
+
+class SiteSet {                                     // lib.rs:158-275
+ public:
+  // One context per GPU; the alignment is replicated to each.
+  static SiteSet from_multiseq(const MultiSequence& ms, const std::vector<int>& devices = {0});
+  SiteSet filter_by(float min_acgt_frac, float min_minor, float max_minor) const;  // main.rs:139-143
+  int64_t n_sites() const;                          // lib.rs:254
+  int64_t n_seqs() const;                           // lib.rs:259
+  int64_t parent_site_index(int64_t idx) const;     // lib.rs:263
+  std::vector<int64_t> site_map() const;
+  ~SiteSet();
+  SiteSet(SiteSet&&) noexcept;
+  SiteSet(const SiteSet&) = delete;
+
+  struct Impl;
+  std::shared_ptr<Impl> impl;                       // shared with the filtered view (same contexts)
+  bool filtered = false;
+ private:
+  SiteSet() = default;
+};
+
+std::vector<float> henikoff_weights(const SiteSet& data);  // lib.rs:340
+PairStore all_weighted_ld_pairs(const SiteSet& site_set, const std::vector<float>& weights, float r2_threshold,
+                                const std::function<void(size_t)>& progress_report);  // lib.rs:578
+
+// main.rs:70-119
+void write_henikoff_weights(const std::string& path, const std::vector<float>& weights);
+void write_pair_stats(const std::string& path, const PairStore& pairs);
+std::string format_f3(float v);  // Rust `{:.3}`
+
+}  // namespace weighted_ld
