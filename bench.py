@@ -62,6 +62,15 @@ def peaks() -> dict:
     return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "source": "B200_PROFILING.md fallback (of fallback)"}
 
 
+def int8_peak() -> dict:
+    """INT8 tensor peak measured on this pool's B200 with tools/measure_peaks.py (cuBLASLt int8 GEMM
+    8192^3 through torch._int_mm, same method as MEASURED_PEAKS.json uses for bf16)."""
+    p = ROOT / "profiles" / "r01_measured_int8_peak.json"
+    d = json.loads(p.read_text())
+    return {"sustained": d["int8_tops_sustained"], "burst": d["int8_tops"],
+            "source": "profiles/r01_measured_int8_peak.json (of measured: torch._int_mm int8 8192^3, tools/measure_peaks.py)"}
+
+
 class ClockSampler:
     """Samples SM clock and throttle reasons during the timed region (NVML)."""
 
@@ -268,9 +277,15 @@ def run_ours(args):
     algo_flop = 8.0 * n_seqs * info.n_limbs * state["done"]      # 8*N flop per pair per limb pass
     useful_flop = 8.0 * n_seqs * state["done"]
     achieved = algo_flop / (pair_ms * 1e-3) / 1e12
-    roof = {"bound": "tensor", "kernel": "pair_umma_kernel" if info.kernel == 0 else "pair_simt_kernel",
-            "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
-            "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
+    if info.kernel == 2:
+        ip = int8_peak()
+        peak, peak_src, kname = ip["sustained"], ip["source"] + ", sustained int8 figure (kernel timed inside a long step)", "pair_umma_kernel<NL, i8>"
+    else:
+        peak, peak_src = pk["bf16_sustained"], pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)"
+        kname = "pair_umma_kernel<NL, bf16>" if info.kernel == 0 else "pair_simt_kernel"
+    roof = {"bound": "tensor", "kernel": kname,
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_source": peak_src,
             "achieved_useful": useful_flop / (pair_ms * 1e-3) / 1e12,
             "executed": info.executed_flop / (pair_ms * 1e-3) / 1e12,
             "algorithmic_flop_per_pair": 8 * n_seqs * info.n_limbs, "n_limbs": info.n_limbs, "limb_bits": info.limb_bits,
@@ -286,7 +301,10 @@ def run_ours(args):
         line = {
             "metric": "weighted LD site-pairs/sec", "value": total_pairs / (ms * 1e-3), "unit": "site-pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": n_warm, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16 limbs x fp32 accumulate (exact), f64 epilogue",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": {0: "bf16 limbs x fp32 accumulate (exact integers), f64 epilogue",
+                      1: "f64 (SIMT verification kernel)",
+                      2: "u8 limbs x s32 accumulate (exact integers), f64 epilogue"}[info.kernel],
             "data": "synthetic",
             "config": {"workload": desc, "n_seqs": n_seqs, "n_cols": n_cols, "n_kept": n_kept, "site_pairs": total_pairs,
                        "survivors": surv_all, "r2_threshold": R2_THRESHOLD, "filter": list(FILTER),
@@ -317,7 +335,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5", choices=list(WORKLOADS))
     ap.add_argument("--limbs", type=int, default=0)
-    ap.add_argument("--kernel", default="", choices=["", "umma", "simt"])
+    ap.add_argument("--kernel", default="", choices=["", "umma", "bf16", "i8", "simt"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--profile", action="store_true", help="profiling run: honour --warmup < 3, skip the e2e leg (numbers are not bench values)")
     args = ap.parse_args()

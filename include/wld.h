@@ -78,8 +78,10 @@ enum {
 
 /* pair-kernel selection for wld_set_pair_kernel */
 enum {
-  WLD_PAIR_KERNEL_UMMA = 0, /* tcgen05/TMEM Gram tiles fed by TMA, fused epilogue (default) */
-  WLD_PAIR_KERNEL_SIMT = 1  /* CUDA-core FP64 kernel, same exact sums and epilogue; verification path */
+  WLD_PAIR_KERNEL_UMMA = 0,   /* tcgen05/TMEM Gram tiles fed by TMA, bf16 limbs x fp32 accumulate (kind::f16) */
+  WLD_PAIR_KERNEL_SIMT = 1,   /* CUDA-core FP64 kernel, same exact sums and epilogue; verification path */
+  WLD_PAIR_KERNEL_UMMA_I8 = 2 /* same tcgen05 kernel, u8 limbs x s32 accumulate (kind::i8): half the operand
+                                 bytes and energy per MAC, exact for any n_seqs; the DEFAULT */
 };
 
 /* stage ids for wld_stage_ms */

@@ -162,12 +162,13 @@ def test_pairs_simt_bit_exact(wld, oracle, n_seqs, n_cols, thr):
     assert_pairs_identical(gpu, ref)
 
 
+@pytest.mark.parametrize("kernel", ["bf16", "i8"])
 @pytest.mark.parametrize("n_limbs", [3, 1, 2, 4])
 @pytest.mark.parametrize("n_seqs,n_cols,thr", PAIR_CASES)
-def test_pairs_umma_bit_exact(wld, oracle, n_seqs, n_cols, thr, n_limbs):
+def test_pairs_umma_bit_exact(wld, oracle, n_seqs, n_cols, thr, n_limbs, kernel):
     chars = synth(n_seqs, n_cols, seed=n_seqs + n_cols, block=60, clonal=True)
-    gpu, done, info, w32, _ = run_gpu_pairs(wld, chars, "umma", thr, n_limbs=n_limbs)
-    assert info.kernel == 0 and info.n_limbs == n_limbs and info.weight_bits == 8 * n_limbs
+    gpu, done, info, w32, _ = run_gpu_pairs(wld, chars, kernel, thr, n_limbs=n_limbs)
+    assert info.kernel == {"bf16": 0, "i8": 2}[kernel] and info.n_limbs == n_limbs and info.weight_bits == 8 * n_limbs
     fs, ref, computed = oracle_pairs(oracle, chars, w32, info.weight_bits, thr)
     assert done == computed
     assert_pairs_identical(gpu, ref)
@@ -193,10 +194,11 @@ def test_pairs_close_to_reference_faithful_f32(wld, oracle):
     assert (got ^ want) <= band
 
 
-def test_umma_matches_simt_all_pairs_multi_tile(wld):
-    # several M and N tiles, ragged edges, K not a multiple of 64, every pair emitted
+@pytest.mark.parametrize("kernel", ["bf16", "i8"])
+def test_umma_matches_simt_all_pairs_multi_tile(wld, kernel):
+    # several M and N tiles, ragged edges, K not a multiple of the K block, every pair emitted
     chars = synth(1111, 1900, seed=77, block=100)
-    a = run_gpu_pairs(wld, chars, "umma", -1.0)
+    a = run_gpu_pairs(wld, chars, kernel, -1.0)
     b = run_gpu_pairs(wld, chars, "simt", -1.0)
     assert a[1] == b[1] and len(a[0]) == len(b[0]) > 500000
     assert a[0].tobytes() == b[0].tobytes()
@@ -205,7 +207,7 @@ def test_umma_matches_simt_all_pairs_multi_tile(wld):
 def test_fp32_accumulation_exact_at_the_limit(wld):
     """Worst case of the exactness argument: every top limb = 256 (all weights max, one slightly
     smaller so that the single-limb shortcut for equal weights is not taken) and N = 65535, so an
-    accumulator reaches 256*65535 = 2^24 - 256 in fp32.  The tensor path must equal the FP64 SIMT path."""
+    accumulator reaches 255*65535 = 2^24 - 65791 in fp32.  The tensor path must equal the FP64 SIMT path."""
     n = 65535
     chars = synth(n, 96, seed=1, block=32)
     w = np.ones(n, np.float32)
@@ -214,12 +216,15 @@ def test_fp32_accumulation_exact_at_the_limit(wld):
     b = run_gpu_pairs(wld, chars, "simt", -1.0, weights=w)
     assert a[2].n_limbs == 3 and a[2].limb_bits == 8
     assert len(a[0]) > 1000 and a[0].tobytes() == b[0].tobytes()
+    c = run_gpu_pairs(wld, chars, "i8", -1.0, weights=w)  # s32 accumulation: exact with room to spare
+    assert c[2].limb_bits == 8 and c[0].tobytes() == b[0].tobytes()
 
 
-def test_unweighted_uses_one_limb_and_matches(wld, oracle):
+@pytest.mark.parametrize("kernel", ["bf16", "i8"])
+def test_unweighted_uses_one_limb_and_matches(wld, oracle, kernel):
     chars = synth(500, 400, seed=4, block=50)
     w = np.ones(500, np.float32)  # main.rs:150-153
-    gpu, done, info, _, _ = run_gpu_pairs(wld, chars, "umma", 0.1, weights=w)
+    gpu, done, info, _, _ = run_gpu_pairs(wld, chars, kernel, 0.1, weights=w)
     assert info.n_limbs == 1 and info.weight_bits == 0
     fs, ref, computed = oracle_pairs(oracle, chars, w, 0, 0.1)
     assert done == computed

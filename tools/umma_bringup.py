@@ -29,15 +29,20 @@ for (n, l, limbs) in [(64, 100, 1), (64, 100, 3), (200, 300, 3), (1000, 900, 3),
     chars = make_alignment(n, l, seed=n + l, block=60, clonal=True)
     w = np.ones(n, np.float32) if limbs == 1 else None
     k, s, sd, sms, _ = run(chars, "simt", limbs=limbs, weights=w)
-    try:
-        k2, u, ud, ums, info = run(chars, "umma", limbs=limbs, weights=w)
-    except Exception as e:  # noqa
-        print(f"[{n}x{l} limbs={limbs}] UMMA FAILED: {e}")
-        ok = False
-        break
-    same = len(s) == len(u) and s.tobytes() == u.tobytes()
-    print(f"[{n}x{l} limbs={limbs}] kept={k} simt: {len(s)} pairs {sms:.3f} ms | umma: {len(u)} pairs {ums:.3f} ms "
-          f"tiles={info.tiles} limb_bits={info.limb_bits} done {sd}/{ud} -> {'IDENTICAL' if same else 'DIFFERENT'}")
+    same = True
+    for kern in ("bf16", "i8"):
+        try:
+            k2, u, ud, ums, info = run(chars, kern, limbs=limbs, weights=w)
+        except Exception as e:  # noqa
+            print(f"[{n}x{l} limbs={limbs}] {kern} FAILED: {e}")
+            ok = False
+            same = False
+            break
+        same = len(s) == len(u) and s.tobytes() == u.tobytes()
+        print(f"[{n}x{l} limbs={limbs}] kept={k} simt: {len(s)} pairs {sms:.3f} ms | {kern}: {len(u)} pairs {ums:.3f} ms "
+              f"tiles={info.tiles} limb_bits={info.limb_bits} done {sd}/{ud} -> {'IDENTICAL' if same else 'DIFFERENT'}")
+        if not same:
+            break
     if not same:
         ok = False
         sm = {(int(p['site_a']), int(p['site_b'])): p for p in s}

@@ -5,7 +5,7 @@ behind the C ABI of include/wld.h (libwld.so).  This package is the thin host-si
 reference's Rust API; it has no CPU or PyTorch fallback and raises if libwld.so is missing.
 """
 from ._lib import (FETCH_KEPT_INDEX, FETCH_PARENT_INDEX, FETCH_UNORDERED, PAIR_DTYPE, PAIR_KERNEL_SIMT,
-                   PAIR_KERNEL_UMMA, STAGE_FILTER, STAGE_HENIKOFF, STAGE_HISTOGRAM, STAGE_LOAD, STAGE_NAMES,
+                   PAIR_KERNEL_UMMA, PAIR_KERNEL_UMMA_I8, STAGE_FILTER, STAGE_HENIKOFF, STAGE_HISTOGRAM, STAGE_LOAD, STAGE_NAMES,
                    STAGE_PAIR, STAGE_PAIR_PREP, WldError)
 from .api import (Context, MultiSequence, PairStore, SiteSet, all_weighted_ld_pairs, format_f3, henikoff_weights,
                   merge_shards, pair_order_key, plan_tiles, read_fasta, single_weighted_ld_pair, write_henikoff_weights, write_pair_stats)

@@ -19,7 +19,7 @@ assert PAIR_DTYPE.itemsize == 20
 WLD_OK = 0
 INPUT_ASCII, INPUT_CODES, INPUT_DEVICE = 0, 1, 2
 FETCH_PARENT_INDEX, FETCH_KEPT_INDEX, FETCH_UNORDERED = 0, 1, 2
-PAIR_KERNEL_UMMA, PAIR_KERNEL_SIMT = 0, 1
+PAIR_KERNEL_UMMA, PAIR_KERNEL_SIMT, PAIR_KERNEL_UMMA_I8 = 0, 1, 2
 STAGE_LOAD, STAGE_HISTOGRAM, STAGE_FILTER, STAGE_HENIKOFF, STAGE_PAIR_PREP, STAGE_PAIR = range(6)
 STAGE_NAMES = ["load", "histogram", "filter", "henikoff", "pair_prep", "pair"]
 STATUS_NAMES = {0: "OK", 1: "INVALID", 2: "STATE", 3: "CUDA", 4: "NOMEM", 5: "UNSUPPORTED", 6: "PANIC"}

@@ -83,7 +83,7 @@ class Context:
 
     def set_pair_kernel(self, kind: int | str):
         if isinstance(kind, str):
-            kind = {"umma": L.PAIR_KERNEL_UMMA, "simt": L.PAIR_KERNEL_SIMT}[kind]
+            kind = {"umma": L.PAIR_KERNEL_UMMA, "bf16": L.PAIR_KERNEL_UMMA, "simt": L.PAIR_KERNEL_SIMT, "i8": L.PAIR_KERNEL_UMMA_I8}[kind]
         self._check(self._lib.wld_set_pair_kernel(self._h, kind))
 
     def set_pair_capacity(self, pairs: int):

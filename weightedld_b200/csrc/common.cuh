@@ -56,7 +56,8 @@ struct PairGeom {
   int limb_bits = 8;     // b
   int rows_per_site = 6; // RPS = 2*NL   rows of the limb operand per kept site
   int sites_per_group = 21; // SPG = floor(128 / RPS) kept sites per 128-row group of the limb operand
-  int64_t k_padded = 0;  // sequences rounded up to 64
+  int elem_bytes = 2;    // operand element: 2 = bf16, 1 = u8
+  int64_t k_padded = 0;  // sequences rounded up to one K block (64 bf16 / 128 u8)
   int64_t a_rows = 0;    // indicator operand rows, padded to 128 (2 rows per site)
   int64_t b_groups = 0;  // 128-row groups of the limb operand
 };
@@ -74,7 +75,7 @@ struct wld_ctx {
   // options
   int part = 0, nparts = 1;
   int n_limbs_opt = 3;
-  int pair_kernel = WLD_PAIR_KERNEL_UMMA;
+  int pair_kernel = WLD_PAIR_KERNEL_UMMA_I8;  // fastest exact path on sm_100a; bf16 and SIMT selectable
   uint64_t pair_cap_opt = 0;
 
   // stage 1
@@ -115,6 +116,11 @@ struct wld_ctx {
   uint64_t pairs_computed = 0;
   wld_pair_info info{};
   float last_thr = 0.f;
+  // cached tile schedule on the device (key: n_kept, n_limbs, part, nparts, kernel)
+  int64_t plan_key[5] = {-1, -1, -1, -1, -1};
+  int64_t plan_tiles_n = 0;
+  uint64_t plan_pairs = 0;
+  double weight_sum = 0.0;         // sum of the fixed-point weights q (upper bound of every pair's T)
 
   wld::StageTimer timers[WLD_STAGE_COUNT];
 
@@ -166,8 +172,10 @@ int run_filter(wld_ctx* c, bool keep_all, float min_acgt, float min_minor, float
                ScopedStageTimer& tm);                                      // encode_filter.cu
 int run_henikoff(wld_ctx* c, ScopedStageTimer& tm);                        // henikoff.cu
 int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm);                       // pair_prep.cu
-int run_pair_simt(wld_ctx* c, float thr, ScopedStageTimer& tm);            // pair_simt.cu
-int run_pair_umma(wld_ctx* c, float thr, ScopedStageTimer& tm);            // pair_umma.cu
+// The pair launchers bracket ONLY the kernel launch with the WLD_STAGE_PAIR timer (host-side
+// planning and the tile-list upload happen before the start event).
+int run_pair_simt(wld_ctx* c, float thr);                                  // pair_simt.cu
+int run_pair_umma(wld_ctx* c, float thr);                                  // pair_umma.cu
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 

@@ -46,6 +46,26 @@ __device__ __forceinline__ bool ld_prefilter(double AB, double Ab, double aB, do
   return den > 0.0 && num >= thr_lo * den;
 }
 
+// The same test in fp32, for inputs that are fp32 ROUNDINGS of the exact sums (relative error of each
+// input <= 3*2^-24, pre-scaled by a power of two so that T <= 2^21: no overflow in n*n, no
+// underflow of den).  Error budget: |fl(A*B) - fl(AB*T) - exact| <= 8*2^-24*(A*B + AB*T) -> covered by
+// the 2e-6 term; den carries <= 10*2^-24 relative error -> covered by thr_lo_f = thr_lo*(1 -+ 1e-5).
+// Exact zeros stay exact zeros (sums of non-negative terms), so den > 0 is decided exactly.
+// The FP64 pipe of B200 is narrow (profiles/r01_ncu_pair_umma_c3_v1.md: stall_math on DADD/DFMA),
+// so only candidates that pass this test pay for the f64 statistics.
+__device__ __forceinline__ bool ld_prefilter_f32(float AB, float Ab, float aB, float ab, float thr_lo_f,
+                                                 bool thr_negative) {
+  const float A = AB + Ab;
+  const float B = AB + aB;
+  const float a = aB + ab;
+  const float b = Ab + ab;
+  const float T = A + a;
+  const float p1 = A * B, p2 = AB * T;
+  const float n = fabsf(p1 - p2) + 2e-6f * (p1 + p2);  // upper bound of |A*B - AB*T|
+  const float den = (A * a) * (B * b);
+  return den > 0.0f && (thr_negative || n * n >= thr_lo_f * den);
+}
+
 __host__ __device__ inline double ld_thr_lo(float thr) {
   const double t = (double)thr;
   return t - (t < 0 ? -t : t) * 1e-6 - 1e-24;

@@ -5,17 +5,21 @@
 // (lib.rs:462-479).  With indicator columns Maj_i[s] = [code==major_i], Min_i[s] = [code==minor_i]
 // those sums are the 2x2 block  (Maj_i,Min_i)^T diag(w) (Maj_j,Min_j)  of a Gram matrix.
 //
-// Exactness: weights become integers q[s] = rint(w[s]/max(w) * 2^(b*NL)) and are split into NL
-// limbs of b bits (top limb may equal 2^b).  Limbs <= 256 and indicators are exact in bf16, every
-// product is a small integer, and fp32 accumulation is exact while a sum stays <= 2^24, which the
-// host checks from the limb column sums (shrinking b if ever needed).  The Gram is therefore an
-// exact integer computation, independent of tile order and GPU count.
+// Exactness: weights become integers q[s] = rint(w[s]/max(w) * (2^(b*NL) - 1)) and are split into NL
+// limbs of b bits (<= 255).  Two operand encodings, both exact:
+//   bf16 (kind::f16, fp32 accumulate): limbs and indicators are exact in bf16, every product is a
+//        small integer, and fp32 accumulation is exact while a sum stays <= 2^24, which the host
+//        checks from the limb column sums (shrinking b if ever needed);
+//   u8   (kind::i8, s32 accumulate): exact for any n_seqs < 2^31/255.
+// The Gram is therefore an exact integer computation, independent of tile order and GPU count.
 //
-// Operands (bf16, K-major = sequence index contiguous, K padded to 64 with zeros):
+// Operands (K-major = sequence index contiguous, K padded with zeros to one 128-byte swizzle atom):
 //   opA : [a_rows][Kp]       row 2*i+alpha           = indicator (alpha: 0 major, 1 minor) of site i
 //   opB : [groups*128][Kp]   row g*128 + r*2NL + beta*NL + l = indicator_beta(site g*SPG+r) * limb_l
 //         SPG = floor(128/(2NL)) sites per 128-row group; unused rows of a group are zero.
 // HBM-bound: reads n_kept*Kp code bytes (twice), writes (2 + 2NL)*2 bytes per (site, sequence).
+#include <cmath>
+
 #include "common.cuh"
 
 namespace wld {
@@ -70,18 +74,17 @@ __global__ void __launch_bounds__(1024) quantize_kernel(const float* __restrict_
   }
   if (threadIdx.x == 0) *flags = (mn == mx) ? 2 : 0;  // bit1: all weights equal
   const int total_bits = n_limbs * limb_bits;
-  const double scale = (double)(1ull << total_bits);
+  const double scale = total_bits > 0 ? (double)((1ull << total_bits) - 1ull) : 1.0;  // q <= 2^B - 1: limbs fit u8
   const uint32_t limb_mask = (1u << limb_bits) - 1u;
   unsigned long long sums[4] = {0, 0, 0, 0};
   for (int64_t s = threadIdx.x; s < ldc; s += blockDim.x) {
-    unsigned long long qi = 0;  // may equal 2^total_bits (up to 2^32) for the largest weight
+    unsigned long long qi = 0;
     if (s < n_seqs) qi = (unsigned long long)rint(__dmul_rn(__ddiv_rn((double)w[s], (double)mx), scale));
     q[s] = (double)qi;
     for (int l = 0; l < n_limbs; ++l) {
       const int shift = limb_bits * (n_limbs - 1 - l);
-      uint32_t v = (uint32_t)(qi >> shift);
-      if (l > 0) v &= limb_mask;  // the top limb keeps the carry (q may equal 2^total_bits)
-      limbs[(int64_t)l * ldc + s] = bf16_bits_of_small_int(v);
+      uint32_t v = (uint32_t)(qi >> shift) & (limb_bits > 0 ? limb_mask : 1u);
+      limbs[(int64_t)l * ldc + s] = (uint16_t)v;  // raw limb value 0..255; converted at expansion
       sums[l] += v;
     }
   }
@@ -99,69 +102,93 @@ __global__ void __launch_bounds__(1024) quantize_kernel(const float* __restrict_
   }
 }
 
-// 8 codes -> 8 bf16 values: value_bits where code == sym, else 0.
-__device__ __forceinline__ uint4 select8(uint2 codes, int sym, const uint16_t* vals /*8, or nullptr => 1.0*/) {
-  uint32_t out[4];
+// Operand element encodings: bf16 bit pattern of a small integer (exact for v <= 256), or the u8 itself.
+template <bool kI8>
+__device__ __forceinline__ uint32_t elem_of(uint32_t v) {
+  return kI8 ? v : (uint32_t)bf16_bits_of_small_int(v);
+}
+
+// 8 codes -> 8 operand elements: vals[k] where code == sym, else 0.  Stored as 16 B (bf16) or 8 B (u8).
+template <bool kI8>
+__device__ __forceinline__ void store_select8(void* dst, uint2 codes, int sym, const uint32_t* vals) {
+  uint32_t e[8];
 #pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    const uint32_t word = p < 2 ? codes.x : codes.y;
-    const uint32_t c0 = (word >> (16 * (p & 1))) & 0xffu;
-    const uint32_t c1 = (word >> (16 * (p & 1) + 8)) & 0xffu;
-    const uint32_t v0 = vals ? vals[2 * p] : 0x3f80u;
-    const uint32_t v1 = vals ? vals[2 * p + 1] : 0x3f80u;
-    out[p] = ((int)c0 == sym ? v0 : 0u) | (((int)c1 == sym ? v1 : 0u) << 16);
+  for (int k = 0; k < 8; ++k) {
+    const uint32_t word = k < 4 ? codes.x : codes.y;
+    const int c = (int)((word >> (8 * (k & 3))) & 0xffu);
+    e[k] = c == sym ? vals[k] : 0u;
   }
-  return make_uint4(out[0], out[1], out[2], out[3]);
+  if (kI8) {
+    *reinterpret_cast<uint2*>(dst) = make_uint2(e[0] | (e[1] << 8) | (e[2] << 16) | (e[3] << 24),
+                                                e[4] | (e[5] << 8) | (e[6] << 16) | (e[7] << 24));
+  } else {
+    *reinterpret_cast<uint4*>(dst) =
+        make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
+  }
+}
+template <bool kI8>
+__device__ __forceinline__ void store_zero8(void* dst) {
+  if (kI8) *reinterpret_cast<uint2*>(dst) = make_uint2(0, 0);
+  else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
 }
 
 // opA: grid (K blocks of 2048, a_rows/2 sites).  Sites >= n_kept are zero rows.
+template <bool kI8>
 __global__ void __launch_bounds__(256) expand_a_kernel(const uint8_t* __restrict__ codes, int64_t ldc, int64_t n_kept,
                                                        const int8_t* __restrict__ maj, const int8_t* __restrict__ mnr,
-                                                       int64_t kp, uint16_t* __restrict__ opA) {
+                                                       int64_t kp, uint8_t* __restrict__ opA) {
+  constexpr int ES = kI8 ? 1 : 2;
   const int64_t i = blockIdx.y;
   const int64_t s0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8;
   if (s0 >= kp) return;
-  uint4 vmaj = make_uint4(0, 0, 0, 0), vmin = vmaj;
+  uint8_t* r0 = opA + ((2 * i) * kp + s0) * ES;
+  uint8_t* r1 = opA + ((2 * i + 1) * kp + s0) * ES;
   if (i < n_kept) {
     const uint2 cw = __ldg(reinterpret_cast<const uint2*>(codes + i * ldc + s0));
-    vmaj = select8(cw, maj[i], nullptr);  // maj/min == -1 never matches a code
-    vmin = select8(cw, mnr[i], nullptr);
+    uint32_t ones[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ones[k] = elem_of<kI8>(1u);
+    store_select8<kI8>(r0, cw, maj[i], ones);  // maj/min == -1 never matches a code
+    store_select8<kI8>(r1, cw, mnr[i], ones);
+  } else {
+    store_zero8<kI8>(r0);
+    store_zero8<kI8>(r1);
   }
-  *reinterpret_cast<uint4*>(opA + (2 * i) * kp + s0) = vmaj;
-  *reinterpret_cast<uint4*>(opA + (2 * i + 1) * kp + s0) = vmin;
 }
 
 // opB: grid (K blocks of 2048, groups*(SPG+1)).  blockIdx.y = g*(SPG+1) + r; r == SPG zero-fills the
 // unused tail rows of the group.
+template <bool kI8>
 __global__ void __launch_bounds__(256) expand_b_kernel(const uint8_t* __restrict__ codes, int64_t ldc, int64_t n_kept,
                                                        const int8_t* __restrict__ maj, const int8_t* __restrict__ mnr,
                                                        const uint16_t* __restrict__ limbs, int n_limbs, int spg,
-                                                       int64_t kp, uint16_t* __restrict__ opB) {
+                                                       int64_t kp, uint8_t* __restrict__ opB) {
+  constexpr int ES = kI8 ? 1 : 2;
   const int64_t g = blockIdx.y / (spg + 1);
   const int r = (int)(blockIdx.y % (spg + 1));
   const int rps = 2 * n_limbs;
   const int64_t s0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8;
   if (s0 >= kp) return;
-  const uint4 zero = make_uint4(0, 0, 0, 0);
   if (r == spg) {
-    for (int row = spg * rps; row < 128; ++row) *reinterpret_cast<uint4*>(opB + (g * 128 + row) * kp + s0) = zero;
+    for (int row = spg * rps; row < 128; ++row) store_zero8<kI8>(opB + ((g * 128 + row) * kp + s0) * ES);
     return;
   }
   const int64_t j = g * spg + r;
   const int64_t row0 = g * 128 + (int64_t)r * rps;
   if (j >= n_kept) {
-    for (int t = 0; t < rps; ++t) *reinterpret_cast<uint4*>(opB + (row0 + t) * kp + s0) = zero;
+    for (int t = 0; t < rps; ++t) store_zero8<kI8>(opB + ((row0 + t) * kp + s0) * ES);
     return;
   }
   const uint2 cw = __ldg(reinterpret_cast<const uint2*>(codes + j * ldc + s0));
   const int sm = maj[j], sn = mnr[j];
   for (int l = 0; l < n_limbs; ++l) {
     const uint4 lv = __ldg(reinterpret_cast<const uint4*>(limbs + (int64_t)l * ldc + s0));
-    uint16_t vals[8];
-    vals[0] = lv.x & 0xffff; vals[1] = lv.x >> 16; vals[2] = lv.y & 0xffff; vals[3] = lv.y >> 16;
-    vals[4] = lv.z & 0xffff; vals[5] = lv.z >> 16; vals[6] = lv.w & 0xffff; vals[7] = lv.w >> 16;
-    *reinterpret_cast<uint4*>(opB + (row0 + l) * kp + s0) = select8(cw, sm, vals);
-    *reinterpret_cast<uint4*>(opB + (row0 + n_limbs + l) * kp + s0) = select8(cw, sn, vals);
+    uint32_t vals[8] = {lv.x & 0xffffu, lv.x >> 16, lv.y & 0xffffu, lv.y >> 16,
+                        lv.z & 0xffffu, lv.z >> 16, lv.w & 0xffffu, lv.w >> 16};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) vals[k] = elem_of<kI8>(vals[k]);
+    store_select8<kI8>(opB + ((row0 + l) * kp + s0) * ES, cw, sm, vals);
+    store_select8<kI8>(opB + ((row0 + n_limbs + l) * kp + s0) * ES, cw, sn, vals);
   }
 }
 
@@ -171,6 +198,9 @@ int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm) {
   PairGeom& gm = c->geom;
   const int64_t n = c->n_seqs, L = c->n_kept;
   gm.n_limbs = c->n_limbs_opt;
+  const bool i8 = c->pair_kernel == WLD_PAIR_KERNEL_UMMA_I8;
+  // exact-accumulation limit of a Gram entry: fp32 holds integers up to 2^24, s32 up to 2^31-1
+  const unsigned long long exact_limit = i8 ? ((1ull << 31) - 1) : (1ull << 24);
 
   WLD_CUDA(c, c->q.ensure(sizeof(double) * (size_t)c->ldc));
   WLD_CUDA(c, c->limbs.ensure(sizeof(uint16_t) * 4 * (size_t)c->ldc));
@@ -202,20 +232,24 @@ int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm) {
     }
     unsigned long long worst = 0;
     for (int l = 0; l < gm.n_limbs; ++l) worst = std::max(worst, sums[l]);
-    if (worst <= (1ull << 24)) break;
-    if (--bits < 1) return c->fail(WLD_ERR_UNSUPPORTED, "n_seqs too large for exact fp32 accumulation");
+    if (worst <= exact_limit) break;
+    if (--bits < 1) return c->fail(WLD_ERR_UNSUPPORTED, "n_seqs too large for exact accumulation");
   }
   gm.limb_bits = bits;
+  c->weight_sum = 0.0;
+  for (int l = 0; l < gm.n_limbs; ++l) c->weight_sum += std::ldexp((double)sums[l], bits * (gm.n_limbs - 1 - l));
   gm.rows_per_site = 2 * gm.n_limbs;
   gm.sites_per_group = 128 / gm.rows_per_site;
-  gm.k_padded = round_up(std::max<int64_t>(n, 1), 64);
+  gm.elem_bytes = i8 ? 1 : 2;
+  gm.k_padded = round_up(std::max<int64_t>(n, 1), i8 ? 128 : 64);  // one 128-byte swizzle atom per K block
   gm.a_rows = round_up(std::max<int64_t>(2 * L, 1), 128);
   gm.b_groups = std::max<int64_t>((L + gm.sites_per_group - 1) / gm.sites_per_group, 1);
   gm.b_groups = round_up(gm.b_groups, 2);  // an N tile is two groups
 
   const int64_t kp = gm.k_padded;
-  WLD_CUDA(c, c->opA.ensure(sizeof(uint16_t) * (size_t)gm.a_rows * (size_t)kp));
-  WLD_CUDA(c, c->opB.ensure(sizeof(uint16_t) * (size_t)gm.b_groups * 128 * (size_t)kp));
+  const size_t es = (size_t)gm.elem_bytes;
+  WLD_CUDA(c, c->opA.ensure(es * (size_t)gm.a_rows * (size_t)kp));
+  WLD_CUDA(c, c->opB.ensure(es * (size_t)gm.b_groups * 128 * (size_t)kp));
   const unsigned kblocks = (unsigned)((kp / 8 + 255) / 256);
   {
     dim3 grid(kblocks, (unsigned)(gm.a_rows / 2));
@@ -223,9 +257,10 @@ int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm) {
     // grid.y limit is 65535: fold larger site counts into several launches
     for (int64_t y0 = 0; y0 < gm.a_rows / 2; y0 += 65535) {
       const unsigned ny = (unsigned)std::min<int64_t>(65535, gm.a_rows / 2 - y0);
-      expand_a_kernel<<<dim3(kblocks, ny), 256, 0, c->stream>>>(
+      auto kern = i8 ? expand_a_kernel<true> : expand_a_kernel<false>;
+      kern<<<dim3(kblocks, ny), 256, 0, c->stream>>>(
           c->codes.as<uint8_t>() + y0 * c->ldc, c->ldc, std::max<int64_t>(L - y0, 0), c->maj.as<int8_t>() + y0,
-          c->mnr.as<int8_t>() + y0, kp, c->opA.as<uint16_t>() + 2 * y0 * kp);
+          c->mnr.as<int8_t>() + y0, kp, c->opA.as<uint8_t>() + (size_t)(2 * y0 * kp) * es);
       tm.launched();
     }
   }
@@ -234,10 +269,11 @@ int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm) {
     const int64_t groups_per_launch = 65535 / (spg + 1);
     for (int64_t g0 = 0; g0 < gm.b_groups; g0 += groups_per_launch) {
       const int64_t ng = std::min<int64_t>(groups_per_launch, gm.b_groups - g0);
-      expand_b_kernel<<<dim3(kblocks, (unsigned)(ng * (spg + 1))), 256, 0, c->stream>>>(
+      auto kern = i8 ? expand_b_kernel<true> : expand_b_kernel<false>;
+      kern<<<dim3(kblocks, (unsigned)(ng * (spg + 1))), 256, 0, c->stream>>>(
           c->codes.as<uint8_t>() + g0 * spg * c->ldc, c->ldc, std::max<int64_t>(L - g0 * spg, 0),
           c->maj.as<int8_t>() + g0 * spg, c->mnr.as<int8_t>() + g0 * spg, c->limbs.as<uint16_t>(), gm.n_limbs, spg,
-          kp, c->opB.as<uint16_t>() + g0 * 128 * kp);
+          kp, c->opB.as<uint8_t>() + (size_t)(g0 * 128 * kp) * es);
       tm.launched();
     }
   }

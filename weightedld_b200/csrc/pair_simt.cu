@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) pair_simt_kernel(const uint8_t* __restric
 
 }  // namespace
 
-int run_pair_simt(wld_ctx* c, float thr, ScopedStageTimer& tm) {
+int run_pair_simt(wld_ctx* c, float thr) {
   const int64_t L = c->n_kept;
   const int64_t nt = (L + kTile - 1) / kTile;
   std::vector<uint2> list;
@@ -117,6 +117,8 @@ int run_pair_simt(wld_ctx* c, float thr, ScopedStageTimer& tm) {
   WLD_CUDA(c, c->tiles.ensure(sizeof(uint2) * list.size()));
   WLD_CUDA(c, cudaMemcpyAsync(c->tiles.p, list.data(), sizeof(uint2) * list.size(), cudaMemcpyHostToDevice, c->stream));
   WLD_CUDA(c, cudaStreamSynchronize(c->stream));  // `list` is pageable and dies at return
+  std::memset(c->plan_key, 0xff, sizeof c->plan_key);  // the tile buffer no longer holds the tcgen05 schedule
+  ScopedStageTimer tm(c, WLD_STAGE_PAIR);          // kernel only
   PairOut out{c->pairs.as<wld_pair>(), c->counters.as<unsigned long long>(), c->pair_cap};
   pair_simt_kernel<<<(unsigned)list.size(), 256, 0, c->stream>>>(
       c->codes.as<uint8_t>(), c->ldc, L, c->n_seqs, c->maj.as<int8_t>(), c->mnr.as<int8_t>(), c->q.as<double>(),

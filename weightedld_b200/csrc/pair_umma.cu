@@ -27,6 +27,8 @@
 //
 // Roofline: tensor pipe.  Algorithmic flop per site pair per launch = 8*N*NL (4 weighted dot
 // products of length N per limb); executed = 2*128*256*Kp per tile.
+#include <cmath>
+
 #include "common.cuh"
 #include "pair_epilogue.cuh"
 
@@ -35,11 +37,11 @@ namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockN = 256;
-constexpr int kBlockK = 64;  // bf16 elements = 128 bytes = one swizzle atom
-constexpr int kUmmaK = 16;
+constexpr int kBlockKBytes = 128;  // one 128-byte swizzle atom along K: 64 bf16 or 128 u8 elements
+constexpr int kUmmaKBytes = 32;    // one MMA consumes 32 bytes of K: 16 bf16 (kind::f16) or 32 u8 (kind::i8)
 constexpr int kStages = 4;
-constexpr int kAStageBytes = kBlockM * kBlockK * 2;  // 16 KB
-constexpr int kBStageBytes = kBlockN * kBlockK * 2;  // 32 KB
+constexpr int kAStageBytes = kBlockM * kBlockKBytes;  // 16 KB
+constexpr int kBStageBytes = kBlockN * kBlockKBytes;  // 32 KB
 constexpr int kStageBytes = kAStageBytes + kBStageBytes;
 constexpr int kNumThreads = 384;
 constexpr int kEpiWarp0 = 4;
@@ -55,6 +57,9 @@ struct UmmaParams {
   int limb_bits;
   float thr;
   double thr_lo;
+  float thr_lo_f;     // fp32 pre-filter threshold (lowered, see ld_prefilter_f32)
+  int thr_negative;   // threshold below zero: every pair with non-empty marginals is a candidate
+  int sum_shift;      // fp32 pre-filter works on sums scaled by 2^-sum_shift so that T <= 2^21
   PairOut out;
   unsigned long long* pairs_done;
   int* error_flag;
@@ -133,21 +138,34 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// Instruction descriptor, kind::f16: D=F32 (bits 4-5 = 1), A=B=BF16 (bits 7-9, 10-12 = 1), both
-// K-major (bits 15, 16 = 0), N>>3 at bits 17-22, M>>4 at bits 24-28.
-constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBlockN >> 3) << 17) |
-                                ((uint32_t)(kBlockM >> 4) << 24);
+// Instruction descriptors (both operands K-major: bits 15, 16 = 0; N>>3 at bits 17-22, M>>4 at 24-28):
+//   kind::f16: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9 and 10-12 = 1)
+//   kind::i8 : D = S32 (bits 4-5 = 2), A = B = unsigned 8-bit (bits 7-9 and 10-12 = 0)
+constexpr uint32_t kInstrDescShape = ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+constexpr uint32_t kInstrDescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | kInstrDescShape;
+constexpr uint32_t kInstrDescU8 = (2u << 4) | kInstrDescShape;
 
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+template <bool kI8>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  if constexpr (kI8) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(kInstrDescU8), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(kInstrDescBf16), "r"(accumulate)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -192,12 +210,13 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* v) {
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <int NL>
+template <int NL, bool kI8>
 __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const UmmaParams p) {
   constexpr int RPS = 2 * NL;      // opB rows per site
   constexpr int SPG = 128 / RPS;   // sites per 128-row group
+  constexpr int kBlockK = kBlockKBytes / (kI8 ? 1 : 2);  // K elements per smem stage
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -268,9 +287,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
           const uint64_t adesc = make_smem_desc(sA + stage * kAStageBytes);
           const uint64_t bdesc = make_smem_desc(sB + stage * kBStageBytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in 16-byte units
-            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, kInstrDesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBlockKBytes / kUmmaKBytes; ++k) {
+            // advance 32 bytes along K inside the swizzle atom: +2 in 16-byte units
+            umma<kI8>(d_tmem, adesc + 2u * k, bdesc + 2u * k, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -284,9 +303,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
     const int half = (warp - kEpiWarp0) >> 2; // which 128-column group of the accumulator
     const int alpha = lane & 1;
-    double scale[NL];
+    double scale[NL];   // exact limb weights for the f64 path
+    float scale_f[NL];  // the same, pre-scaled by 2^-sum_shift, for the fp32 pre-filter
 #pragma unroll
-    for (int l = 0; l < NL; ++l) scale[l] = (double)(1ull << (p.limb_bits * (NL - 1 - l)));
+    for (int l = 0; l < NL; ++l) {
+      scale[l] = (double)(1ull << (p.limb_bits * (NL - 1 - l)));
+      scale_f[l] = __int_as_float((127 + p.limb_bits * (NL - 1 - l) - p.sum_shift) << 23);
+    }
     unsigned long long done = 0;
     uint32_t tcount = 0;
     for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++tcount) {
@@ -299,7 +322,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * kBlockN + half * 128;
       // whole tile below the diagonal band for this warp?  (i >= every j) -> nothing to do
       const int i_min = (int)tile.x * (kBlockM / 2) + quarter * 16;
-      const bool any_work = i_min < min(site_j0 + SPG, p.n_kept) - 0 && site_j0 < p.n_kept;
+      const bool any_work = i_min < min(site_j0 + SPG, p.n_kept) && site_j0 < p.n_kept;
       if (any_work) {
 #pragma unroll 1
         for (int jp = 0; jp < (SPG + 1) / 2; ++jp) {
@@ -313,34 +336,54 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
             for (int x = RPS; x < 2 * RPS; ++x) v[x] = 0u;
           }
           tmem_ld_wait();
-          double S[2][2];
+          // ---- fp32 pass: limb recombination (rounded), half-table swap, conservative pre-filter
+          float F[2][2];
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
             for (int beta = 0; beta < 2; ++beta) {
-              double s = 0.0;
+              float s = 0.0f;
 #pragma unroll
-              for (int l = 0; l < NL; ++l)
-                s = fma((double)__uint_as_float(v[jj * RPS + beta * NL + l]), scale[l], s);  // exact
-              S[jj][beta] = s;
+              for (int l = 0; l < NL; ++l) {
+                const uint32_t raw = v[jj * RPS + beta * NL + l];  // exact integer: fp32 or s32 accumulator
+                s = fmaf(kI8 ? (float)(int)raw : __uint_as_float(raw), scale_f[l], s);
+              }
+              F[jj][beta] = s;
             }
           // lane alpha=0 finishes site j0 = 2jp, lane alpha=1 finishes j1 = 2jp+1; swap the other halves
-          const double send0 = alpha ? S[0][0] : S[1][0];
-          const double send1 = alpha ? S[0][1] : S[1][1];
-          const double recv0 = __shfl_xor_sync(0xffffffffu, send0, 1);
-          const double recv1 = __shfl_xor_sync(0xffffffffu, send1, 1);
-          const double own0 = alpha ? S[1][0] : S[0][0];
-          const double own1 = alpha ? S[1][1] : S[0][1];
-          const double AB = alpha ? recv0 : own0;
-          const double Ab = alpha ? recv1 : own1;
-          const double aB = alpha ? own0 : recv0;
-          const double ab = alpha ? own1 : recv1;
+          const float fr0 = __shfl_xor_sync(0xffffffffu, alpha ? F[0][0] : F[1][0], 1);
+          const float fr1 = __shfl_xor_sync(0xffffffffu, alpha ? F[0][1] : F[1][1], 1);
+          const float fo0 = alpha ? F[1][0] : F[0][0];
+          const float fo1 = alpha ? F[1][1] : F[0][1];
           const int j_local = 2 * jp + alpha;
           const int site_j = site_j0 + j_local;
           const bool valid = j_local < SPG && site_i < site_j && site_j < p.n_kept;  // lib.rs:651
           done += valid;
-          bool keep = valid && ld_prefilter(AB, Ab, aB, ab, p.thr_lo);
+          bool keep = valid && ld_prefilter_f32(alpha ? fr0 : fo0, alpha ? fr1 : fo1, alpha ? fo0 : fr0,
+                                                alpha ? fo1 : fr1, p.thr_lo_f, p.thr_negative != 0);
           if (__any_sync(0xffffffffu, keep)) {
+            // ---- f64 pass (candidates only): exact sums, lib.rs:482-518 operation for operation
+            double S[2][2];
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+              for (int beta = 0; beta < 2; ++beta) {
+                double s = 0.0;
+#pragma unroll
+                for (int l = 0; l < NL; ++l) {
+                  const uint32_t raw = v[jj * RPS + beta * NL + l];
+                  s = fma(kI8 ? (double)(int)raw : (double)__uint_as_float(raw), scale[l], s);  // exact
+                }
+                S[jj][beta] = s;
+              }
+            const double recv0 = __shfl_xor_sync(0xffffffffu, alpha ? S[0][0] : S[1][0], 1);
+            const double recv1 = __shfl_xor_sync(0xffffffffu, alpha ? S[0][1] : S[1][1], 1);
+            const double own0 = alpha ? S[1][0] : S[0][0];
+            const double own1 = alpha ? S[1][1] : S[0][1];
+            const double AB = alpha ? recv0 : own0;
+            const double Ab = alpha ? recv1 : own1;
+            const double aB = alpha ? own0 : recv0;
+            const double ab = alpha ? own1 : recv1;
             float d = 0.f, dp = 0.f, r2 = 0.f;
             if (keep) keep = ld_stats_exact(AB, Ab, aB, ab, p.thr, d, dp, r2);
             emit_pairs_warp(keep, (uint32_t)site_i, (uint32_t)site_j, d, dp, r2, p.out);
@@ -383,24 +426,26 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-bool make_tensor_map(CUtensorMap* map, void* base, uint64_t rows, uint64_t kp, uint32_t box_rows) {
+bool make_tensor_map(CUtensorMap* map, void* base, uint64_t rows, uint64_t kp, uint32_t box_rows, int elem_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   const cuuint64_t gdim[2] = {kp, rows};
-  const cuuint64_t gstride[1] = {kp * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+  const cuuint64_t gstride[1] = {kp * (uint64_t)elem_bytes};
+  const cuuint32_t box[2] = {(cuuint32_t)(kBlockKBytes / elem_bytes), box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  return fn(map, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim,
+            gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int NL>
+template <int NL, bool kI8>
 cudaError_t launch(int grid, cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                    const UmmaParams& prm) {
-  cudaError_t e = cudaFuncSetAttribute(pair_umma_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  cudaError_t e =
+      cudaFuncSetAttribute(pair_umma_kernel<NL, kI8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (e != cudaSuccess) return e;
-  pair_umma_kernel<NL><<<grid, kNumThreads, kSmemBytes, stream>>>(tmA, tmB, prm);
+  pair_umma_kernel<NL, kI8><<<grid, kNumThreads, kSmemBytes, stream>>>(tmA, tmB, prm);
   return cudaGetLastError();
 }
 
@@ -442,46 +487,67 @@ TilePlan plan_tiles(int64_t L, int n_limbs, int part, int nparts, int sm_count) 
   return plan;
 }
 
-int run_pair_umma(wld_ctx* c, float thr, ScopedStageTimer& tm) {
+int run_pair_umma(wld_ctx* c, float thr) {
   const PairGeom& gm = c->geom;
   const int64_t L = c->n_kept;
-  TilePlan plan = plan_tiles(L, gm.n_limbs, c->part, c->nparts, c->sm_count);
-  std::vector<uint2>& list = plan.tiles;
-  const int64_t tile_m = plan.tile_m, tile_n = plan.tile_n;
-  c->info.tiles = (int64_t)list.size();
-  c->info.tile_sites_m = tile_m;
-  c->info.tile_sites_n = tile_n;
-  c->info.executed_flop = (double)list.size() * 2.0 * kBlockM * kBlockN * (double)gm.k_padded;
-  if (list.empty()) return WLD_OK;
-
-  WLD_CUDA(c, c->tiles.ensure(sizeof(uint2) * list.size()));
-  WLD_CUDA(c, cudaMemcpyAsync(c->tiles.p, list.data(), sizeof(uint2) * list.size(), cudaMemcpyHostToDevice, c->stream));
-  WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+  // The schedule only depends on (n_kept, n_limbs, partition): keep it on the device between calls.
+  const int64_t key[5] = {L, gm.n_limbs, c->part, c->nparts, 0};
+  if (std::memcmp(key, c->plan_key, sizeof key) != 0) {
+    TilePlan plan = plan_tiles(L, gm.n_limbs, c->part, c->nparts, c->sm_count);
+    WLD_CUDA(c, c->tiles.ensure(sizeof(uint2) * std::max<size_t>(plan.tiles.size(), 1)));
+    if (!plan.tiles.empty())
+      WLD_CUDA(c, cudaMemcpyAsync(c->tiles.p, plan.tiles.data(), sizeof(uint2) * plan.tiles.size(),
+                                  cudaMemcpyHostToDevice, c->stream));
+    WLD_CUDA(c, cudaStreamSynchronize(c->stream));  // the host vector dies at the end of this block
+    std::memcpy(c->plan_key, key, sizeof key);
+    c->plan_tiles_n = (int64_t)plan.tiles.size();
+    c->plan_pairs = plan.pairs;
+  }
+  const int64_t n_tiles = c->plan_tiles_n;
+  c->info.tiles = n_tiles;
+  c->info.tile_sites_m = kBlockM / 2;
+  c->info.tile_sites_n = 2 * gm.sites_per_group;
+  c->info.executed_flop = (double)n_tiles * 2.0 * kBlockM * kBlockN * (double)gm.k_padded;
+  if (n_tiles == 0) return WLD_OK;
 
   CUtensorMap tmA, tmB;
-  if (!make_tensor_map(&tmA, c->opA.p, (uint64_t)gm.a_rows, (uint64_t)gm.k_padded, kBlockM) ||
-      !make_tensor_map(&tmB, c->opB.p, (uint64_t)gm.b_groups * 128, (uint64_t)gm.k_padded, kBlockN))
+  if (!make_tensor_map(&tmA, c->opA.p, (uint64_t)gm.a_rows, (uint64_t)gm.k_padded, kBlockM, gm.elem_bytes) ||
+      !make_tensor_map(&tmB, c->opB.p, (uint64_t)gm.b_groups * 128, (uint64_t)gm.k_padded, kBlockN, gm.elem_bytes))
     return c->fail(WLD_ERR_CUDA, "cuTensorMapEncodeTiled failed (driver without TMA support?)");
 
   UmmaParams prm;
   prm.tiles = c->tiles.as<uint2>();
-  prm.n_tiles = (int)list.size();
-  prm.k_blocks = (int)(gm.k_padded / kBlockK);
+  prm.n_tiles = (int)n_tiles;
+  prm.k_blocks = (int)(gm.k_padded * gm.elem_bytes / kBlockKBytes);
   prm.n_kept = (int)L;
   prm.limb_bits = gm.limb_bits;
   prm.thr = thr;
   prm.thr_lo = ld_thr_lo(thr);
+  {
+    // fp32 pre-filter threshold: lowered once more by 1e-5 relative, rounded towards -inf
+    const double lo = prm.thr_lo;
+    prm.thr_negative = lo < 0.0 ? 1 : 0;
+    float f = (float)(lo * (1.0 - 1e-5));
+    if ((double)f > lo * (1.0 - 1e-5)) f = nextafterf(f, -INFINITY);
+    prm.thr_lo_f = f > 0.f ? f : 0.f;
+    // scale sums so that T <= sum of all weights <= 2^21
+    int shift = 0;
+    while (std::ldexp(c->weight_sum, -shift) > 2097152.0) ++shift;
+    prm.sum_shift = shift;
+  }
   prm.out = PairOut{c->pairs.as<wld_pair>(), c->counters.as<unsigned long long>(), c->pair_cap};
   prm.pairs_done = c->counters.as<unsigned long long>() + 1;
   prm.error_flag = reinterpret_cast<int*>(c->counters.as<unsigned long long>() + 2);
 
-  const int grid = (int)std::min<size_t>(list.size(), (size_t)c->sm_count);
+  const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)c->sm_count);
   cudaError_t e;
+  ScopedStageTimer tm(c, WLD_STAGE_PAIR);  // kernel only
+  const bool i8 = gm.elem_bytes == 1;
   switch (gm.n_limbs) {
-    case 1: e = launch<1>(grid, c->stream, tmA, tmB, prm); break;
-    case 2: e = launch<2>(grid, c->stream, tmA, tmB, prm); break;
-    case 3: e = launch<3>(grid, c->stream, tmA, tmB, prm); break;
-    case 4: e = launch<4>(grid, c->stream, tmA, tmB, prm); break;
+    case 1: e = i8 ? launch<1, true>(grid, c->stream, tmA, tmB, prm) : launch<1, false>(grid, c->stream, tmA, tmB, prm); break;
+    case 2: e = i8 ? launch<2, true>(grid, c->stream, tmA, tmB, prm) : launch<2, false>(grid, c->stream, tmA, tmB, prm); break;
+    case 3: e = i8 ? launch<3, true>(grid, c->stream, tmA, tmB, prm) : launch<3, false>(grid, c->stream, tmA, tmB, prm); break;
+    case 4: e = i8 ? launch<4, true>(grid, c->stream, tmA, tmB, prm) : launch<4, false>(grid, c->stream, tmA, tmB, prm); break;
     default: return c->fail(WLD_ERR_INVALID, "n_limbs must be 1..4");
   }
   tm.launched();

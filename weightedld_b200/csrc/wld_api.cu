@@ -97,7 +97,7 @@ int wld_set_limbs(wld_ctx* c, int n_limbs) {
 
 int wld_set_pair_kernel(wld_ctx* c, int kind) {
   WLD_CHECK_CTX(c);
-  if (kind != WLD_PAIR_KERNEL_UMMA && kind != WLD_PAIR_KERNEL_SIMT) return c->fail(WLD_ERR_INVALID, "unknown pair kernel %d", kind);
+  if (kind != WLD_PAIR_KERNEL_UMMA && kind != WLD_PAIR_KERNEL_SIMT && kind != WLD_PAIR_KERNEL_UMMA_I8) return c->fail(WLD_ERR_INVALID, "unknown pair kernel %d", kind);
   c->pair_kernel = kind;
   return WLD_OK;
 }
@@ -301,9 +301,7 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
     for (int attempt = 0; attempt < 3; ++attempt) {
       WLD_CUDA(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 8, c->stream));
       {
-        ScopedStageTimer tm(c, WLD_STAGE_PAIR);
-        int rc = c->pair_kernel == WLD_PAIR_KERNEL_SIMT ? run_pair_simt(c, r2_threshold, tm)
-                                                        : run_pair_umma(c, r2_threshold, tm);
+        int rc = c->pair_kernel == WLD_PAIR_KERNEL_SIMT ? run_pair_simt(c, r2_threshold) : run_pair_umma(c, r2_threshold);
         if (rc != WLD_OK) return rc;
       }
       unsigned long long cnt[4] = {0, 0, 0, 0};
