@@ -216,6 +216,8 @@ def run_ours(args):
         ctx.set_limbs(args.limbs)
     if args.kernel:
         ctx.set_pair_kernel(args.kernel)
+    if args.ctas:
+        ctx.set_cta_group(args.ctas)
 
     stages = {k: 0.0 for k in wld.STAGE_NAMES}
     launches = {"n": 0}
@@ -336,6 +338,7 @@ def main():
     ap.add_argument("--workload", default="c5", choices=list(WORKLOADS))
     ap.add_argument("--limbs", type=int, default=0)
     ap.add_argument("--kernel", default="", choices=["", "umma", "bf16", "i8", "simt"])
+    ap.add_argument("--ctas", type=int, default=0, choices=[0, 1, 2], help="tcgen05 cta_group (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--profile", action="store_true", help="profiling run: honour --warmup < 3, skip the e2e leg (numbers are not bench values)")
     args = ap.parse_args()

@@ -119,6 +119,9 @@ WLD_API int wld_set_partition(wld_ctx* ctx, int part, int nparts);
  * limbs could round — see DESIGN.md "precision contract"). */
 WLD_API int wld_set_limbs(wld_ctx* ctx, int n_limbs);
 WLD_API int wld_set_pair_kernel(wld_ctx* ctx, int kind);
+/* CTAs cooperating on one tensor-core tile of the pair stage: 2 (default) = tcgen05 cta_group::2, a
+ * CTA pair computes 256 x 256 and each CTA stages half of the limb operand; 1 = single-CTA 128 x 256. */
+WLD_API int wld_set_cta_group(wld_ctx* ctx, int ctas);
 /* Initial capacity (in pairs) of the device survivor buffer; it grows automatically. */
 WLD_API int wld_set_pair_capacity(wld_ctx* ctx, uint64_t pairs);
 
@@ -180,7 +183,7 @@ WLD_API uint64_t wld_pair_order_key(int64_t n_kept, uint32_t kept_a, uint32_t ke
  * 2*floor(128/(2*n_limbs)); only pairs a < b inside it are evaluated.  Writes 2 uint32 (tm, tn) per
  * tile into tiles_mn (may be NULL to count), n_tiles = number of tiles, n_pairs = site pairs they
  * cover.  sm_count sizes the round-robin blocks (148 on B200). */
-WLD_API int wld_plan_tiles(int64_t n_kept, int n_limbs, int part, int nparts, int sm_count, uint32_t* tiles_mn,
+WLD_API int wld_plan_tiles(int64_t n_kept, int n_limbs, int cta_group, int part, int nparts, int sm_count, uint32_t* tiles_mn,
                            uint64_t cap_tiles, uint64_t* n_tiles, uint64_t* n_pairs);
 
 /* ---- introspection ------------------------------------------------------------------------- */

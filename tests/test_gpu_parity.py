@@ -122,9 +122,11 @@ def test_henikoff_rust_kats(wld, golden):
 
 
 # ------------------------------------------------------------------------------------------ stage 3
-def run_gpu_pairs(wld, chars, kernel, thr, n_limbs=3, weights=None, partition=None, cap=None, filt=(0.8, 0.02, 0.5)):
+def run_gpu_pairs(wld, chars, kernel, thr, n_limbs=3, weights=None, partition=None, cap=None, filt=(0.8, 0.02, 0.5),
+                  ctas=2):
     with wld.Context(0) as ctx:
         ctx.set_pair_kernel(kernel)
+        ctx.set_cta_group(ctas)
         ctx.set_limbs(n_limbs)
         if cap:
             ctx.set_pair_capacity(cap)
@@ -162,12 +164,13 @@ def test_pairs_simt_bit_exact(wld, oracle, n_seqs, n_cols, thr):
     assert_pairs_identical(gpu, ref)
 
 
+@pytest.mark.parametrize("ctas", [2, 1])
 @pytest.mark.parametrize("kernel", ["bf16", "i8"])
 @pytest.mark.parametrize("n_limbs", [3, 1, 2, 4])
 @pytest.mark.parametrize("n_seqs,n_cols,thr", PAIR_CASES)
-def test_pairs_umma_bit_exact(wld, oracle, n_seqs, n_cols, thr, n_limbs, kernel):
+def test_pairs_umma_bit_exact(wld, oracle, n_seqs, n_cols, thr, n_limbs, kernel, ctas):
     chars = synth(n_seqs, n_cols, seed=n_seqs + n_cols, block=60, clonal=True)
-    gpu, done, info, w32, _ = run_gpu_pairs(wld, chars, kernel, thr, n_limbs=n_limbs)
+    gpu, done, info, w32, _ = run_gpu_pairs(wld, chars, kernel, thr, n_limbs=n_limbs, ctas=ctas)
     assert info.kernel == {"bf16": 0, "i8": 2}[kernel] and info.n_limbs == n_limbs and info.weight_bits == 8 * n_limbs
     fs, ref, computed = oracle_pairs(oracle, chars, w32, info.weight_bits, thr)
     assert done == computed
@@ -194,11 +197,12 @@ def test_pairs_close_to_reference_faithful_f32(wld, oracle):
     assert (got ^ want) <= band
 
 
+@pytest.mark.parametrize("ctas", [2, 1])
 @pytest.mark.parametrize("kernel", ["bf16", "i8"])
-def test_umma_matches_simt_all_pairs_multi_tile(wld, kernel):
+def test_umma_matches_simt_all_pairs_multi_tile(wld, kernel, ctas):
     # several M and N tiles, ragged edges, K not a multiple of the K block, every pair emitted
     chars = synth(1111, 1900, seed=77, block=100)
-    a = run_gpu_pairs(wld, chars, kernel, -1.0)
+    a = run_gpu_pairs(wld, chars, kernel, -1.0, ctas=ctas)
     b = run_gpu_pairs(wld, chars, "simt", -1.0)
     assert a[1] == b[1] and len(a[0]) == len(b[0]) > 500000
     assert a[0].tobytes() == b[0].tobytes()

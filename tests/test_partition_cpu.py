@@ -17,15 +17,17 @@ def tile_owner_mask(wld, n_kept, a, b, tiles, tile_m, tile_n):
     return own[a // tile_m, b // tile_n]
 
 
+@pytest.mark.parametrize("ctas", [1, 2])
 @pytest.mark.parametrize("n_limbs,tile_n", [(1, 128), (2, 64), (3, 42), (4, 32)])
 @pytest.mark.parametrize("n_kept", [1, 2, 63, 64, 65, 700, 5000])
-def test_plan_covers_each_pair_once(n_kept, n_limbs, tile_n):
+def test_plan_covers_each_pair_once(n_kept, n_limbs, tile_n, ctas):
     import weightedld_b200 as wld
+    tile_m = 64 * ctas
     for nparts in (1, 2, 3, 8):
-        seen = np.zeros((n_kept // 64 + 1, n_kept // tile_n + 1), np.int32)
+        seen = np.zeros((n_kept // tile_m + 1, n_kept // tile_n + 1), np.int32)
         total = 0
         for part in range(nparts):
-            tiles, pairs = wld.plan_tiles(n_kept, n_limbs, part, nparts, sm_count=4)
+            tiles, pairs = wld.plan_tiles(n_kept, n_limbs, part, nparts, sm_count=4, cta_group=ctas)
             total += pairs
             if len(tiles):
                 np.add.at(seen, (tiles[:, 0], tiles[:, 1]), 1)
@@ -35,15 +37,19 @@ def test_plan_covers_each_pair_once(n_kept, n_limbs, tile_n):
         for tm in range(seen.shape[0]):
             for tn in range(seen.shape[1]):
                 j_last = min(n_kept, (tn + 1) * tile_n) - 1
-                needed = tm * 64 < j_last and tm * 64 < n_kept and tn * tile_n < n_kept
+                needed = tm * tile_m < j_last and tm * tile_m < n_kept and tn * tile_n < n_kept
                 assert bool(seen[tm, tn]) == needed, (tm, tn)
 
 
 def test_plan_is_balanced_at_config5():
     import weightedld_b200 as wld
-    for nparts in (2, 4, 8):
-        pairs = [wld.plan_tiles(48601, 3, p, nparts)[1] for p in range(nparts)]
-        assert max(pairs) / min(pairs) < 1.01
+    for ctas in (1, 2):
+        for nparts in (2, 4, 8):
+            plans = [wld.plan_tiles(48601, 3, p, nparts, cta_group=ctas) for p in range(nparts)]
+            pairs = [p[1] for p in plans]
+            tiles = [len(p[0]) for p in plans]
+            assert max(pairs) / min(pairs) < 1.01                 # site pairs
+            assert max(tiles) - min(tiles) <= 2 * (148 // ctas)   # MMA work: at most one block of tiles apart
 
 
 def _worker(rank, world, port, n_kept, q):
@@ -64,8 +70,8 @@ def _worker(rank, world, port, n_kept, q):
     w = O.quantize_weights(O.henikoff_weights(fs), 24)
     kept = O.SiteSet(fs.codes, fs.hists, None)  # kept indices, like WLD_FETCH_KEPT_INDEX
     full, computed = O.all_weighted_ld_pairs(kept, w, 0.1, O.F64)
-    tiles, my_pairs = wld.plan_tiles(fs.n_sites, 3, rank, world, sm_count=2)
-    mine = full[tile_owner_mask(wld, fs.n_sites, full["a"], full["b"], tiles, 64, 42)]
+    tiles, my_pairs = wld.plan_tiles(fs.n_sites, 3, rank, world, sm_count=2, cta_group=2)
+    mine = full[tile_owner_mask(wld, fs.n_sites, full["a"], full["b"], tiles, 128, 42)]
     rng = np.random.default_rng(rank)
     shard = np.empty(len(mine), wld.PAIR_DTYPE)  # the GPU emits its survivors unordered
     for src, dst in (("a", "site_a"), ("b", "site_b"), ("d", "d"), ("d_prime", "d_prime"), ("r2", "r2")):

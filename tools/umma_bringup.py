@@ -10,9 +10,10 @@ import weightedld_b200 as wld
 from weightedld_b200.synth import make_alignment
 
 
-def run(chars, kernel, thr=-1.0, limbs=3, weights=None):
+def run(chars, kernel, thr=-1.0, limbs=3, weights=None, ctas=2):
     with wld.Context(0) as ctx:
         ctx.set_pair_kernel(kernel)
+        ctx.set_cta_group(ctas)
         ctx.set_limbs(limbs)
         ctx.load_alignment(chars)
         k = ctx.filter_sites()
@@ -30,16 +31,16 @@ for (n, l, limbs) in [(64, 100, 1), (64, 100, 3), (200, 300, 3), (1000, 900, 3),
     w = np.ones(n, np.float32) if limbs == 1 else None
     k, s, sd, sms, _ = run(chars, "simt", limbs=limbs, weights=w)
     same = True
-    for kern in ("bf16", "i8"):
+    for kern, ctas in (("bf16", 1), ("i8", 1), ("bf16", 2), ("i8", 2)):
         try:
-            k2, u, ud, ums, info = run(chars, kern, limbs=limbs, weights=w)
+            k2, u, ud, ums, info = run(chars, kern, limbs=limbs, weights=w, ctas=ctas)
         except Exception as e:  # noqa
-            print(f"[{n}x{l} limbs={limbs}] {kern} FAILED: {e}")
+            print(f"[{n}x{l} limbs={limbs}] {kern} x{ctas}cta FAILED: {e}")
             ok = False
             same = False
             break
         same = len(s) == len(u) and s.tobytes() == u.tobytes()
-        print(f"[{n}x{l} limbs={limbs}] kept={k} simt: {len(s)} pairs {sms:.3f} ms | {kern}: {len(u)} pairs {ums:.3f} ms "
+        print(f"[{n}x{l} limbs={limbs}] kept={k} simt: {len(s)} pairs {sms:.3f} ms | {kern} x{ctas}cta: {len(u)} pairs {ums:.3f} ms "
               f"tiles={info.tiles} limb_bits={info.limb_bits} done {sd}/{ud} -> {'IDENTICAL' if same else 'DIFFERENT'}")
         if not same:
             break

@@ -70,7 +70,8 @@ SIGNATURES = {
     "wld_ld_pairs": (_int, [_vp, C.c_float, PROGRESS_FN, _vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "wld_fetch_pairs": (_int, [_vp, _vp, _u64, _int, C.POINTER(_u64)]),
     "wld_pair_order_key": (_u64, [_i64, C.c_uint32, C.c_uint32]),
-    "wld_plan_tiles": (_int, [_i64, _int, _int, _int, _int, _vp, _u64, C.POINTER(_u64), C.POINTER(_u64)]),
+    "wld_plan_tiles": (_int, [_i64, _int, _int, _int, _int, _int, _vp, _u64, C.POINTER(_u64), C.POINTER(_u64)]),
+    "wld_set_cta_group": (_int, [_vp, _int]),
     "wld_stage_ms": (_int, [_vp, _int, C.POINTER(C.c_float)]),
     "wld_stage_launches": (_int, [_vp, _int, C.POINTER(_int)]),
     "wld_get_pair_info": (_int, [_vp, C.POINTER(PairInfo)]),

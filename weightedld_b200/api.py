@@ -86,6 +86,9 @@ class Context:
             kind = {"umma": L.PAIR_KERNEL_UMMA, "bf16": L.PAIR_KERNEL_UMMA, "simt": L.PAIR_KERNEL_SIMT, "i8": L.PAIR_KERNEL_UMMA_I8}[kind]
         self._check(self._lib.wld_set_pair_kernel(self._h, kind))
 
+    def set_cta_group(self, ctas: int):
+        self._check(self._lib.wld_set_cta_group(self._h, ctas))
+
     def set_pair_capacity(self, pairs: int):
         self._check(self._lib.wld_set_pair_capacity(self._h, pairs))
 
@@ -217,16 +220,17 @@ def pair_order_key(n_kept: int, kept_a, kept_b) -> np.ndarray:
     return (np.uint64(n - 1) - tr) * np.uint64(n) + tc
 
 
-def plan_tiles(n_kept: int, n_limbs: int = 3, part: int = 0, nparts: int = 1, sm_count: int = 148):
+def plan_tiles(n_kept: int, n_limbs: int = 3, part: int = 0, nparts: int = 1, sm_count: int = 148,
+               cta_group: int = 2):
     """Host-only pair-stage schedule (wld_plan_tiles): ((n_tiles, 2) uint32 tile coordinates,
     site pairs covered).  Needs no GPU."""
     lib = L.load()
     n, pairs = C.c_uint64(), C.c_uint64()
-    rc = lib.wld_plan_tiles(n_kept, n_limbs, part, nparts, sm_count, None, 0, C.byref(n), C.byref(pairs))
+    rc = lib.wld_plan_tiles(n_kept, n_limbs, cta_group, part, nparts, sm_count, None, 0, C.byref(n), C.byref(pairs))
     if rc != L.WLD_OK:
         raise WldError(rc, "bad tile plan arguments")
     tiles = np.empty((n.value, 2), np.uint32)
-    rc = lib.wld_plan_tiles(n_kept, n_limbs, part, nparts, sm_count, _ptr(tiles), n.value, C.byref(n), C.byref(pairs))
+    rc = lib.wld_plan_tiles(n_kept, n_limbs, cta_group, part, nparts, sm_count, _ptr(tiles), n.value, C.byref(n), C.byref(pairs))
     if rc != L.WLD_OK:
         raise WldError(rc, "bad tile plan arguments")
     return tiles, pairs.value

@@ -77,6 +77,7 @@ struct wld_ctx {
   int n_limbs_opt = 3;
   int pair_kernel = WLD_PAIR_KERNEL_UMMA_I8;  // fastest exact path on sm_100a; bf16 and SIMT selectable
   uint64_t pair_cap_opt = 0;
+  int cta_group = 2;               // CTAs cooperating on one MMA tile (tcgen05 cta_group::1 / ::2)
 
   // stage 1
   int64_t n_seqs = 0, n_cols = 0, row_stride = 0;
@@ -185,6 +186,6 @@ struct TilePlan {
   uint64_t pairs = 0;
   int64_t tile_m = 64, tile_n = 42;
 };
-TilePlan plan_tiles(int64_t n_kept, int n_limbs, int part, int nparts, int sm_count);
+TilePlan plan_tiles(int64_t n_kept, int n_limbs, int part, int nparts, int sm_count, int ctas);
 
 }  // namespace wld

@@ -39,15 +39,22 @@ constexpr int kBlockM = 128;
 constexpr int kBlockN = 256;
 constexpr int kBlockKBytes = 128;  // one 128-byte swizzle atom along K: 64 bf16 or 128 u8 elements
 constexpr int kUmmaKBytes = 32;    // one MMA consumes 32 bytes of K: 16 bf16 (kind::f16) or 32 u8 (kind::i8)
-constexpr int kStages = 4;
-constexpr int kAStageBytes = kBlockM * kBlockKBytes;  // 16 KB
-constexpr int kBStageBytes = kBlockN * kBlockKBytes;  // 32 KB
-constexpr int kStageBytes = kAStageBytes + kBStageBytes;
+constexpr int kAStageBytes = kBlockM * kBlockKBytes;  // 16 KB per CTA
+// kCtas = 1: one CTA computes a 128 x 256 tile and stages all 256 B rows (32 KB) -> 4 stages of 48 KB.
+// kCtas = 2: a CTA pair (cta_group::2) computes 256 x 256; each CTA stages its 128 A rows and HALF of
+//            the B rows (16 KB) -> 6 stages of 32 KB; one third less L2->SMEM traffic per MMA.
+template <int kCtas> struct StageCfg {
+  static constexpr int kBRows = kBlockN / kCtas;
+  static constexpr int kBBytes = kBRows * kBlockKBytes;
+  static constexpr int kBytes = kAStageBytes + kBBytes;
+  static constexpr int kStages = kCtas == 1 ? 4 : 6;
+  static constexpr int kSmemBytes = 1024 /*alignment slack*/ + kStages * kBytes + 256 /*barriers*/;
+};
 constexpr int kNumThreads = 384;
 constexpr int kEpiWarp0 = 4;
 constexpr int kNumEpiWarps = 8;
 constexpr int kTmemCols = 512;
-constexpr int kSmemBytes = 1024 /*alignment slack*/ + kStages * kStageBytes + 256 /*barriers*/;
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> CTA 0
 
 struct UmmaParams {
   const uint2* tiles;
@@ -118,6 +125,38 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// remote-capable arrive: `bar` is a shared::cluster address (own CTA's, or CTA 0's after masking)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// 2-CTA TMA load: data lands in THIS CTA's smem, the transaction bytes are counted on CTA 0's barrier
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* m, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(bar & kPeerBitMask)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// commit of a cta_group::2 MMA: arrives on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_cg2(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -141,13 +180,38 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 // Instruction descriptors (both operands K-major: bits 15, 16 = 0; N>>3 at bits 17-22, M>>4 at 24-28):
 //   kind::f16: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9 and 10-12 = 1)
 //   kind::i8 : D = S32 (bits 4-5 = 2), A = B = unsigned 8-bit (bits 7-9 and 10-12 = 0)
-constexpr uint32_t kInstrDescShape = ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
-constexpr uint32_t kInstrDescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | kInstrDescShape;
-constexpr uint32_t kInstrDescU8 = (2u << 4) | kInstrDescShape;
+// The instruction M is 128 for one CTA and 256 for a CTA pair (each CTA holds 128 accumulator rows).
+template <bool kI8, int kCtas>
+__device__ __forceinline__ constexpr uint32_t instr_desc() {
+  return (kI8 ? (2u << 4) : ((1u << 4) | (1u << 7) | (1u << 10))) | ((uint32_t)(kBlockN >> 3) << 17) |
+         ((uint32_t)((kBlockM * kCtas) >> 4) << 24);
+}
 
-template <bool kI8>
+template <bool kI8, int kCtas>
 __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-  if constexpr (kI8) {
+  constexpr uint32_t kInstrDescU8 = instr_desc<true, kCtas>();
+  constexpr uint32_t kInstrDescBf16 = instr_desc<false, kCtas>();
+  if constexpr (kCtas == 2) {
+    if constexpr (kI8) {
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "setp.ne.b32 p, %4, 0;\n"
+          "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
+          "}\n" ::"r"(d_tmem),
+          "l"(adesc), "l"(bdesc), "r"(kInstrDescU8), "r"(accumulate)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "setp.ne.b32 p, %4, 0;\n"
+          "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+          "}\n" ::"r"(d_tmem),
+          "l"(adesc), "l"(bdesc), "r"(kInstrDescBf16), "r"(accumulate)
+          : "memory");
+    }
+  } else if constexpr (kI8) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -210,10 +274,12 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* v) {
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <int NL, bool kI8>
+template <int NL, bool kI8, int kCtas>
 __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const UmmaParams p) {
+  using Cfg = StageCfg<kCtas>;
+  constexpr int kStages = Cfg::kStages;
   constexpr int RPS = 2 * NL;      // opB rows per site
   constexpr int SPG = 128 / RPS;   // sites per 128-row group
   constexpr int kBlockK = kBlockKBytes / (kI8 ? 1 : 2);  // K elements per smem stage
@@ -222,14 +288,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sA = smem_u32(smem);
   const uint32_t sB = sA + kStages * kAStageBytes;
-  const uint32_t bars = sB + kStages * kBStageBytes;
+  const uint32_t bars = sB + kStages * Cfg::kBBytes;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
   auto tfull_bar = [&](int b) { return bars + 8u * (2 * kStages + b); };
   auto tempty_bar = [&](int b) { return bars + 8u * (2 * kStages + 2 + b); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kStages * kStageBytes + 8 * (2 * kStages + 4));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kStages * Cfg::kBytes + 8 * (2 * kStages + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = kCtas == 2 ? cluster_ctarank() : 0u;  // rank 0 = leader: issues the MMAs
+  const int first_tile = (int)(blockIdx.x / kCtas), tile_step = (int)(gridDim.x / kCtas);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -237,64 +305,79 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(full_bar(s), 1);   // leader's expect_tx arrive; TMA bytes of BOTH CTAs complete it
+      mbar_init(empty_bar(s), 1);  // one tcgen05.commit (multicast to both CTAs for a pair)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), kNumEpiWarps);
+      mbar_init(tempty_bar(b), kNumEpiWarps * kCtas);  // the leader waits for the epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  if (warp == 2) {
+    if constexpr (kCtas == 2) tmem_alloc_cg2(smem_u32(tmem_slot), kTmemCols);
+    else tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCtas == 2) cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (both CTAs of a pair) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+      for (int t = first_tile; t < p.n_tiles; t += tile_step) {
         const uint2 tile = p.tiles[t];
-        const int m_row = (int)tile.x * kBlockM, n_row = (int)tile.y * kBlockN;
+        const int m_row = (int)tile.x * (kBlockM * kCtas) + (int)cta_rank * kBlockM;
+        const int n_row = (int)tile.y * kBlockN + (int)cta_rank * Cfg::kBRows;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, p.error_flag, 1);
-          mbar_expect_tx(full_bar(stage), kStageBytes);
-          tma_load_2d(sA + stage * kAStageBytes, &tmA, kb * kBlockK, m_row, full_bar(stage));
-          tma_load_2d(sB + stage * kBStageBytes, &tmB, kb * kBlockK, n_row, full_bar(stage));
+          if constexpr (kCtas == 2) {
+            if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::kBytes);
+            tma_load_2d_cg2(sA + stage * kAStageBytes, &tmA, kb * kBlockK, m_row, full_bar(stage));
+            tma_load_2d_cg2(sB + stage * Cfg::kBBytes, &tmB, kb * kBlockK, n_row, full_bar(stage));
+          } else {
+            mbar_expect_tx(full_bar(stage), Cfg::kBytes);
+            tma_load_2d(sA + stage * kAStageBytes, &tmA, kb * kBlockK, m_row, full_bar(stage));
+            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, kb * kBlockK, n_row, full_bar(stage));
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && cta_rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t tcount = 0;
-      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++tcount) {
+      for (int t = first_tile; t < p.n_tiles; t += tile_step, ++tcount) {
         const uint32_t buf = tcount & 1u, bphase = (tcount >> 1) & 1u;
-        mbar_wait(tempty_bar(buf), bphase ^ 1u, p.error_flag, 2);  // epilogue drained this accumulator
+        mbar_wait(tempty_bar(buf), bphase ^ 1u, p.error_flag, 2);  // epilogues drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * kBlockN;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(full_bar(stage), phase, p.error_flag, 3);  // TMA bytes landed
+          mbar_wait(full_bar(stage), phase, p.error_flag, 3);  // TMA bytes (of both CTAs) landed
           tc_fence_after();
           const uint64_t adesc = make_smem_desc(sA + stage * kAStageBytes);
-          const uint64_t bdesc = make_smem_desc(sB + stage * kBStageBytes);
+          const uint64_t bdesc = make_smem_desc(sB + stage * Cfg::kBBytes);
 #pragma unroll
           for (int k = 0; k < kBlockKBytes / kUmmaKBytes; ++k) {
             // advance 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-            umma<kI8>(d_tmem, adesc + 2u * k, bdesc + 2u * k, (kb | k) != 0 ? 1u : 0u);
+            umma<kI8, kCtas>(d_tmem, adesc + 2u * k, bdesc + 2u * k, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
+          // frees the smem stage (in both CTAs) when these MMAs retire
+          if constexpr (kCtas == 2) umma_commit_cg2(empty_bar(stage));
+          else umma_commit(empty_bar(stage));
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(buf));  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if constexpr (kCtas == 2) umma_commit_cg2(tfull_bar(buf));
+        else umma_commit(tfull_bar(buf));
       }
     }
     __syncwarp();
@@ -312,16 +395,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
     }
     unsigned long long done = 0;
     uint32_t tcount = 0;
-    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++tcount) {
+    for (int t = first_tile; t < p.n_tiles; t += tile_step, ++tcount) {
       const uint2 tile = p.tiles[t];
       const uint32_t buf = tcount & 1u, bphase = (tcount >> 1) & 1u;
-      const int site_i = (int)tile.x * (kBlockM / 2) + quarter * 16 + (lane >> 1);
+      const int i_min = ((int)tile.x * kCtas + (int)cta_rank) * (kBlockM / 2) + quarter * 16;
+      const int site_i = i_min + (lane >> 1);
       const int site_j0 = (int)tile.y * (2 * SPG) + half * SPG;
       mbar_wait(tfull_bar(buf), bphase, p.error_flag, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * kBlockN + half * 128;
       // whole tile below the diagonal band for this warp?  (i >= every j) -> nothing to do
-      const int i_min = (int)tile.x * (kBlockM / 2) + quarter * 16;
       const bool any_work = i_min < min(site_j0 + SPG, p.n_kept) && site_j0 < p.n_kept;
       if (any_work) {
 #pragma unroll 1
@@ -392,7 +475,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(buf));
+      if (lane == 0) {
+        if constexpr (kCtas == 2) mbar_arrive_cluster(tempty_bar(buf) & kPeerBitMask);  // the leader's barrier
+        else mbar_arrive(tempty_bar(buf));
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) done += __shfl_xor_sync(0xffffffffu, done, o);
@@ -400,10 +486,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCtas == 2) cluster_sync_all();  // nobody leaves while the peer may still touch its smem / TMEM
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (kCtas == 2) tmem_dealloc_cg2(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -439,14 +527,42 @@ bool make_tensor_map(CUtensorMap* map, void* base, uint64_t rows, uint64_t kp, u
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int NL, bool kI8>
+template <int NL, bool kI8, int kCtas>
 cudaError_t launch(int grid, cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                    const UmmaParams& prm) {
-  cudaError_t e =
-      cudaFuncSetAttribute(pair_umma_kernel<NL, kI8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  auto kern = pair_umma_kernel<NL, kI8, kCtas>;
+  constexpr int smem = StageCfg<kCtas>::kSmemBytes;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  pair_umma_kernel<NL, kI8><<<grid, kNumThreads, kSmemBytes, stream>>>(tmA, tmB, prm);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, prm);
+}
+
+template <int kCtas>
+cudaError_t launch_any(int n_limbs, bool i8, int grid, cudaStream_t stream, const CUtensorMap& tmA,
+                       const CUtensorMap& tmB, const UmmaParams& prm) {
+  switch (n_limbs * 2 + (i8 ? 1 : 0)) {
+    case 2: return launch<1, false, kCtas>(grid, stream, tmA, tmB, prm);
+    case 3: return launch<1, true, kCtas>(grid, stream, tmA, tmB, prm);
+    case 4: return launch<2, false, kCtas>(grid, stream, tmA, tmB, prm);
+    case 5: return launch<2, true, kCtas>(grid, stream, tmA, tmB, prm);
+    case 6: return launch<3, false, kCtas>(grid, stream, tmA, tmB, prm);
+    case 7: return launch<3, true, kCtas>(grid, stream, tmA, tmB, prm);
+    case 8: return launch<4, false, kCtas>(grid, stream, tmA, tmB, prm);
+    case 9: return launch<4, true, kCtas>(grid, stream, tmA, tmB, prm);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 }  // namespace
@@ -455,9 +571,9 @@ cudaError_t launch(int grid, cudaStream_t stream, const CUtensorMap& tmA, const 
 // share operand panels through L2 (about 18 A panels x 8 B panels); for multi-GPU runs blocks of
 // 2*SM consecutive tiles are dealt round-robin (load-balanced, no collective; replaces rayon's
 // fan-out over triu_index, lib.rs:623-637).
-TilePlan plan_tiles(int64_t L, int n_limbs, int part, int nparts, int sm_count) {
+TilePlan plan_tiles(int64_t L, int n_limbs, int part, int nparts, int sm_count, int ctas) {
   TilePlan plan;
-  plan.tile_m = kBlockM / 2;
+  plan.tile_m = (kBlockM / 2) * ctas;
   plan.tile_n = 2 * (128 / (2 * n_limbs));
   const int64_t tile_m = plan.tile_m, tile_n = plan.tile_n;
   const int64_t n_mt = (L + tile_m - 1) / tile_m, n_nt = (L + tile_n - 1) / tile_n;
@@ -474,7 +590,7 @@ TilePlan plan_tiles(int64_t L, int n_limbs, int part, int nparts, int sm_count) 
   if (nparts <= 1) {
     plan.tiles.swap(all);
   } else {
-    const size_t blk = (size_t)std::max(sm_count, 1) * 2;
+    const size_t blk = (size_t)std::max(sm_count / ctas, 1) * 2;  // two waves of tiles per block
     for (size_t b0 = 0, bi = 0; b0 < all.size(); b0 += blk, ++bi)
       if ((int)(bi % (size_t)nparts) == part)
         plan.tiles.insert(plan.tiles.end(), all.begin() + b0, all.begin() + std::min(all.size(), b0 + blk));
@@ -491,9 +607,10 @@ int run_pair_umma(wld_ctx* c, float thr) {
   const PairGeom& gm = c->geom;
   const int64_t L = c->n_kept;
   // The schedule only depends on (n_kept, n_limbs, partition): keep it on the device between calls.
-  const int64_t key[5] = {L, gm.n_limbs, c->part, c->nparts, 0};
+  const int ctas = c->cta_group;
+  const int64_t key[5] = {L, gm.n_limbs, c->part, c->nparts, ctas};
   if (std::memcmp(key, c->plan_key, sizeof key) != 0) {
-    TilePlan plan = plan_tiles(L, gm.n_limbs, c->part, c->nparts, c->sm_count);
+    TilePlan plan = plan_tiles(L, gm.n_limbs, c->part, c->nparts, c->sm_count, ctas);
     WLD_CUDA(c, c->tiles.ensure(sizeof(uint2) * std::max<size_t>(plan.tiles.size(), 1)));
     if (!plan.tiles.empty())
       WLD_CUDA(c, cudaMemcpyAsync(c->tiles.p, plan.tiles.data(), sizeof(uint2) * plan.tiles.size(),
@@ -505,14 +622,14 @@ int run_pair_umma(wld_ctx* c, float thr) {
   }
   const int64_t n_tiles = c->plan_tiles_n;
   c->info.tiles = n_tiles;
-  c->info.tile_sites_m = kBlockM / 2;
+  c->info.tile_sites_m = (kBlockM / 2) * ctas;
   c->info.tile_sites_n = 2 * gm.sites_per_group;
-  c->info.executed_flop = (double)n_tiles * 2.0 * kBlockM * kBlockN * (double)gm.k_padded;
+  c->info.executed_flop = (double)n_tiles * 2.0 * (kBlockM * ctas) * kBlockN * (double)gm.k_padded;
   if (n_tiles == 0) return WLD_OK;
 
   CUtensorMap tmA, tmB;
   if (!make_tensor_map(&tmA, c->opA.p, (uint64_t)gm.a_rows, (uint64_t)gm.k_padded, kBlockM, gm.elem_bytes) ||
-      !make_tensor_map(&tmB, c->opB.p, (uint64_t)gm.b_groups * 128, (uint64_t)gm.k_padded, kBlockN, gm.elem_bytes))
+      !make_tensor_map(&tmB, c->opB.p, (uint64_t)gm.b_groups * 128, (uint64_t)gm.k_padded, kBlockN / ctas, gm.elem_bytes))
     return c->fail(WLD_ERR_CUDA, "cuTensorMapEncodeTiled failed (driver without TMA support?)");
 
   UmmaParams prm;
@@ -539,17 +656,12 @@ int run_pair_umma(wld_ctx* c, float thr) {
   prm.pairs_done = c->counters.as<unsigned long long>() + 1;
   prm.error_flag = reinterpret_cast<int*>(c->counters.as<unsigned long long>() + 2);
 
-  const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)c->sm_count);
-  cudaError_t e;
-  ScopedStageTimer tm(c, WLD_STAGE_PAIR);  // kernel only
+  const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)(c->sm_count / ctas)) * ctas;
   const bool i8 = gm.elem_bytes == 1;
-  switch (gm.n_limbs) {
-    case 1: e = i8 ? launch<1, true>(grid, c->stream, tmA, tmB, prm) : launch<1, false>(grid, c->stream, tmA, tmB, prm); break;
-    case 2: e = i8 ? launch<2, true>(grid, c->stream, tmA, tmB, prm) : launch<2, false>(grid, c->stream, tmA, tmB, prm); break;
-    case 3: e = i8 ? launch<3, true>(grid, c->stream, tmA, tmB, prm) : launch<3, false>(grid, c->stream, tmA, tmB, prm); break;
-    case 4: e = i8 ? launch<4, true>(grid, c->stream, tmA, tmB, prm) : launch<4, false>(grid, c->stream, tmA, tmB, prm); break;
-    default: return c->fail(WLD_ERR_INVALID, "n_limbs must be 1..4");
-  }
+  if (gm.n_limbs < 1 || gm.n_limbs > 4) return c->fail(WLD_ERR_INVALID, "n_limbs must be 1..4");
+  ScopedStageTimer tm(c, WLD_STAGE_PAIR);  // kernel only
+  const cudaError_t e = ctas == 2 ? launch_any<2>(gm.n_limbs, i8, grid, c->stream, tmA, tmB, prm)
+                                  : launch_any<1>(gm.n_limbs, i8, grid, c->stream, tmA, tmB, prm);
   tm.launched();
   if (e != cudaSuccess) return c->fail(WLD_ERR_CUDA, "pair_umma launch failed: %s", cudaGetErrorString(e));
   return WLD_OK;

@@ -102,6 +102,13 @@ int wld_set_pair_kernel(wld_ctx* c, int kind) {
   return WLD_OK;
 }
 
+int wld_set_cta_group(wld_ctx* c, int ctas) {
+  WLD_CHECK_CTX(c);
+  if (ctas != 1 && ctas != 2) return c->fail(WLD_ERR_INVALID, "cta_group must be 1 or 2");
+  c->cta_group = ctas;
+  return WLD_OK;
+}
+
 int wld_set_pair_capacity(wld_ctx* c, uint64_t pairs) {
   WLD_CHECK_CTX(c);
   c->pair_cap_opt = pairs;
@@ -342,10 +349,11 @@ uint64_t wld_pair_order_key(int64_t n_kept, uint32_t kept_a, uint32_t kept_b) {
   return (n - 1 - tr) * n + tc;
 }
 
-int wld_plan_tiles(int64_t n_kept, int n_limbs, int part, int nparts, int sm_count, uint32_t* tiles_mn,
+int wld_plan_tiles(int64_t n_kept, int n_limbs, int cta_group, int part, int nparts, int sm_count, uint32_t* tiles_mn,
                    uint64_t cap_tiles, uint64_t* n_tiles, uint64_t* n_pairs) {
+  if (cta_group != 1 && cta_group != 2) return WLD_ERR_INVALID;
   if (n_kept < 0 || n_limbs < 1 || n_limbs > 4 || nparts < 1 || part < 0 || part >= nparts) return WLD_ERR_INVALID;
-  TilePlan plan = plan_tiles(n_kept, n_limbs, part, nparts, sm_count > 0 ? sm_count : kNumSMsB200);
+  TilePlan plan = plan_tiles(n_kept, n_limbs, part, nparts, sm_count > 0 ? sm_count : kNumSMsB200, cta_group);
   if (n_tiles) *n_tiles = plan.tiles.size();
   if (n_pairs) *n_pairs = plan.pairs;
   if (tiles_mn) {
