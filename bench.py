@@ -38,6 +38,7 @@ WORKLOADS = {
     "c5": ("synthetic 10,000 sequences x 50,000 variable sites (BASELINE.json configs[4])", 10_000, 50_000, {}),
     "c4": ("synthetic SARS-CoV-2-like 100,000 sequences x 30 kb, ~1/3 variable (configs[3])", 100_000, 30_000, {"sars": True}),
     "c3": ("synthetic 2,000 sequences x 20,000 variable sites (configs[2])", 2_000, 20_000, {}),
+    "c3ld": ("synthetic 2,000 sequences x 20,000 sites, clonal / high-LD (about a third of all pairs survive)", 2_000, 20_000, {"clonal": True}),
     "tiny": ("synthetic 512 sequences x 3,000 sites (smoke)", 512, 3_000, {}),
 }
 R2_THRESHOLD = 0.1
@@ -50,6 +51,9 @@ def make_input(name: str) -> np.ndarray:
     seed = 0xC0FFEE + list(WORKLOADS).index(name)
     if kw.get("sars"):
         return make_sarscov2_like(n, l, seed=seed)
+    if kw.get("clonal"):
+        return make_alignment(n, l, seed=seed, founders=256, block=400, clonal=True, stray=0.02, private_rate=0.002,
+                              gap_rate=1e-3, n_rate=1e-3, third_rate=1e-3)
     return make_alignment(n, l, seed=seed)
 
 
@@ -219,6 +223,13 @@ def run_ours(args):
     if args.ctas:
         ctx.set_cta_group(args.ctas)
 
+    out_buf = {"t": None}
+
+    def pinned_out(n):  # pinned host buffer for the survivors (grown on demand, reused across steps)
+        if out_buf["t"] is None or out_buf["t"].numel() < 20 * n:
+            out_buf["t"] = torch.empty(max(20 * n, 1 << 20), dtype=torch.uint8).pin_memory()
+        return out_buf["t"].numpy()[: 20 * (out_buf["t"].numel() // 20)].view(wld.PAIR_DTYPE)
+
     stages = {k: 0.0 for k in wld.STAGE_NAMES}
     launches = {"n": 0}
     state = {}
@@ -228,7 +239,7 @@ def run_ours(args):
         n_kept = ctx.filter_sites(*FILTER)
         ctx.henikoff()
         n_surv, done = ctx.ld_pairs(R2_THRESHOLD)
-        out = ctx.fetch_pairs(n_surv, wld.FETCH_KEPT_INDEX | wld.FETCH_UNORDERED) if fetch else None
+        out = ctx.fetch_pairs(n_surv, wld.FETCH_KEPT_INDEX | wld.FETCH_UNORDERED, out=pinned_out(n_surv)) if fetch else None
         state.update(n_kept=n_kept, n_surv=n_surv, done=done)
         if record:
             for i, nm in enumerate(wld.STAGE_NAMES):

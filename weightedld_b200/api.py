@@ -189,10 +189,14 @@ class Context:
         self._check(self._lib.wld_ld_pairs(self._h, r2_threshold, cb, None, C.byref(n), C.byref(done)))
         return n.value, done.value
 
-    def fetch_pairs(self, n: int, flags: int = L.FETCH_PARENT_INDEX) -> np.ndarray:
-        out = np.empty(n, PAIR_DTYPE)
+    def fetch_pairs(self, n: int, flags: int = L.FETCH_PARENT_INDEX, out: np.ndarray | None = None) -> np.ndarray:
+        """Survivors as a structured array.  `out` may be a preallocated (e.g. pinned) PAIR_DTYPE array."""
+        if out is None:
+            out = np.empty(n, PAIR_DTYPE)
+        elif out.dtype != PAIR_DTYPE or len(out) < n or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous PAIR_DTYPE array with room for n records")
         got = C.c_uint64()
-        self._check(self._lib.wld_fetch_pairs(self._h, _ptr(out), n, flags, C.byref(got)))
+        self._check(self._lib.wld_fetch_pairs(self._h, _ptr(out), len(out), flags, C.byref(got)))
         return out[: got.value]
 
     # ---- introspection

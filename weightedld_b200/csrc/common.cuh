@@ -112,6 +112,7 @@ struct wld_ctx {
   wld::DevBuf tiles;               // uint2 [n_tiles]
   wld::DevBuf pairs;               // wld_pair [pair_cap]
   wld::DevBuf counters;            // u64 [4]: survivors, pairs_done, ...
+  wld::DevBuf sorted, sort_keys, sort_idx, sort_temp;  // output ordering scratch (pair_order.cu)
   uint64_t pair_cap = 0;
   uint64_t n_survivors = 0;
   uint64_t pairs_computed = 0;
@@ -177,6 +178,7 @@ int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm);                       // pa
 // planning and the tile-list upload happen before the start event).
 int run_pair_simt(wld_ctx* c, float thr);                                  // pair_simt.cu
 int run_pair_umma(wld_ctx* c, float thr);                                  // pair_umma.cu
+int run_pair_order(wld_ctx* c, bool ordered, bool parent);                 // pair_order.cu
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 

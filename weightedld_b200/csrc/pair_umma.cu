@@ -40,6 +40,10 @@ constexpr int kBlockN = 256;
 constexpr int kBlockKBytes = 128;  // one 128-byte swizzle atom along K: 64 bf16 or 128 u8 elements
 constexpr int kUmmaKBytes = 32;    // one MMA consumes 32 bytes of K: 16 bf16 (kind::f16) or 32 u8 (kind::i8)
 constexpr int kAStageBytes = kBlockM * kBlockKBytes;  // 16 KB per CTA
+// Per-epilogue-warp candidate queue (see CandidateQueue): 64 entries of {4 x int64 sums, site_i, site_j}.
+constexpr int kQueueCap = 64;
+constexpr int kQueueBytesPerWarp = kQueueCap * (4 * 8 + 2 * 4);  // 2560 B
+constexpr int kNumEpiWarpsC = 8;
 // kCtas = 1: one CTA computes a 128 x 256 tile and stages all 256 B rows (32 KB) -> 4 stages of 48 KB.
 // kCtas = 2: a CTA pair (cta_group::2) computes 256 x 256; each CTA stages its 128 A rows and HALF of
 //            the B rows (16 KB) -> 6 stages of 32 KB; one third less L2->SMEM traffic per MMA.
@@ -48,7 +52,8 @@ template <int kCtas> struct StageCfg {
   static constexpr int kBBytes = kBRows * kBlockKBytes;
   static constexpr int kBytes = kAStageBytes + kBBytes;
   static constexpr int kStages = kCtas == 1 ? 4 : 6;
-  static constexpr int kSmemBytes = 1024 /*alignment slack*/ + kStages * kBytes + 256 /*barriers*/;
+  static constexpr int kQueueOffset = kStages * kBytes + 256;  // after the stage ring and the barriers
+  static constexpr int kSmemBytes = 1024 /*alignment slack*/ + kQueueOffset + kNumEpiWarpsC * kQueueBytesPerWarp;
 };
 constexpr int kNumThreads = 384;
 constexpr int kEpiWarp0 = 4;
@@ -272,6 +277,78 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* v) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Candidate queue.  The exact f64 statistics (about 170 FP64 instructions, 10 divisions) are far more
+// expensive than everything else in the epilogue and B200's FP64 pipe is narrow, so running them
+// whenever ANY lane of a warp holds a candidate wastes up to 31/32 of that work.  Each epilogue warp
+// instead appends its candidates (exact integer sums + site indices) to a private shared-memory queue
+// and runs the f64 path only on full groups of 32, one candidate per lane; the tail is drained when the
+// warp has finished its tiles.  FP64 work is then proportional to the number of candidates.
+// ------------------------------------------------------------------------------------------------
+struct CandidateQueue {
+  long long* sums;  // [4][kQueueCap]  AB, Ab, aB, ab
+  uint32_t* si;     // [kQueueCap]
+  uint32_t* sj;     // [kQueueCap]
+  int count;        // warp-uniform
+
+  __device__ __forceinline__ void init(uint8_t* base) {
+    sums = reinterpret_cast<long long*>(base);
+    si = reinterpret_cast<uint32_t*>(base + 4 * 8 * kQueueCap);
+    sj = si + kQueueCap;
+    count = 0;
+  }
+  // all 32 lanes call; lanes with `cand` append one record
+  __device__ __forceinline__ void push(bool cand, long long AB, long long Ab, long long aB, long long ab,
+                                       uint32_t i, uint32_t j) {
+    const unsigned ballot = __ballot_sync(0xffffffffu, cand);
+    if (cand) {
+      const int pos = count + __popc(ballot & ((1u << (threadIdx.x & 31)) - 1u));
+      sums[0 * kQueueCap + pos] = AB;
+      sums[1 * kQueueCap + pos] = Ab;
+      sums[2 * kQueueCap + pos] = aB;
+      sums[3 * kQueueCap + pos] = ab;
+      si[pos] = i;
+      sj[pos] = j;
+    }
+    count += __popc(ballot);
+    __syncwarp();
+  }
+  // all 32 lanes call; evaluates the first min(count, 32) records, one per lane, and removes them
+  __device__ __forceinline__ void drain32(float thr, const PairOut& out) {
+    const int lane = threadIdx.x & 31;
+    const int n = min(count, 32);
+    bool keep = lane < n;
+    float d = 0.f, dp = 0.f, r2 = 0.f;
+    uint32_t i = 0, j = 0;
+    if (keep) {
+      const double AB = (double)sums[0 * kQueueCap + lane], Ab = (double)sums[1 * kQueueCap + lane];
+      const double aB = (double)sums[2 * kQueueCap + lane], ab = (double)sums[3 * kQueueCap + lane];
+      i = si[lane];
+      j = sj[lane];
+      keep = ld_stats_exact(AB, Ab, aB, ab, thr, d, dp, r2);
+    }
+    emit_pairs_warp(keep, i, j, d, dp, r2, out);
+    __syncwarp();
+    // move the remaining (< 32) records to the front
+    const int rest = count - n;
+    long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    uint32_t ti = 0, tj = 0;
+    if (lane < rest) {
+      t0 = sums[0 * kQueueCap + n + lane]; t1 = sums[1 * kQueueCap + n + lane];
+      t2 = sums[2 * kQueueCap + n + lane]; t3 = sums[3 * kQueueCap + n + lane];
+      ti = si[n + lane]; tj = sj[n + lane];
+    }
+    __syncwarp();
+    if (lane < rest) {
+      sums[0 * kQueueCap + lane] = t0; sums[1 * kQueueCap + lane] = t1;
+      sums[2 * kQueueCap + lane] = t2; sums[3 * kQueueCap + lane] = t3;
+      si[lane] = ti; sj[lane] = tj;
+    }
+    count = rest;
+    __syncwarp();
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
 template <int NL, bool kI8, int kCtas>
@@ -294,6 +371,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
   auto tfull_bar = [&](int b) { return bars + 8u * (2 * kStages + b); };
   auto tempty_bar = [&](int b) { return bars + 8u * (2 * kStages + 2 + b); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kStages * Cfg::kBytes + 8 * (2 * kStages + 4));
+  static_assert(8 * (2 * kStages + 4) + 4 <= 256, "barrier block overflows its 256 bytes");
+  static_assert(kNumEpiWarps == kNumEpiWarpsC, "queue sizing");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = kCtas == 2 ? cluster_ctarank() : 0u;  // rank 0 = leader: issues the MMAs
@@ -386,13 +465,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
     const int half = (warp - kEpiWarp0) >> 2; // which 128-column group of the accumulator
     const int alpha = lane & 1;
-    double scale[NL];   // exact limb weights for the f64 path
-    float scale_f[NL];  // the same, pre-scaled by 2^-sum_shift, for the fp32 pre-filter
+    float scale_f[NL];  // limb weights 2^(b*(NL-1-l)), pre-scaled by 2^-sum_shift, for the fp32 pre-filter
 #pragma unroll
-    for (int l = 0; l < NL; ++l) {
-      scale[l] = (double)(1ull << (p.limb_bits * (NL - 1 - l)));
+    for (int l = 0; l < NL; ++l)
       scale_f[l] = __int_as_float((127 + p.limb_bits * (NL - 1 - l) - p.sum_shift) << 23);
-    }
+    CandidateQueue queue;
+    queue.init(smem + Cfg::kQueueOffset + (warp - kEpiWarp0) * kQueueBytesPerWarp);
     unsigned long long done = 0;
     uint32_t tcount = 0;
     for (int t = first_tile; t < p.n_tiles; t += tile_step, ++tcount) {
@@ -445,31 +523,28 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
           bool keep = valid && ld_prefilter_f32(alpha ? fr0 : fo0, alpha ? fr1 : fo1, alpha ? fo0 : fr0,
                                                 alpha ? fo1 : fr1, p.thr_lo_f, p.thr_negative != 0);
           if (__any_sync(0xffffffffu, keep)) {
-            // ---- f64 pass (candidates only): exact sums, lib.rs:482-518 operation for operation
-            double S[2][2];
+            // ---- candidates: exact integer sums (limbs recombined in int64), swap halves, enqueue
+            long long S[2][2];
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
               for (int beta = 0; beta < 2; ++beta) {
-                double s = 0.0;
+                long long acc = 0;
 #pragma unroll
                 for (int l = 0; l < NL; ++l) {
                   const uint32_t raw = v[jj * RPS + beta * NL + l];
-                  s = fma(kI8 ? (double)(int)raw : (double)__uint_as_float(raw), scale[l], s);  // exact
+                  const long long limb = kI8 ? (long long)(int)raw : (long long)__float2int_rn(__uint_as_float(raw));
+                  acc += limb << (p.limb_bits * (NL - 1 - l));
                 }
-                S[jj][beta] = s;
+                S[jj][beta] = acc;
               }
-            const double recv0 = __shfl_xor_sync(0xffffffffu, alpha ? S[0][0] : S[1][0], 1);
-            const double recv1 = __shfl_xor_sync(0xffffffffu, alpha ? S[0][1] : S[1][1], 1);
-            const double own0 = alpha ? S[1][0] : S[0][0];
-            const double own1 = alpha ? S[1][1] : S[0][1];
-            const double AB = alpha ? recv0 : own0;
-            const double Ab = alpha ? recv1 : own1;
-            const double aB = alpha ? own0 : recv0;
-            const double ab = alpha ? own1 : recv1;
-            float d = 0.f, dp = 0.f, r2 = 0.f;
-            if (keep) keep = ld_stats_exact(AB, Ab, aB, ab, p.thr, d, dp, r2);
-            emit_pairs_warp(keep, (uint32_t)site_i, (uint32_t)site_j, d, dp, r2, p.out);
+            const long long recv0 = __shfl_xor_sync(0xffffffffu, alpha ? S[0][0] : S[1][0], 1);
+            const long long recv1 = __shfl_xor_sync(0xffffffffu, alpha ? S[0][1] : S[1][1], 1);
+            const long long own0 = alpha ? S[1][0] : S[0][0];
+            const long long own1 = alpha ? S[1][1] : S[0][1];
+            queue.push(keep, alpha ? recv0 : own0, alpha ? recv1 : own1, alpha ? own0 : recv0, alpha ? own1 : recv1,
+                       (uint32_t)site_i, (uint32_t)site_j);
+            if (queue.count >= 32) queue.drain32(p.thr, p.out);  // f64 statistics, lib.rs:482-518, 32 at a time
           }
         }
       }
@@ -480,6 +555,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
         else mbar_arrive(tempty_bar(buf));
       }
     }
+    while (queue.count > 0) queue.drain32(p.thr, p.out);  // tail
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) done += __shfl_xor_sync(0xffffffffu, done, o);
     if (lane == 0 && done) atomicAdd(p.pairs_done, done);

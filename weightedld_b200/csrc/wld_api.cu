@@ -14,11 +14,6 @@ namespace {
   if (!(c)) return WLD_ERR_INVALID; \
   cudaSetDevice((c)->device)
 
-struct HostPairKey {
-  uint64_t tile;
-  uint32_t a, b;
-  uint32_t idx;
-};
 }  // namespace
 
 extern "C" {
@@ -61,7 +56,8 @@ void wld_destroy(wld_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->raw_own, &c->hist, &c->keep, &c->rank, &c->maj_raw, &c->min_raw, &c->site_map, &c->maj,
                     &c->mnr, &c->kept_count, &c->codes, &c->table, &c->partial, &c->w64, &c->w32, &c->scalars,
-                    &c->q, &c->limbs, &c->opA, &c->opB, &c->tiles, &c->pairs, &c->counters};
+                    &c->q, &c->limbs, &c->opA, &c->opB, &c->tiles, &c->pairs, &c->counters,
+                    &c->sorted, &c->sort_keys, &c->sort_idx, &c->sort_temp};
   for (DevBuf* b : bufs) b->release();
   for (auto& t : c->timers) {
     if (t.beg) cudaEventDestroy(t.beg);
@@ -373,34 +369,44 @@ int wld_fetch_pairs(wld_ctx* c, wld_pair* out, uint64_t cap, int flags, uint64_t
   if (n_written) *n_written = 0;
   if (cap < n) return c->fail(WLD_ERR_INVALID, "pair buffer holds %llu, need %llu", (unsigned long long)cap, (unsigned long long)n);
   if (n == 0) return WLD_OK;
-  std::vector<wld_pair> host((size_t)n);
-  WLD_CUDA(c, cudaMemcpyAsync(host.data(), c->pairs.p, sizeof(wld_pair) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  const bool ordered = !(flags & WLD_FETCH_UNORDERED), parent = !(flags & WLD_FETCH_KEPT_INDEX);
+  if (!ordered && !parent) {  // raw shard: straight device -> caller copy
+    WLD_CUDA(c, cudaMemcpyAsync(out, c->pairs.p, sizeof(wld_pair) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (n_written) *n_written = n;
+    return WLD_OK;
+  }
+  // Order (and map to raw columns) on the device, then one copy straight into the caller's buffer.
+  int rc = run_pair_order(c, ordered, parent);
+  if (rc == WLD_OK) {
+    WLD_CUDA(c, cudaMemcpyAsync(out, c->sorted.p, sizeof(wld_pair) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (n_written) *n_written = n;
+    return WLD_OK;
+  }
+  if (rc != WLD_ERR_NOMEM) return rc;
+  // Not enough device memory for the sort scratch: merge on the host (same order, slower).
+  WLD_CUDA(c, cudaMemcpyAsync(out, c->pairs.p, sizeof(wld_pair) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
   std::vector<int32_t> smap;
-  if (!(flags & WLD_FETCH_KEPT_INDEX)) {
+  if (parent) {
     smap.resize((size_t)c->n_kept);
     WLD_CUDA(c, cudaMemcpyAsync(smap.data(), c->site_map.p, sizeof(int32_t) * smap.size(), cudaMemcpyDeviceToHost, c->stream));
   }
   WLD_CUDA(c, cudaStreamSynchronize(c->stream));
-  std::vector<HostPairKey> keys;
-  if (!(flags & WLD_FETCH_UNORDERED)) {
-    keys.resize((size_t)n);
-    for (uint64_t i = 0; i < n; ++i)
-      keys[(size_t)i] = HostPairKey{wld_pair_order_key(c->n_kept, host[(size_t)i].site_a, host[(size_t)i].site_b),
-                                    host[(size_t)i].site_a, host[(size_t)i].site_b, (uint32_t)i};
-    std::sort(keys.begin(), keys.end(), [](const HostPairKey& x, const HostPairKey& y) {
-      if (x.tile != y.tile) return x.tile < y.tile;
-      if (x.a != y.a) return x.a < y.a;
-      return x.b < y.b;
+  if (ordered) {
+    const int64_t nk = c->n_kept;
+    std::sort(out, out + n, [nk](const wld_pair& x, const wld_pair& y) {
+      const uint64_t kx = wld_pair_order_key(nk, x.site_a, x.site_b), ky = wld_pair_order_key(nk, y.site_a, y.site_b);
+      if (kx != ky) return kx < ky;
+      if (x.site_a != y.site_a) return x.site_a < y.site_a;
+      return x.site_b < y.site_b;
     });
   }
-  for (uint64_t i = 0; i < n; ++i) {
-    wld_pair p = host[(size_t)(keys.empty() ? i : keys[(size_t)i].idx)];
-    if (!smap.empty()) {
-      p.site_a = (uint32_t)smap[p.site_a];  // lib.rs:662-663
-      p.site_b = (uint32_t)smap[p.site_b];
+  if (parent)
+    for (uint64_t i = 0; i < n; ++i) {
+      out[i].site_a = (uint32_t)smap[out[i].site_a];  // lib.rs:662-663
+      out[i].site_b = (uint32_t)smap[out[i].site_b];
     }
-    out[i] = p;
-  }
   if (n_written) *n_written = n;
   return WLD_OK;
 }
