@@ -28,6 +28,7 @@
 // Roofline: tensor pipe.  Algorithmic flop per site pair per launch = 8*N*NL (4 weighted dot
 // products of length N per limb); executed = 2*128*256*Kp per tile.
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "pair_epilogue.cuh"
@@ -654,7 +655,9 @@ TilePlan plan_tiles(int64_t L, int n_limbs, int part, int nparts, int sm_count, 
   const int64_t tile_m = plan.tile_m, tile_n = plan.tile_n;
   const int64_t n_mt = (L + tile_m - 1) / tile_m, n_nt = (L + tile_n - 1) / tile_n;
   std::vector<uint2> all;
-  constexpr int64_t kStrip = 8;
+  // strip width in N tiles; WLD_STRIP overrides it for experiments
+  int64_t kStrip = 8;
+  if (const char* e = std::getenv("WLD_STRIP")) kStrip = std::max(1, std::atoi(e));
   for (int64_t ns = 0; ns < n_nt; ns += kStrip) {
     const int64_t ne = std::min(ns + kStrip, n_nt);
     for (int64_t mi = 0; mi < n_mt; ++mi)
