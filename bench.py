@@ -8,7 +8,8 @@ One "step" = one pass of the whole hot path over one synthetic alignment: encode
 site filter -> Henikoff weights -> operand expansion -> tcgen05 Gram + fused epilogue + compaction.
 `value` times it with the alignment already resident in HBM; `e2e` runs the same through the
 C ABI from pinned HOST memory (H2D of the alignment and D2H of the surviving pairs inside the timed
-region).  With N ranks the upper-triangular tile grid is partitioned (no collective on the data
+region; with N > 1 ranks each rank copies only its 1/N of the rows over its own PCIe link and one NCCL
+all-gather over NVLink rebuilds the matrix on every GPU — weightedld_b200/multi_gpu.py).  With N ranks the upper-triangular tile grid is partitioned (no collective on the data
 path); the alignment is replicated; value = all pairs / max-over-ranks time ("strong" scaling: the
 total work is fixed).  Inputs (0.5-3 GB of text, 8 GB of operands) are far larger than the 126 MB
 L2, so no explicit flush is needed between iterations.
@@ -236,7 +237,14 @@ def run_ours(args):
     launches = {"n": 0}
     state = {}
 
+    loader = None
+    if world > 1:
+        from weightedld_b200.multi_gpu import ShardedLoader
+        loader = ShardedLoader(n_seqs, n_cols, rank, world, torch.device("cuda", local))
+
     def step(src, fetch: bool, record: bool):
+        if src is host_np and loader is not None:
+            src = loader.load(host)  # this rank's rows H2D + all-gather over NVLink
         ctx.load_alignment(src)
         n_kept = ctx.filter_sites(*FILTER)
         ctx.henikoff()
@@ -327,7 +335,10 @@ def run_ours(args):
             "stages_ms": {k: v / args.steps for k, v in stages.items()},
             "roofline": roof,
             "e2e": {"value": total_pairs / (ms_e2e * 1e-3), "unit": "site-pairs/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": int(chars_np.nbytes), "d2h_bytes_per_step": int(20 * state["n_surv"] + 64)},
+                    "h2d_bytes_per_step": int(chars_np.nbytes),  # whole job: each rank copies 1/N of the rows
+                    "d2h_bytes_per_step": int(20 * surv_all + 64 * world),
+                    "input_distribution": "host buffer -> one GPU" if world == 1 else
+                    f"rows sharded over {world} PCIe links + NCCL all-gather over NVLink"},
             "gpu_launches": launches["n"],
             "clocks": clocks.summary(),
         }

@@ -119,6 +119,18 @@ WLD_API int wld_set_partition(wld_ctx* ctx, int part, int nparts);
  * limbs could round — see DESIGN.md "precision contract"). */
 WLD_API int wld_set_limbs(wld_ctx* ctx, int n_limbs);
 WLD_API int wld_set_pair_kernel(wld_ctx* ctx, int kind);
+/* Numeric dialect.  WLD_COMPAT_RUST (default): the Rust crate, normative for this library.
+ * WLD_COMPAT_PYTHON: the reference's WeightedLD.py where the two differ —
+ *  - Henikoff contributions 1/count with the code-5 fill = sum / known sequences (WeightedLD.py:132-145;
+ *    the scalar `unique_base` cancels in the max-normalisation);
+ *  - alleles are called per PAIR after deleting the sequences with code 5 at either site
+ *    (WeightedLD.py:183-211): pairs where that can differ from the per-site call are recomputed by a
+ *    per-pair kernel, all others run on the tensor cores as usual;
+ *  - pairs whose PA or PB rounds to 1.0 at one decimal are skipped (WeightedLD.py:234-237).
+ * The Python program applies no r2 threshold (pass -INFINITY) and filters sites with
+ * wld_filter_sites_python.  Pairs with an empty marginal, printed as nan by Python, are dropped. */
+enum { WLD_COMPAT_RUST = 0, WLD_COMPAT_PYTHON = 1 };
+WLD_API int wld_set_compat(wld_ctx* ctx, int mode);
 /* CTAs cooperating on one tensor-core tile of the pair stage: 2 (default) = tcgen05 cta_group::2, a
  * CTA pair computes 256 x 256 and each CTA stages half of the limb operand; 1 = single-CTA 128 x 256. */
 WLD_API int wld_set_cta_group(wld_ctx* ctx, int ctas);
@@ -138,6 +150,10 @@ WLD_API int wld_load_alignment(wld_ctx* ctx, const uint8_t* data, int64_t n_seqs
  * and a minor symbol exist and min_minor <= minor/(minor+major) <= max_minor (f32).  Builds the
  * kept, site-major 0..5 code matrix on the device. */
 WLD_API int wld_filter_sites(wld_ctx* ctx, float min_acgt, float min_minor, float max_minor, int64_t* n_kept);
+/* compute_variable_sites (WeightedLD.py:44-98), the site filter of the Python program, all in f64:
+ * keep a site iff acgt/n_seqs > min_acgt and (known symbols other than the most frequent one, gaps
+ * included) / (known symbols) >= min_variability.  Same outputs as wld_filter_sites. */
+WLD_API int wld_filter_sites_python(wld_ctx* ctx, double min_acgt, double min_variability, int64_t* n_kept);
 /* Use every column unfiltered (the reference's unit tests call henikoff_weights and
  * single_weighted_ld_pair on unfiltered SiteSets, lib.rs:731-801). */
 WLD_API int wld_keep_all_sites(wld_ctx* ctx, int64_t* n_kept);

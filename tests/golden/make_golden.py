@@ -16,6 +16,7 @@ Two kinds of vectors are written:
   * fixtures.json      — the character matrices of the reference's FASTA fixtures (tiny test
                          DATA, so that the GPU box, which has no /root/reference, can run them).
   * t7_haplotypes.npz  — the 5008 x 6 allele matrix + POS of tests/t7_1000genome.vcf.
+  * t7_1000genome.vcf.gz — that fixture itself (test DATA), so the VCF readers can be tested on the GPU box.
 """
 import io
 import json
@@ -108,6 +109,46 @@ def main():
         "weights_distinct": sorted(set(np.round(w, 12).tolist())),
         "ld_stdout": buf.getvalue().splitlines(),
     }
+    # Synthetic alignment WITH ambiguity codes, near-ties between alleles and rare minors: pins the
+    # per-pair allele calls of WeightedLD.py:183-211 (none of the reference's own fixtures has code 5
+    # inside an LD site) and the PA/PB skip of WeightedLD.py:234-237.
+    rng = np.random.Generator(np.random.PCG64(20260118))
+    n_seq, n_site = 60, 26
+    founders = rng.integers(0, 2, size=(6, n_site))
+    owner = rng.integers(0, 6, size=n_seq)
+    syn = np.empty((n_seq, n_site), np.uint8)
+    for j in range(n_site):
+        maj, mnr, third = rng.permutation(4)[:3]
+        col = np.where(founders[owner, j] == 0, maj, mnr)
+        flip = rng.random(n_seq) < 0.15
+        col = np.where(flip, np.where(col == maj, mnr, maj), col)
+        col = np.where(rng.random(n_seq) < 0.06, third, col)
+        col = np.where(rng.random(n_seq) < 0.05, 4, col)
+        col = np.where(rng.random(n_seq) < (0.25 if j % 3 == 0 else 0.04), 5, col)
+        syn[:, j] = col
+    syn[:, 5] = np.where(np.arange(n_seq) < 58, 2, 1)          # rare minor: PA rounds to 1.0 for most weights
+    syn[:30, 7], syn[30:, 7] = 0, 3                              # exact tie between two alleles
+    syn[[3, 33], 7] = 5
+    hk, ldm = wld.compute_variable_sites(syn, 0.5, 0.02)
+    w_syn = wld.henikoff_weighting(syn)
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        wld.ld(syn, w_syn, np.arange(n_site))
+    sub = syn[:, ldm]
+    w_sub = wld.henikoff_weighting(sub)
+    buf2 = io.StringIO()
+    with redirect_stdout(buf2):
+        wld.ld(sub, w_sub, np.where(ldm)[0])
+    pyref["synthetic_ambiguous"] = {
+        "alignment": ["".join(map(str, r)) for r in syn.tolist()],
+        "min_acgt": 0.5, "min_variability": 0.02,
+        "var_sites_hk": hk.tolist(), "var_sites_ld": ldm.tolist(),
+        "weights_all_sites": w_syn.tolist(), "ld_stdout_all_sites": buf.getvalue().splitlines(),
+        "weights_on_ld_sites": w_sub.tolist(), "ld_stdout": buf2.getvalue().splitlines(),
+    }
+    import gzip
+    (OUT / "t7_1000genome.vcf.gz").write_bytes(gzip.compress((REF / "tests" / "t7_1000genome.vcf").read_bytes(), mtime=0))
+
     # all six variant rows (the Python reader drops the last, WeightedLD.py:365)
     rows, pos = [], []
     for line in (REF / "tests" / "t7_1000genome.vcf").read_text().split("\n"):

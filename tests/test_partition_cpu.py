@@ -111,3 +111,59 @@ def test_two_rank_partition_and_merge_gloo():
     assert total == computed            # the two parts cover every pair exactly once
     assert ms == 11.0                   # max over ranks
     assert ok and n_ref > 100 and min(sizes) > 0
+
+
+def _loader_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    import torch
+    import torch.distributed as dist
+
+    from weightedld_b200.multi_gpu import ShardedLoader, gather_pairs, shard_rows
+    import weightedld_b200 as wld
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ok = True
+    for n_seqs, n_cols in ((7, 5), (64, 33), (101, 48)):
+        chars = torch.from_numpy(np.random.default_rng(1).integers(0, 255, (n_seqs, n_cols), dtype=np.uint8))
+        ld = ShardedLoader(n_seqs, n_cols, rank, world, torch.device("cpu"))
+        lo, hi, per = shard_rows(n_seqs, rank, world)
+        full = ld.load(chars)                 # every rank passes the whole matrix
+        ok &= bool(torch.equal(full, chars)) and full.stride(0) % 16 == 0 and ld.h2d_bytes == (hi - lo) * n_cols
+        full2 = ld.load(chars[lo:hi])         # or only its own rows
+        ok &= bool(torch.equal(full2, chars))
+    shard = np.zeros(3, wld.PAIR_DTYPE)
+    shard["site_a"] = [rank, rank, 300 + rank]
+    shard["site_b"] = [rank + 5, rank + 300, 400 + rank]
+    merged = gather_pairs(shard, 600, None, rank, world)
+    if rank == 0:
+        key = wld.pair_order_key(600, merged["site_a"], merged["site_b"])
+        ok &= len(merged) == 3 * world and bool(np.all(np.diff(key.astype(np.int64)) >= 0))
+    else:
+        ok &= merged is None
+    t = torch.tensor([1 if ok else 0])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        q.put(int(t.item()))
+    dist.destroy_process_group()
+
+
+def test_sharded_input_broadcast_and_output_gather_gloo():
+    """multi_gpu.ShardedLoader (rows sharded over the ranks' host links + all-gather) and gather_pairs,
+    world size 2 over gloo."""
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_loader_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    assert q.get(timeout=240) == 1
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0

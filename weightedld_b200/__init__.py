@@ -10,7 +10,10 @@ from ._lib import (FETCH_KEPT_INDEX, FETCH_PARENT_INDEX, FETCH_UNORDERED, PAIR_D
 from .api import (Context, MultiSequence, PairStore, SiteSet, all_weighted_ld_pairs, format_f3, henikoff_weights,
                   merge_shards, pair_order_key, plan_tiles, read_fasta, single_weighted_ld_pair, write_henikoff_weights, write_pair_stats)
 
+from . import pycompat  # mirror of the reference's Python program (WeightedLD.py), WLD_COMPAT_PYTHON
+
 __all__ = [
+    "pycompat",
     "Context", "MultiSequence", "PairStore", "SiteSet", "WldError", "all_weighted_ld_pairs", "format_f3",
     "henikoff_weights", "merge_shards", "pair_order_key", "plan_tiles", "read_fasta", "single_weighted_ld_pair", "write_henikoff_weights",
     "write_pair_stats", "PAIR_DTYPE",

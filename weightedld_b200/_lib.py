@@ -20,6 +20,7 @@ WLD_OK = 0
 INPUT_ASCII, INPUT_CODES, INPUT_DEVICE = 0, 1, 2
 FETCH_PARENT_INDEX, FETCH_KEPT_INDEX, FETCH_UNORDERED = 0, 1, 2
 PAIR_KERNEL_UMMA, PAIR_KERNEL_SIMT, PAIR_KERNEL_UMMA_I8 = 0, 1, 2
+COMPAT_RUST, COMPAT_PYTHON = 0, 1
 STAGE_LOAD, STAGE_HISTOGRAM, STAGE_FILTER, STAGE_HENIKOFF, STAGE_PAIR_PREP, STAGE_PAIR = range(6)
 STAGE_NAMES = ["load", "histogram", "filter", "henikoff", "pair_prep", "pair"]
 STATUS_NAMES = {0: "OK", 1: "INVALID", 2: "STATE", 3: "CUDA", 4: "NOMEM", 5: "UNSUPPORTED", 6: "PANIC"}
@@ -72,6 +73,8 @@ SIGNATURES = {
     "wld_pair_order_key": (_u64, [_i64, C.c_uint32, C.c_uint32]),
     "wld_plan_tiles": (_int, [_i64, _int, _int, _int, _int, _int, _vp, _u64, C.POINTER(_u64), C.POINTER(_u64)]),
     "wld_set_cta_group": (_int, [_vp, _int]),
+    "wld_set_compat": (_int, [_vp, _int]),
+    "wld_filter_sites_python": (_int, [_vp, C.c_double, C.c_double, C.POINTER(_i64)]),
     "wld_stage_ms": (_int, [_vp, _int, C.POINTER(C.c_float)]),
     "wld_stage_launches": (_int, [_vp, _int, C.POINTER(_int)]),
     "wld_get_pair_info": (_int, [_vp, C.POINTER(PairInfo)]),

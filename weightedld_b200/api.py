@@ -86,6 +86,12 @@ class Context:
             kind = {"umma": L.PAIR_KERNEL_UMMA, "bf16": L.PAIR_KERNEL_UMMA, "simt": L.PAIR_KERNEL_SIMT, "i8": L.PAIR_KERNEL_UMMA_I8}[kind]
         self._check(self._lib.wld_set_pair_kernel(self._h, kind))
 
+    def set_compat(self, mode: int | str):
+        """'rust' (default) or 'python': numeric dialect, see wld_set_compat in include/wld.h."""
+        if isinstance(mode, str):
+            mode = {"rust": L.COMPAT_RUST, "python": L.COMPAT_PYTHON}[mode]
+        self._check(self._lib.wld_set_compat(self._h, mode))
+
     def set_cta_group(self, ctas: int):
         self._check(self._lib.wld_set_cta_group(self._h, ctas))
 
@@ -124,6 +130,12 @@ class Context:
     def filter_sites(self, min_acgt: float = 0.8, min_minor: float = 0.02, max_minor: float = 0.5) -> int:
         n = C.c_int64()
         self._check(self._lib.wld_filter_sites(self._h, min_acgt, min_minor, max_minor, C.byref(n)))
+        return n.value
+
+    def filter_sites_python(self, min_acgt: float = 0.8, min_variability: float = 0.02) -> int:
+        """compute_variable_sites of the Python program (WeightedLD.py:44-98), LD mask."""
+        n = C.c_int64()
+        self._check(self._lib.wld_filter_sites_python(self._h, min_acgt, min_variability, C.byref(n)))
         return n.value
 
     def keep_all_sites(self) -> int:

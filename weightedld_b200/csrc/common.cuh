@@ -77,6 +77,7 @@ struct wld_ctx {
   int n_limbs_opt = 3;
   int pair_kernel = WLD_PAIR_KERNEL_UMMA_I8;  // fastest exact path on sm_100a; bf16 and SIMT selectable
   uint64_t pair_cap_opt = 0;
+  int compat = WLD_COMPAT_RUST;    // numeric dialect (wld_set_compat)
   int cta_group = 2;               // CTAs cooperating on one MMA tile (tcgen05 cta_group::1 / ::2)
 
   // stage 1
@@ -112,6 +113,7 @@ struct wld_ctx {
   wld::DevBuf tiles;               // uint2 [n_tiles]
   wld::DevBuf pairs;               // wld_pair [pair_cap]
   wld::DevBuf counters;            // u64 [4]: survivors, pairs_done, ...
+  wld::DevBuf py_aux;              // uint2 [n_kept] {n5, margin}: WLD_COMPAT_PYTHON only (pair_python.cu)
   wld::DevBuf sorted, sort_keys, sort_idx, sort_temp;  // output ordering scratch (pair_order.cu)
   uint64_t pair_cap = 0;
   uint64_t n_survivors = 0;
@@ -170,8 +172,10 @@ struct ScopedStageTimer {
 
 // ---- stage launchers (each in its own .cu) ------------------------------------------------------
 int run_histogram(wld_ctx* c, ScopedStageTimer& tm);                       // encode_filter.cu
-int run_filter(wld_ctx* c, bool keep_all, float min_acgt, float min_minor, float max_minor,
-               ScopedStageTimer& tm);                                      // encode_filter.cu
+// mode 0: is_site_of_interest (lib.rs:310-338); 1: keep every column; 2: compute_variable_sites
+// (WeightedLD.py:44-98) with the f64 thresholds py_min_acgt / py_min_variability
+int run_filter(wld_ctx* c, int mode, float min_acgt, float min_minor, float max_minor, double py_min_acgt,
+               double py_min_variability, ScopedStageTimer& tm);           // encode_filter.cu
 int run_henikoff(wld_ctx* c, ScopedStageTimer& tm);                        // henikoff.cu
 int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm);                       // pair_prep.cu
 // The pair launchers bracket ONLY the kernel launch with the WLD_STAGE_PAIR timer (host-side
@@ -179,6 +183,8 @@ int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm);                       // pa
 int run_pair_simt(wld_ctx* c, float thr);                                  // pair_simt.cu
 int run_pair_umma(wld_ctx* c, float thr);                                  // pair_umma.cu
 int run_pair_order(wld_ctx* c, bool ordered, bool parent);                 // pair_order.cu
+int run_pair_python_prepare(wld_ctx* c);                                   // pair_python.cu
+int run_pair_python_fixup(wld_ctx* c, float thr);                          // pair_python.cu
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 

@@ -7,6 +7,7 @@
 //   major_minor_symbols                      lib.rs:126-140
 //   is_site_of_interest + threshold          lib.rs:310-338, main.rs:139
 //   SiteSet::from_multiseq / filter_by       lib.rs:176-206, 230-251
+//   compute_variable_sites (Python dialect)  WeightedLD.py:44-98
 //
 // All three kernels are HBM-bound byte kernels.  Algorithmic bytes: n_seqs*n_cols read for the
 // histogram; n_seqs*n_cols read + n_seqs*n_kept written for the gather (tiles without a kept
@@ -148,8 +149,9 @@ __global__ void __launch_bounds__(256) hist_generic_kernel(const uint8_t* __rest
 // major/minor scan of lib.rs:126-140 and the filter of lib.rs:310-338.
 // ---------------------------------------------------------------------------------------------
 __global__ void decide_kernel(uint32_t* __restrict__ hist, int64_t cols_padded, int64_t n_cols,
-                              int64_t n_seqs, bool keep_all, unsigned long long min_acgt, float min_minor,
-                              float max_minor, uint8_t* __restrict__ keep, int8_t* __restrict__ maj_raw,
+                              int64_t n_seqs, int mode, unsigned long long min_acgt, float min_minor,
+                              float max_minor, double py_min_acgt, double py_min_variability,
+                              uint8_t* __restrict__ keep, int8_t* __restrict__ maj_raw,
                               int8_t* __restrict__ min_raw) {
   const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= cols_padded) return;
@@ -184,7 +186,16 @@ __global__ void decide_kernel(uint32_t* __restrict__ hist, int64_t cols_padded, 
   min_raw[col] = (int8_t)mnr;
 
   bool k = true;
-  if (!keep_all) {
+  if (mode == 2) {
+    // WeightedLD.py:64-95 (return_ld_varsites), all in f64: concrete fraction acgt/n > min_acgt, and
+    // (everything that is not the major symbol, gaps included) / (known symbols) >= min_variability.
+    const double acgt = (double)((unsigned long long)h[0] + h[1] + h[2] + h[3]);
+    const bool sufficient = __ddiv_rn(acgt, (double)n_seqs) > py_min_acgt;          // WeightedLD.py:65-68
+    const uint32_t major = maj >= 0 ? h[maj] : 0u;                                   // WeightedLD.py:76
+    const uint32_t minor = sum - major;                                              // WeightedLD.py:77
+    const double frac = minor > 0u ? __ddiv_rn((double)minor, (double)sum) : 0.0;    // WeightedLD.py:80-84
+    k = sufficient && frac >= py_min_variability;                                    // WeightedLD.py:87-95
+  } else if (mode == 0) {
     const unsigned long long acgt = (unsigned long long)h[0] + h[1] + h[2] + h[3];  // lib.rs:106-109
     if (acgt <= min_acgt) {                                                        // lib.rs:315
       k = false;
@@ -377,8 +388,8 @@ int run_histogram(wld_ctx* c, ScopedStageTimer& tm) {
   return WLD_OK;
 }
 
-int run_filter(wld_ctx* c, bool keep_all, float min_acgt, float min_minor, float max_minor,
-               ScopedStageTimer& tm) {
+int run_filter(wld_ctx* c, int mode, float min_acgt, float min_minor, float max_minor, double py_min_acgt,
+               double py_min_variability, ScopedStageTimer& tm) {
   const bool ascii = !(c->input_flags & WLD_INPUT_CODES);
   const int64_t cp = c->cols_padded;
   WLD_CUDA(c, c->keep.ensure((size_t)cp + 16));
@@ -395,8 +406,8 @@ int run_filter(wld_ctx* c, bool keep_all, float min_acgt, float min_minor, float
   }
   if (cp > 0) {
     decide_kernel<<<(unsigned)((cp + 255) / 256), 256, 0, c->stream>>>(
-        c->hist.as<uint32_t>(), cp, c->n_cols, c->n_seqs, keep_all, min_count, min_minor, max_minor,
-        c->keep.as<uint8_t>(), c->maj_raw.as<int8_t>(), c->min_raw.as<int8_t>());
+        c->hist.as<uint32_t>(), cp, c->n_cols, c->n_seqs, mode, min_count, min_minor, max_minor, py_min_acgt,
+        py_min_variability, c->keep.as<uint8_t>(), c->maj_raw.as<int8_t>(), c->min_raw.as<int8_t>());
     tm.launched();
   }
   scan_kernel<<<1, kScanThreads, 0, c->stream>>>(c->keep.as<uint8_t>(), cp, c->rank.as<int32_t>(),

@@ -20,8 +20,12 @@ namespace {
 constexpr int kSiteChunk = 256;
 constexpr int kAccThreads = 256;
 
+// python_mode (WeightedLD.py:125-145): contribution 1/count[code] (the scalar unique_base of
+// WeightedLD.py:132 cancels in the normalisation), code-5 fill = sum of the known contributions divided
+// by the number of KNOWN sequences at the site.
 __global__ void table_kernel(const uint32_t* __restrict__ hist, int64_t cols_padded,
-                             const int32_t* __restrict__ site_map, int64_t n_kept, double* __restrict__ table) {
+                             const int32_t* __restrict__ site_map, int64_t n_kept, bool python_mode,
+                             double* __restrict__ table) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_kept) return;
   const int64_t col = site_map[k];
@@ -32,7 +36,7 @@ __global__ void table_kernel(const uint32_t* __restrict__ hist, int64_t cols_pad
     n[c] = hist[(int64_t)c * cols_padded + col];
     distinct += n[c] > 0;  // lib.rs:116-124
   }
-  const double kd = (double)distinct;
+  const double kd = python_mode ? 1.0 : (double)distinct;
   double total = 0.0;  // lib.rs:364-371: sum of the contributions of the known sequences
   double t[8];
 #pragma unroll
@@ -40,7 +44,12 @@ __global__ void table_kernel(const uint32_t* __restrict__ hist, int64_t cols_pad
     t[c] = n[c] > 0 ? __ddiv_rn(1.0, __dmul_rn(kd, (double)n[c])) : 0.0;  // lib.rs:368
     if (n[c] > 0) total = __dadd_rn(total, __dmul_rn((double)n[c], t[c]));
   }
-  t[5] = __ddiv_rn(total, kd);  // lib.rs:373 (0/0 = NaN when the site has no known symbol)
+  if (python_mode) {
+    const double known = (double)n[0] + (double)n[1] + (double)n[2] + (double)n[3] + (double)n[4];
+    t[5] = __ddiv_rn(total, known);  // WeightedLD.py:142-145
+  } else {
+    t[5] = __ddiv_rn(total, kd);  // lib.rs:373 (0/0 = NaN when the site has no known symbol)
+  }
   t[6] = 0.0;
   t[7] = 0.0;
 #pragma unroll
@@ -123,7 +132,7 @@ int run_henikoff(wld_ctx* c, ScopedStageTimer& tm) {
   if (L > 0) {
     table_kernel<<<(unsigned)((L + 255) / 256), 256, 0, c->stream>>>(c->hist.as<uint32_t>(), c->cols_padded,
                                                                     c->site_map.as<int32_t>(), L,
-                                                                    c->table.as<double>());
+                                                                    c->compat == WLD_COMPAT_PYTHON, c->table.as<double>());
     tm.launched();
     dim3 grid((unsigned)((c->ldc / 4 + kAccThreads - 1) / kAccThreads), (unsigned)n_chunks);
     if (grid.y > 65535) return c->fail(WLD_ERR_UNSUPPORTED, "too many kept sites for the Henikoff grid");

@@ -72,8 +72,10 @@ __host__ __device__ inline double ld_thr_lo(float thr) {
 }
 
 // lib.rs:482-518 in f64.  Returns true when the pair survives `r2 > thr` (f32 compare).
+// `python_skip` adds WeightedLD.py:234-237: skip when round(PA,1) == 1.0 or round(PB,1) == 1.0.  PA is a
+// numpy float64 there, whose __round__ is rint(x*10)/10 (ties to even), so the test is fl(PA*10) >= 9.5.
 __device__ __forceinline__ bool ld_stats_exact(double AB, double Ab, double aB, double ab, float thr, float& d_out,
-                                               float& dprime_out, float& r2_out) {
+                                               float& dprime_out, float& r2_out, bool python_skip = false) {
   // total_weight, PA, PB, ld_obs[3] as the reference accumulates them (lib.rs:469-479); exact here.
   const double total = __dadd_rn(__dadd_rn(AB, Ab), __dadd_rn(aB, ab));
   double PA = __dadd_rn(AB, Ab);
@@ -92,6 +94,7 @@ __device__ __forceinline__ bool ld_stats_exact(double AB, double Ab, double aB, 
   o1 = __ddiv_rn(o1, total);
   o2 = __ddiv_rn(o2, total);
   o3 = __ddiv_rn(o3, total);
+  if (python_skip && (__dmul_rn(PA, 10.0) >= 9.5 || __dmul_rn(PB, 10.0) >= 9.5)) return false;
   const double PAB = __dmul_rn(PA, PB);  // lib.rs:497-500
   const double PAb = __dmul_rn(PA, Pb);
   const double PaB = __dmul_rn(Pa, PB);
@@ -114,6 +117,18 @@ __device__ __forceinline__ bool ld_stats_exact(double AB, double Ab, double aB, 
   dprime_out = (float)dprime;
   r2_out = (float)r2;
   return r2_out > thr;  // lib.rs:660 (NaN fails)
+}
+
+// WLD_COMPAT_PYTHON.  WeightedLD.py:186-211 calls the major / dominant-minor allele of each site PER PAIR,
+// after deleting the sequences that hold code 5 at either site; the Gram recast calls them per site.  Both
+// give the same alleles unless the deletions can reorder a site's top symbols.  aux[k] = {n5, margin} of
+// kept site k: n5 = sequences with code 5, margin = min(count[major] - count[minor], count[minor] -
+// count[third]) (third = 0 when absent).  Deleting at most n5_j sequences cannot change site i's call, nor
+// empty its minor, while n5_j < margin_i; pairs that fail this test are left to the per-pair kernel
+// (pair_python.cu) and must not be emitted by the Gram kernels.
+__device__ __forceinline__ bool py_flagged(const uint2* __restrict__ aux, uint32_t i, uint32_t j) {
+  const uint2 a = aux[i], b = aux[j];
+  return (b.x > 0u && b.x >= a.y) || (a.x > 0u && a.x >= b.y);
 }
 
 // Warp-aggregated compaction: one atomicAdd per warp, survivors written to consecutive slots.

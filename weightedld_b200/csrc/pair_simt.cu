@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) pair_simt_kernel(const uint8_t* __restric
                                                         const int8_t* __restrict__ mnr,
                                                         const double* __restrict__ q,
                                                         const uint2* __restrict__ tiles, float thr, double thr_lo,
-                                                        PairOut out, unsigned long long* __restrict__ pairs_done) {
+                                                        const uint2* __restrict__ py_aux, PairOut out, unsigned long long* __restrict__ pairs_done) {
   __shared__ double sAM[kKC][kTile], sAm[kKC][kTile], sBM[kKC][kTile], sBm[kKC][kTile];
   const uint2 tile = tiles[blockIdx.x];
   const int64_t i0 = (int64_t)tile.x * kTile, j0 = (int64_t)tile.y * kTile;
@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(256) pair_simt_kernel(const uint8_t* __restric
       done += valid;
       bool keep = valid && ld_prefilter(acc[u][v][0], acc[u][v][1], acc[u][v][2], acc[u][v][3], thr_lo);
       float d = 0.f, dp = 0.f, r2 = 0.f;
-      if (keep) keep = ld_stats_exact(acc[u][v][0], acc[u][v][1], acc[u][v][2], acc[u][v][3], thr, d, dp, r2);
+      if (keep) keep = ld_stats_exact(acc[u][v][0], acc[u][v][1], acc[u][v][2], acc[u][v][3], thr, d, dp, r2, py_aux != nullptr);
+      if (py_aux != nullptr && keep) keep = !py_flagged(py_aux, (uint32_t)i, (uint32_t)j);  // left to pair_python.cu
       emit_pairs_warp(keep, (uint32_t)i, (uint32_t)j, d, dp, r2, out);
     }
 #pragma unroll
@@ -122,7 +123,8 @@ int run_pair_simt(wld_ctx* c, float thr) {
   PairOut out{c->pairs.as<wld_pair>(), c->counters.as<unsigned long long>(), c->pair_cap};
   pair_simt_kernel<<<(unsigned)list.size(), 256, 0, c->stream>>>(
       c->codes.as<uint8_t>(), c->ldc, L, c->n_seqs, c->maj.as<int8_t>(), c->mnr.as<int8_t>(), c->q.as<double>(),
-      c->tiles.as<uint2>(), thr, ld_thr_lo(thr), out, c->counters.as<unsigned long long>() + 1);
+      c->tiles.as<uint2>(), thr, ld_thr_lo(thr),
+      c->compat == WLD_COMPAT_PYTHON ? c->py_aux.as<uint2>() : nullptr, out, c->counters.as<unsigned long long>() + 1);
   tm.launched();
   WLD_CUDA(c, cudaGetLastError());
   return WLD_OK;

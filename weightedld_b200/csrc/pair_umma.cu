@@ -73,6 +73,8 @@ struct UmmaParams {
   float thr_lo_f;     // fp32 pre-filter threshold (lowered, see ld_prefilter_f32)
   int thr_negative;   // threshold below zero: every pair with non-empty marginals is a candidate
   int sum_shift;      // fp32 pre-filter works on sums scaled by 2^-sum_shift so that T <= 2^21
+  uint64_t hint_a, hint_b;  // L2 eviction policy of the indicator (streamed) and limb (strip-resident) panels
+  const uint2* py_aux; // WLD_COMPAT_PYTHON only (else null): per-site {n5, margin}, see py_flagged
   PairOut out;
   unsigned long long* pairs_done;
   int* error_flag;
@@ -124,10 +126,17 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, int c0, int c1, uint32_t bar) {
+// L2 cache policies for TMA loads (the encodings CUTLASS passes as .L2::cache_hint operands)
+constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull;
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, int c0, int c1, uint32_t bar,
+                                            uint64_t hint) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(bar)
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(bar), "l"(hint)
       : "memory");
 }
 
@@ -144,10 +153,12 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // 2-CTA TMA load: data lands in THIS CTA's smem, the transaction bytes are counted on CTA 0's barrier
-__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* m, int c0, int c1, uint32_t bar) {
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* m, int c0, int c1, uint32_t bar,
+                                                uint64_t hint) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(bar & kPeerBitMask)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(bar & kPeerBitMask), "l"(hint)
       : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_cg2(uint32_t slot_smem, uint32_t ncols) {
@@ -314,7 +325,7 @@ struct CandidateQueue {
     __syncwarp();
   }
   // all 32 lanes call; evaluates the first min(count, 32) records, one per lane, and removes them
-  __device__ __forceinline__ void drain32(float thr, const PairOut& out) {
+  __device__ __forceinline__ void drain32(float thr, const PairOut& out, const uint2* __restrict__ py_aux) {
     const int lane = threadIdx.x & 31;
     const int n = min(count, 32);
     bool keep = lane < n;
@@ -325,7 +336,8 @@ struct CandidateQueue {
       const double aB = (double)sums[2 * kQueueCap + lane], ab = (double)sums[3 * kQueueCap + lane];
       i = si[lane];
       j = sj[lane];
-      keep = ld_stats_exact(AB, Ab, aB, ab, thr, d, dp, r2);
+      keep = ld_stats_exact(AB, Ab, aB, ab, thr, d, dp, r2, py_aux != nullptr);
+      if (py_aux != nullptr && keep) keep = !py_flagged(py_aux, i, j);  // left to pair_python.cu
     }
     emit_pairs_warp(keep, i, j, d, dp, r2, out);
     __syncwarp();
@@ -417,12 +429,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
           mbar_wait(empty_bar(stage), phase ^ 1u, p.error_flag, 1);
           if constexpr (kCtas == 2) {
             if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::kBytes);
-            tma_load_2d_cg2(sA + stage * kAStageBytes, &tmA, kb * kBlockK, m_row, full_bar(stage));
-            tma_load_2d_cg2(sB + stage * Cfg::kBBytes, &tmB, kb * kBlockK, n_row, full_bar(stage));
+            tma_load_2d_cg2(sA + stage * kAStageBytes, &tmA, kb * kBlockK, m_row, full_bar(stage), p.hint_a);
+            tma_load_2d_cg2(sB + stage * Cfg::kBBytes, &tmB, kb * kBlockK, n_row, full_bar(stage), p.hint_b);
           } else {
             mbar_expect_tx(full_bar(stage), Cfg::kBytes);
-            tma_load_2d(sA + stage * kAStageBytes, &tmA, kb * kBlockK, m_row, full_bar(stage));
-            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, kb * kBlockK, n_row, full_bar(stage));
+            tma_load_2d(sA + stage * kAStageBytes, &tmA, kb * kBlockK, m_row, full_bar(stage), p.hint_a);
+            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, kb * kBlockK, n_row, full_bar(stage), p.hint_b);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -545,7 +557,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
             const long long own1 = alpha ? S[1][1] : S[0][1];
             queue.push(keep, alpha ? recv0 : own0, alpha ? recv1 : own1, alpha ? own0 : recv0, alpha ? own1 : recv1,
                        (uint32_t)site_i, (uint32_t)site_j);
-            if (queue.count >= 32) queue.drain32(p.thr, p.out);  // f64 statistics, lib.rs:482-518, 32 at a time
+            if (queue.count >= 32) queue.drain32(p.thr, p.out, p.py_aux);  // f64 statistics, lib.rs:482-518, 32 at a time
           }
         }
       }
@@ -556,7 +568,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
         else mbar_arrive(tempty_bar(buf));
       }
     }
-    while (queue.count > 0) queue.drain32(p.thr, p.out);  // tail
+    while (queue.count > 0) queue.drain32(p.thr, p.out, p.py_aux);  // tail
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) done += __shfl_xor_sync(0xffffffffu, done, o);
     if (lane == 0 && done) atomicAdd(p.pairs_done, done);
@@ -719,6 +731,18 @@ int run_pair_umma(wld_ctx* c, float thr) {
   prm.limb_bits = gm.limb_bits;
   prm.thr = thr;
   prm.thr_lo = ld_thr_lo(thr);
+  prm.py_aux = c->compat == WLD_COMPAT_PYTHON ? c->py_aux.as<uint2>() : nullptr;
+  {
+    // Within a strip the limb panels (B) are reused by every M tile while the indicator panels (A) stream
+    // past once: keep B, let A go first.  WLD_HINT_A / WLD_HINT_B = normal|first|last override (experiments).
+    auto policy = [](const char* env, uint64_t dflt) {
+      const char* e = std::getenv(env);
+      if (!e) return dflt;
+      return e[0] == 'f' ? kL2EvictFirst : e[0] == 'l' ? kL2EvictLast : kL2EvictNormal;
+    };
+    prm.hint_a = policy("WLD_HINT_A", kL2EvictNormal);
+    prm.hint_b = policy("WLD_HINT_B", kL2EvictNormal);
+  }
   {
     // fp32 pre-filter threshold: lowered once more by 1e-5 relative, rounded towards -inf
     const double lo = prm.thr_lo;

@@ -56,7 +56,7 @@ void wld_destroy(wld_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->raw_own, &c->hist, &c->keep, &c->rank, &c->maj_raw, &c->min_raw, &c->site_map, &c->maj,
                     &c->mnr, &c->kept_count, &c->codes, &c->table, &c->partial, &c->w64, &c->w32, &c->scalars,
-                    &c->q, &c->limbs, &c->opA, &c->opB, &c->tiles, &c->pairs, &c->counters,
+                    &c->q, &c->limbs, &c->opA, &c->opB, &c->tiles, &c->pairs, &c->counters, &c->py_aux,
                     &c->sorted, &c->sort_keys, &c->sort_idx, &c->sort_temp};
   for (DevBuf* b : bufs) b->release();
   for (auto& t : c->timers) {
@@ -95,6 +95,13 @@ int wld_set_pair_kernel(wld_ctx* c, int kind) {
   WLD_CHECK_CTX(c);
   if (kind != WLD_PAIR_KERNEL_UMMA && kind != WLD_PAIR_KERNEL_SIMT && kind != WLD_PAIR_KERNEL_UMMA_I8) return c->fail(WLD_ERR_INVALID, "unknown pair kernel %d", kind);
   c->pair_kernel = kind;
+  return WLD_OK;
+}
+
+int wld_set_compat(wld_ctx* c, int mode) {
+  WLD_CHECK_CTX(c);
+  if (mode != WLD_COMPAT_RUST && mode != WLD_COMPAT_PYTHON) return c->fail(WLD_ERR_INVALID, "unknown compat mode %d", mode);
+  c->compat = mode;
   return WLD_OK;
 }
 
@@ -152,11 +159,12 @@ int wld_load_alignment(wld_ctx* c, const uint8_t* data, int64_t n_seqs, int64_t 
   return WLD_OK;
 }
 
-static int filter_common(wld_ctx* c, bool keep_all, float min_acgt, float min_minor, float max_minor, int64_t* n_kept) {
+static int filter_common(wld_ctx* c, int mode, float min_acgt, float min_minor, float max_minor, double py_min_acgt,
+                         double py_min_variability, int64_t* n_kept) {
   if (c->stage < Stage::Loaded) return c->fail(WLD_ERR_STATE, "wld_filter_sites before wld_load_alignment");
   {
     ScopedStageTimer tm(c, WLD_STAGE_FILTER);
-    int rc = run_filter(c, keep_all, min_acgt, min_minor, max_minor, tm);
+    int rc = run_filter(c, mode, min_acgt, min_minor, max_minor, py_min_acgt, py_min_variability, tm);
     if (rc != WLD_OK) return rc;
   }
   WLD_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -167,12 +175,17 @@ static int filter_common(wld_ctx* c, bool keep_all, float min_acgt, float min_mi
 
 int wld_filter_sites(wld_ctx* c, float min_acgt, float min_minor, float max_minor, int64_t* n_kept) {
   WLD_CHECK_CTX(c);
-  return filter_common(c, false, min_acgt, min_minor, max_minor, n_kept);
+  return filter_common(c, 0, min_acgt, min_minor, max_minor, 0.0, 0.0, n_kept);
+}
+
+int wld_filter_sites_python(wld_ctx* c, double min_acgt, double min_variability, int64_t* n_kept) {
+  WLD_CHECK_CTX(c);
+  return filter_common(c, 2, 0.f, 0.f, 0.f, min_acgt, min_variability, n_kept);
 }
 
 int wld_keep_all_sites(wld_ctx* c, int64_t* n_kept) {
   WLD_CHECK_CTX(c);
-  return filter_common(c, true, 0.f, 0.f, 0.f, n_kept);
+  return filter_common(c, 1, 0.f, 0.f, 0.f, 0.0, 0.0, n_kept);
 }
 
 int64_t wld_n_seqs(const wld_ctx* c) { return c ? c->n_seqs : -1; }
@@ -301,10 +314,16 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
       WLD_CUDA(c, c->pairs.ensure(sizeof(wld_pair) * (size_t)cap));
       c->pair_cap = cap;
     }
+    if (c->compat == WLD_COMPAT_PYTHON) {
+      int rc = run_pair_python_prepare(c);
+      if (rc != WLD_OK) return rc;
+    }
     for (int attempt = 0; attempt < 3; ++attempt) {
       WLD_CUDA(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 8, c->stream));
       {
         int rc = c->pair_kernel == WLD_PAIR_KERNEL_SIMT ? run_pair_simt(c, r2_threshold) : run_pair_umma(c, r2_threshold);
+        // pairs whose per-pair allele call may differ from the per-site call (WeightedLD.py:186-211)
+        if (rc == WLD_OK && c->compat == WLD_COMPAT_PYTHON) rc = run_pair_python_fixup(c, r2_threshold);
         if (rc != WLD_OK) return rc;
       }
       unsigned long long cnt[4] = {0, 0, 0, 0};

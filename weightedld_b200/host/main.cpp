@@ -1,6 +1,10 @@
 // main.cpp — the `weighted_ld` command-line tool on the B200 library: same long flags, defaults,
 // stage order, stderr log lines and TSV outputs as the reference binary
-// (rust/weighted_ld/src/main.rs:14-213).  Extension: --gpus N (tile-partitioned pair stage).
+// (rust/weighted_ld/src/main.rs:14-213).  Extensions: --gpus N (tile-partitioned pair stage);
+// --vcf-input (the VCF reader of the reference's Python program, WeightedLD.py:311-379; sites are
+// labelled by POS); --python-compat (the whole Python dialect: its FASTA reader, site filter with
+// --min-variability, Henikoff fill, per-pair allele calls, no r2 threshold, `posa posb D D' R2` output
+// rounded to 4 decimals, WeightedLD.py:382-402; VCF input is then not site-filtered, as there).
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -69,9 +73,10 @@ std::string human(double v, const char* units = "") {
 }
 
 struct Opt {  // main.rs:19-68
-  std::string fasta_input, weights_output, pair_output;
+  std::string fasta_input, vcf_input, weights_output, pair_output;
   float min_acgt = 0.8f, min_minor = 0.02f, max_minor = 0.5f, r2_threshold = 0.1f;
-  bool unweighted = false;
+  double min_acgt_f64 = 0.8, min_variability = 0.02;  // --python-compat parses these as Python floats
+  bool unweighted = false, python_compat = false;
   int gpus = 1;
 };
 
@@ -89,7 +94,10 @@ void usage(FILE* f) {
       "        --pair-output <pair-output>          Filename to write the per-pair weighted LD figures to, in Tab Separated Value format\n"
       "        --r2-threshold <r2-threshold>        Minimum value of R2 to be included in the output [default: 0.1]\n"
       "        --weights-output <weights-output>    Filename to write the per-sequence weights to, in Tab Separated Value format\n"
-      "        --gpus <gpus>                        (B200 build) number of GPUs for the pair stage [default: 1]\n",
+      "        --gpus <gpus>                        (B200 build) number of GPUs for the pair stage [default: 1]\n"
+      "        --vcf-input <vcf-input>              (B200 build) phased diploid VCF instead of --fasta-input (WeightedLD.py reader)\n"
+      "        --python-compat                      (B200 build) numeric dialect and output of WeightedLD.py\n"
+      "        --min-variability <v>                (B200 build, --python-compat) minimum non-major fraction [default: 0.02]\n",
       f);
 }
 
@@ -111,11 +119,23 @@ bool parse(int argc, char** argv, Opt& o) {
     const char* a = argv[i];
     if (!std::strcmp(a, "-h") || !std::strcmp(a, "--help")) { usage(stdout); std::exit(0); }
     if (!std::strcmp(a, "-V") || !std::strcmp(a, "--version")) { std::puts("weighted_ld 0.1.0"); std::exit(0); }
+    if (is(a, "--format-py4")) {  // self-test hook (no GPU): prints repr(round(float64(v), 4)) and `{:.3}` of f32(v)
+      const double v = std::strtod(need(i, "--format-py4"), nullptr);
+      std::printf("%s %s\n", format_py4(v).c_str(), format_f3((float)v).c_str());
+      std::exit(0);
+    }
     if (!std::strcmp(a, "--unweighted")) o.unweighted = true;
+    else if (!std::strcmp(a, "--python-compat")) o.python_compat = true;
     else if (is(a, "--fasta-input")) o.fasta_input = need(i, "--fasta-input");
+    else if (is(a, "--vcf-input")) o.vcf_input = need(i, "--vcf-input");
+    else if (is(a, "--min-variability")) o.min_variability = std::strtod(need(i, "--min-variability"), nullptr);
     else if (is(a, "--pair-output")) o.pair_output = need(i, "--pair-output");
     else if (is(a, "--weights-output")) o.weights_output = need(i, "--weights-output");
-    else if (is(a, "--min-acgt")) o.min_acgt = std::strtof(need(i, "--min-acgt"), nullptr);
+    else if (is(a, "--min-acgt")) {
+      const char* v = need(i, "--min-acgt");
+      o.min_acgt = std::strtof(v, nullptr);
+      o.min_acgt_f64 = std::strtod(v, nullptr);
+    }
     else if (is(a, "--min-minor")) o.min_minor = std::strtof(need(i, "--min-minor"), nullptr);
     else if (is(a, "--max-minor")) o.max_minor = std::strtof(need(i, "--max-minor"), nullptr);
     else if (is(a, "--r2-threshold")) o.r2_threshold = std::strtof(need(i, "--r2-threshold"), nullptr);
@@ -125,6 +145,7 @@ bool parse(int argc, char** argv, Opt& o) {
       return false;
     }
   }
+  if (!o.vcf_input.empty() && o.fasta_input.empty()) o.fasta_input = o.vcf_input;  // one of the two is required
   if (o.fasta_input.empty() || o.pair_output.empty()) {
     std::fprintf(stderr, "error: The following required arguments were not provided:\n%s%s\nUSAGE:\n    weighted_ld [FLAGS] [OPTIONS] --fasta-input <fasta-input> --pair-output <pair-output>\n\nFor more information try --help\n",
                  o.fasta_input.empty() ? "    --fasta-input <fasta-input>\n" : "", o.pair_output.empty() ? "    --pair-output <pair-output>\n" : "");
@@ -143,13 +164,19 @@ int main(int argc, char** argv) {
     for (int g = 0; g < std::max(1, opt.gpus); ++g) devices.push_back(g);
 
     auto sw = Clock::now();
-    MultiSequence multiseq = read_fasta(opt.fasta_input);                 // main.rs:129
+    const bool vcf = !opt.vcf_input.empty();
+    MultiSequence multiseq = vcf ? read_vcf(opt.vcf_input)                // WeightedLD.py:311-379
+                                 : opt.python_compat ? read_fasta_python(opt.fasta_input)  // WeightedLD.py:21-41
+                                                     : read_fasta(opt.fasta_input);        // main.rs:129
     SiteSet siteset = SiteSet::from_multiseq(multiseq, devices);          // main.rs:130
-    INFO("Loaded fasta file in " + fmt_duration(Clock::now() - sw));      // main.rs:131
+    INFO(std::string("Loaded ") + (vcf ? "vcf" : "fasta") + " file in " + fmt_duration(Clock::now() - sw));  // main.rs:131
     INFO("    " + std::to_string(siteset.n_seqs()) + " sequences, " + std::to_string(siteset.n_sites()) + " sites");
+    siteset.set_python_compat(opt.python_compat);
 
     sw = Clock::now();
-    SiteSet filtered = siteset.filter_by(opt.min_acgt, opt.min_minor, opt.max_minor);  // main.rs:139-143
+    SiteSet filtered = !opt.python_compat ? siteset.filter_by(opt.min_acgt, opt.min_minor, opt.max_minor)  // main.rs:139-143
+                       : vcf ? siteset.keep_all()                                                          // WeightedLD.py:385-386
+                             : siteset.filter_by_python(opt.min_acgt_f64, opt.min_variability);            // WeightedLD.py:298-304
     INFO("Computed + filtered sites of interest in " + fmt_duration(Clock::now() - sw));
     INFO("    Found " + std::to_string(filtered.n_sites()) + " sites of interest");
 
@@ -170,7 +197,9 @@ int main(int argc, char** argv) {
     sw = Clock::now();
     const int64_t L = filtered.n_sites();
     const uint64_t total_pairs = (uint64_t)((L - 1) * (L - 2) / 2);       // main.rs:168 (sic)
-    PairStore store = all_weighted_ld_pairs(filtered, weights, opt.r2_threshold, [&](size_t computed) {
+    // the Python program prints every computed pair (no threshold, WeightedLD.py:283-284)
+    const float thr = opt.python_compat ? -INFINITY : opt.r2_threshold;
+    PairStore store = all_weighted_ld_pairs(filtered, weights, thr, [&](size_t computed) {
       if (g_level >= 4) DEBUG("progress " + std::to_string(computed) + "/" + std::to_string(total_pairs));
     });
     const auto dur = Clock::now() - sw;
@@ -181,7 +210,8 @@ int main(int argc, char** argv) {
 
     INFO("Writing output to \"" + opt.pair_output + "\"");                // main.rs:207
     sw = Clock::now();
-    write_pair_stats(opt.pair_output, store);                             // main.rs:209
+    if (opt.python_compat) write_pair_stats_python(opt.pair_output, store, multiseq.site_labels);  // WeightedLD.py:176,283
+    else write_pair_stats(opt.pair_output, store, multiseq.site_labels);  // main.rs:209
     INFO("Finshed writing output in " + fmt_duration(Clock::now() - sw)); // main.rs:210 (sic)
     return 0;
   } catch (const Panic& p) {

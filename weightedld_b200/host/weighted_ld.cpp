@@ -7,6 +7,8 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <charconv>
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -92,6 +94,174 @@ MultiSequence read_fasta(const std::string& path) {
   return ms;
 }
 
+namespace {
+struct MappedFile {
+  const char* data = nullptr;
+  size_t size = 0;
+  explicit MappedFile(const std::string& path) {
+    int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) throw std::ios_base::failure(std::string(std::strerror(errno)) + " (os error " + std::to_string(errno) + ")");
+    struct stat st;
+    if (fstat(fd, &st) != 0) { ::close(fd); throw std::ios_base::failure("fstat failed"); }
+    size = (size_t)st.st_size;
+    if (size) {
+      void* p = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+      if (p == MAP_FAILED) { ::close(fd); throw std::ios_base::failure("mmap failed"); }
+      data = (const char*)p;
+    }
+    ::close(fd);
+  }
+  ~MappedFile() { if (data) munmap((void*)data, size); }
+};
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// read_fasta_python, WeightedLD.py:21-41 through Bio.AlignIO.read(.., "fasta"): a record is a '>'
+// line plus every following line, concatenated without line terminators; symbols are lower-cased and
+// a c g t - map to 0..4, everything else to 5.  Returns codes (MultiSequence::codes = true).
+// ---------------------------------------------------------------------------------------------
+MultiSequence read_fasta_python(const std::string& path) {
+  MultiSequence ms;
+  ms.source = path;
+  ms.codes = true;
+  MappedFile f(path);
+  uint8_t lut[256];
+  std::memset(lut, 5, sizeof lut);
+  lut['a'] = lut['A'] = 0; lut['c'] = lut['C'] = 1; lut['g'] = lut['G'] = 2; lut['t'] = lut['T'] = 3; lut['-'] = 4;
+  std::vector<std::vector<uint8_t>> recs;
+  bool in_rec = false;
+  size_t pos = 0;
+  while (pos < f.size) {
+    const char* nl = (const char*)memchr(f.data + pos, '\n', f.size - pos);
+    size_t end = nl ? (size_t)(nl - f.data) : f.size;
+    size_t a = pos, b = end;
+    while (a < b && std::isspace((unsigned char)f.data[a])) ++a;
+    while (b > a && std::isspace((unsigned char)f.data[b - 1])) --b;
+    if (pos < end && f.data[pos] == '>') {
+      recs.emplace_back();
+      ms.names.emplace_back(f.data + pos + 1, end - pos - 1);
+      in_rec = true;
+    } else if (in_rec) {
+      auto& r = recs.back();
+      for (size_t i = a; i < b; ++i) r.push_back(lut[(unsigned char)f.data[i]]);
+    }
+    pos = end + 1;
+  }
+  ms.n_seqs = (int64_t)recs.size();
+  if (recs.empty()) return ms;
+  ms.n_cols = (int64_t)recs[0].size();
+  for (auto& r : recs)
+    if ((int64_t)r.size() != ms.n_cols) ms.ragged = true;
+  if (ms.ragged) return ms;
+  ms.row_stride = (ms.n_cols + 15) / 16 * 16;
+  ms.chars.assign((size_t)ms.row_stride * recs.size(), 5);
+  for (size_t i = 0; i < recs.size(); ++i) std::memcpy(ms.chars.data() + i * (size_t)ms.row_stride, recs[i].data(), recs[i].size());
+  return ms;
+}
+
+// ---------------------------------------------------------------------------------------------
+// read_vcf, WeightedLD.py:311-379.  The reference munges the text with regular expressions; for
+// well-formed phased diploid GT-only input that amounts to: variant lines follow the first line
+// containing "#CHROM"; the LAST line of the file is always dropped (:365 expects a trailing blank
+// line); POS (column 2) labels the site; every sample call `a|b` yields two haplotypes with the allele
+// index as the symbol code, `x/y` (unphased) and `.` become 4 (Missing); np.rot90 (:375) turns the
+// site x haplotype table into haplotype x site with the haplotype order REVERSED.  Variant rows are
+// parsed by all host threads.
+// ---------------------------------------------------------------------------------------------
+MultiSequence read_vcf(const std::string& path) {
+  MultiSequence ms;
+  ms.source = path;
+  ms.codes = true;
+  MappedFile f(path);
+  std::vector<std::pair<size_t, size_t>> lines;  // [begin, end) without the newline
+  bool header_seen = false;
+  size_t pos = 0;
+  while (pos <= f.size) {
+    const char* nl = pos < f.size ? (const char*)memchr(f.data + pos, '\n', f.size - pos) : nullptr;
+    const size_t end = nl ? (size_t)(nl - f.data) : f.size;
+    if (header_seen) {
+      lines.emplace_back(pos, end);
+    } else {
+      static const char key[] = "#CHROM";
+      if (end - pos >= 6 && std::search(f.data + pos, f.data + end, key, key + 6) != f.data + end) header_seen = true;
+    }
+    if (!nl) break;
+    pos = end + 1;
+  }
+  if (!header_seen) throw std::runtime_error("No #CHROM header block identified");            // :327-330
+  auto count_fields = [&](size_t a, size_t b) { return (size_t)std::count(f.data + a, f.data + b, '\t') + 1; };
+  if (lines.empty() || count_fields(lines[0].first, lines[0].second) <= 12)                    // :333-337
+    throw std::runtime_error("The VCF data contains too small a population, are you sure this is a multi VCF?");
+  lines.pop_back();                                                                            // :365
+  const size_t n_sites = lines.size();
+  if (n_sites == 0) return ms;
+  std::vector<std::vector<uint8_t>> site_haps(n_sites);
+  ms.site_labels.assign(n_sites, 0);
+  std::vector<std::string> errs(n_sites);
+  parallel_for(n_sites, 4, [&](size_t lo, size_t hi) {
+    for (size_t k = lo; k < hi; ++k) {
+      const char* p = f.data + lines[k].first;
+      const char* e = f.data + lines[k].second;
+      if (e > p && e[-1] == '\r') --e;
+      int field = 0;
+      const char* q = p;
+      while (q < e && field < 9) {  // skip CHROM..FORMAT, remember POS
+        const char* t = (const char*)memchr(q, '\t', (size_t)(e - q));
+        if (!t) { q = e; break; }
+        if (field == 1) ms.site_labels[k] = std::strtoll(std::string(q, t).c_str(), nullptr, 10);
+        q = t + 1;
+        ++field;
+      }
+      if (field < 9) { errs[k] = "variant row with fewer than 10 columns"; continue; }
+      auto& hap = site_haps[k];
+      while (q <= e) {
+        const char* t = (const char*)memchr(q, '\t', (size_t)(e - q));
+        const char* fe = t ? t : e;
+        // one call: alleles separated by '|'; a three-character `x/y` is unphased -> both missing (:353)
+        if (fe - q == 3 && q[1] == '/') {
+          hap.push_back(4);
+          hap.push_back(4);
+        } else {
+          const char* a = q;
+          while (a <= fe) {
+            const char* bar = (const char*)memchr(a, '|', (size_t)(fe - a));
+            const char* ae = bar ? bar : fe;
+            if (ae - a == 1 && *a == '.') hap.push_back(4);                                    // :356
+            else {
+              int v = 0;
+              bool ok = ae > a;
+              for (const char* c = a; c < ae; ++c) { if (*c < '0' || *c > '9') ok = false; v = v * 10 + (*c - '0'); if (v > 255) ok = false; }
+              if (!ok) { errs[k] = "call '" + std::string(q, fe) + "' is not a phased GT-only genotype"; break; }
+              hap.push_back((uint8_t)v);
+            }
+            if (!bar) break;
+            a = bar + 1;
+          }
+        }
+        if (!t) break;
+        q = t + 1;
+      }
+    }
+  });
+  for (auto& er : errs)
+    if (!er.empty()) throw std::runtime_error("VCF: " + er);
+  const size_t n_haps = site_haps[0].size();
+  for (auto& h : site_haps)
+    if (h.size() != n_haps) throw std::runtime_error("VCF: variant rows with different numbers of calls");
+  ms.n_seqs = (int64_t)n_haps;
+  ms.n_cols = (int64_t)n_sites;
+  ms.row_stride = (ms.n_cols + 15) / 16 * 16;
+  ms.chars.assign((size_t)ms.row_stride * n_haps, 5);
+  parallel_for(n_haps, 1024, [&](size_t lo, size_t hi) {
+    for (size_t h = lo; h < hi; ++h) {  // np.rot90: output row h = input haplotype n_haps-1-h
+      uint8_t* dst = ms.chars.data() + h * (size_t)ms.row_stride;
+      for (size_t k = 0; k < n_sites; ++k) dst[k] = site_haps[k][n_haps - 1 - h];
+    }
+  });
+  ms.names.assign(n_haps, std::string());
+  return ms;
+}
+
 // ---------------------------------------------------------------------------------------------
 struct SiteSet::Impl {
   std::vector<wld_ctx*> ctx;
@@ -124,7 +294,9 @@ SiteSet SiteSet::from_multiseq(const MultiSequence& ms, const std::vector<int>& 
     th.emplace_back([&, g] {
       wld_ctx* c = s.impl->ctx[(size_t)g];
       int rc = wld_set_partition(c, g, n);
-      if (rc == WLD_OK) rc = wld_load_alignment(c, ms.chars.data(), ms.n_seqs, ms.n_cols, ms.row_stride, WLD_INPUT_ASCII);
+      if (rc == WLD_OK)
+        rc = wld_load_alignment(c, ms.chars.data(), ms.n_seqs, ms.n_cols, ms.row_stride,
+                                ms.codes ? WLD_INPUT_CODES : WLD_INPUT_ASCII);
       if (rc != WLD_OK) errs[(size_t)g] = wld_last_error(c);
     });
   for (auto& t : th) t.join();
@@ -142,6 +314,32 @@ SiteSet SiteSet::filter_by(float min_acgt, float min_minor, float max_minor) con
   f.impl = impl;
   f.filtered = true;
   return f;
+}
+
+SiteSet SiteSet::filter_by_python(double min_acgt, double min_variability) const {
+  for (auto* c : impl->ctx) {
+    int64_t kept = 0;
+    check(c, wld_filter_sites_python(c, min_acgt, min_variability, &kept));
+  }
+  SiteSet f;
+  f.impl = impl;
+  f.filtered = true;
+  return f;
+}
+
+SiteSet SiteSet::keep_all() const {
+  for (auto* c : impl->ctx) {
+    int64_t kept = 0;
+    check(c, wld_keep_all_sites(c, &kept));
+  }
+  SiteSet f;
+  f.impl = impl;
+  f.filtered = true;
+  return f;
+}
+
+void SiteSet::set_python_compat(bool on) const {
+  for (auto* c : impl->ctx) check(c, wld_set_compat(c, on ? WLD_COMPAT_PYTHON : WLD_COMPAT_RUST));
 }
 
 int64_t SiteSet::n_sites() const { return filtered ? wld_n_kept(impl->ctx[0]) : wld_n_cols(impl->ctx[0]); }
@@ -259,7 +457,73 @@ void write_henikoff_weights(const std::string& path, const std::vector<float>& w
   std::fclose(f);
 }
 
-void write_pair_stats(const std::string& path, const PairStore& store) {
+// repr(round(numpy.float64(v), 4)): numpy rounds as rint(v*1e4)/1e4; repr prints the shortest digits
+// that round-trip, in fixed notation unless the decimal exponent is < -4 or >= 16.
+std::string format_py4(double v) {
+  if (std::isnan(v)) return "nan";
+  if (std::isinf(v)) return v < 0 ? "-inf" : "inf";
+  const double r = std::nearbyint(v * 1e4) / 1e4;
+  if (r == 0.0) return std::signbit(r) ? "-0.0" : "0.0";
+  char buf[64];
+  auto res = std::to_chars(buf, buf + sizeof buf, std::fabs(r), std::chars_format::scientific);
+  std::string sci(buf, res.ptr);                 // d[.ddd]e[+-]XX
+  const size_t epos = sci.find('e');
+  std::string digits;
+  for (size_t i = 0; i < epos; ++i)
+    if (sci[i] != '.') digits.push_back(sci[i]);
+  const int exp10 = std::atoi(sci.c_str() + epos + 1);
+  const int decpt = exp10 + 1;                   // value = 0.DIGITS x 10^decpt
+  std::string out = r < 0 ? "-" : "";
+  if (decpt <= -4 || decpt > 16) {
+    out += digits.substr(0, 1);
+    if (digits.size() > 1) out += "." + digits.substr(1);
+    char eb[16];
+    std::snprintf(eb, sizeof eb, "e%c%02d", exp10 < 0 ? '-' : '+', std::abs(exp10));
+    out += eb;
+  } else if (decpt <= 0) {
+    out += "0." + std::string((size_t)(-decpt), '0') + digits;
+  } else if ((size_t)decpt >= digits.size()) {
+    out += digits + std::string((size_t)decpt - digits.size(), '0') + ".0";
+  } else {
+    out += digits.substr(0, (size_t)decpt) + "." + digits.substr((size_t)decpt);
+  }
+  return out;
+}
+
+void write_pair_stats_python(const std::string& path, const PairStore& store, const std::vector<int64_t>& labels) {
+  FILE* f = path == "-" ? stdout : std::fopen(path.c_str(), "w");
+  if (!f) throw std::ios_base::failure(std::string(std::strerror(errno)) + " (os error " + std::to_string(errno) + ")");
+  std::fputs("posa\tposb\tD\tD'\tR2\n", f);
+  // WeightedLD.py:177-179 prints in plain row-major order of the upper triangle
+  std::vector<wld_pair> sorted = store.pairs;
+  std::sort(sorted.begin(), sorted.end(), [](const wld_pair& x, const wld_pair& y) {
+    return x.site_a != y.site_a ? x.site_a < y.site_a : x.site_b < y.site_b;
+  });
+  const size_t n = sorted.size(), chunk = 1 << 14;
+  for (size_t base = 0; base < n; base += chunk * 64) {
+    const size_t hi = std::min(n, base + chunk * 64);
+    const size_t nchunks = (hi - base + chunk - 1) / chunk;
+    std::vector<std::string> out(nchunks);
+    parallel_for(nchunks, 1, [&](size_t a, size_t b) {
+      for (size_t ci = a; ci < b; ++ci) {
+        std::string& s = out[ci];
+        const size_t lo = base + ci * chunk, up = std::min(hi, lo + chunk);
+        for (size_t i = lo; i < up; ++i) {
+          const wld_pair& p = sorted[i];
+          const long long la = labels.empty() ? (long long)p.site_a : (long long)labels[p.site_a];
+          const long long lb = labels.empty() ? (long long)p.site_b : (long long)labels[p.site_b];
+          s += std::to_string(la) + "\t" + std::to_string(lb) + "\t" + format_py4((double)p.d) + "\t" +
+               format_py4((double)p.d_prime) + "\t" + format_py4((double)p.r2) + "\n";
+        }
+      }
+    });
+    for (auto& s : out) std::fwrite(s.data(), 1, s.size(), f);
+  }
+  if (f != stdout) std::fclose(f);
+  else std::fflush(f);
+}
+
+void write_pair_stats(const std::string& path, const PairStore& store, const std::vector<int64_t>& labels) {
   FILE* f = std::fopen(path.c_str(), "w");
   if (!f) throw std::ios_base::failure(std::string(std::strerror(errno)) + " (os error " + std::to_string(errno) + ")");
   std::fputs("site_a\tsite_b\td\td'\tr2\n", f);
@@ -277,7 +541,8 @@ void write_pair_stats(const std::string& path, const PairStore& store) {
         s.reserve((up - lo) * 40);
         for (size_t i = lo; i < up; ++i) {
           const wld_pair& p = store.pairs[i];
-          int k = std::sprintf(line, "%u\t%u\t", p.site_a, p.site_b);
+          int k = labels.empty() ? std::sprintf(line, "%u\t%u\t", p.site_a, p.site_b)
+                                 : std::sprintf(line, "%lld\t%lld\t", (long long)labels[p.site_a], (long long)labels[p.site_b]);
           k += fmt_f3(p.d, line + k);
           line[k++] = '\t';
           k += fmt_f3(p.d_prime, line + k);

@@ -5,6 +5,11 @@
 //   SiteSet::filter_by        lib.rs:230-251 + is_site_of_interest lib.rs:310-338 + main.rs:139
 //   henikoff_weights          lib.rs:340-358
 //   all_weighted_ld_pairs     lib.rs:578-684     -> PairStore (lib.rs:529-576), reference order
+// plus the input side and dialect of the reference's Python program (WeightedLD.py), which is the only
+// reference implementation that reads VCF:
+//   read_vcf                  WeightedLD.py:311-379   read_fasta_python   WeightedLD.py:21-41
+//   SiteSet::filter_by_python WeightedLD.py:44-98     set_python_compat   wld_set_compat (include/wld.h)
+//   write_pair_stats_python   WeightedLD.py:176,283-284 (`posa posb D D' R2`, round(x, 4))
 // No CPU fallback: every stage below the text parser is a CUDA kernel in libwld.so.
 #pragma once
 #include <cstdint>
@@ -32,9 +37,16 @@ struct MultiSequence {                 // lib.rs:153-156
   std::vector<uint8_t> chars;          // n_seqs rows, pitch row_stride (16-byte multiple), newline column kept
   std::vector<std::string> names;      // lib.rs:143-146 (empty = None)
   bool ragged = false;                 // rows of unequal length: from_multiseq panics (lib.rs:180-182)
+  bool codes = false;                  // chars already hold 0..5 codes (VCF allele indices, Python FASTA reader)
+  std::vector<int64_t> site_labels;    // VCF: POS of every column (WeightedLD.py:369); empty = column index
 };
 
 MultiSequence read_fasta(const std::string& path);  // throws std::ios_base::failure on I/O errors
+// WeightedLD.py:21-41 (Bio.AlignIO): multi-line records, no newline column, returns 0..5 codes.
+MultiSequence read_fasta_python(const std::string& path);
+// WeightedLD.py:311-379: phased diploid GT-only VCF -> haplotype x site codes (allele index, '.' and
+// unphased calls -> 4), haplotypes in reversed column order, last line dropped, POS as site labels.
+MultiSequence read_vcf(const std::string& path);
 
 struct LdStats { float r2, d, d_prime; };          // lib.rs:382-387
 
@@ -50,6 +62,9 @@ class SiteSet {                                     // lib.rs:158-275
   // One context per GPU; the alignment is replicated to each.
   static SiteSet from_multiseq(const MultiSequence& ms, const std::vector<int>& devices = {0});
   SiteSet filter_by(float min_acgt_frac, float min_minor, float max_minor) const;  // main.rs:139-143
+  SiteSet filter_by_python(double min_acgt, double min_variability) const;         // WeightedLD.py:44-98
+  SiteSet keep_all() const;                        // no site filter (the VCF path of WeightedLD.py:385-386)
+  void set_python_compat(bool on) const;           // wld_set_compat on every context
   int64_t n_sites() const;                          // lib.rs:254
   int64_t n_seqs() const;                           // lib.rs:259
   int64_t parent_site_index(int64_t idx) const;     // lib.rs:263
@@ -71,7 +86,11 @@ PairStore all_weighted_ld_pairs(const SiteSet& site_set, const std::vector<float
 
 // main.rs:70-119
 void write_henikoff_weights(const std::string& path, const std::vector<float>& weights);
-void write_pair_stats(const std::string& path, const PairStore& pairs);
+// labels (optional): VCF POS printed instead of the column index
+void write_pair_stats(const std::string& path, const PairStore& pairs, const std::vector<int64_t>& labels = {});
 std::string format_f3(float v);  // Rust `{:.3}`
+// WeightedLD.py:176,283-284; labels[i] replaces site index i when non-empty (VCF POS)
+void write_pair_stats_python(const std::string& path, const PairStore& pairs, const std::vector<int64_t>& labels);
+std::string format_py4(double v);  // repr(round(numpy.float64(v), 4))
 
 }  // namespace weighted_ld

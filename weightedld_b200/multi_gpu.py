@@ -1,0 +1,63 @@
+"""One-process-per-GPU plumbing around the C ABI: `torch.distributed` is used for
+device memory, the NVLink all-gather of the input and the host gather of the outputs — never for the
+pair stage itself, which needs no collective (independent tiles, lib.rs:593-594).
+
+    broadcast once   the alignment is sequence-major, so rank r copies only rows [r*R, (r+1)*R) over its
+                     own PCIe link and one all-gather over NVLink/NVSwitch rebuilds the full matrix on
+                     every GPU: host->device traffic per rank drops from N*L to N*L/world bytes.
+    compute          every rank runs stages 1-2 on the full matrix (< 3 % of a step) and its own part of
+                     the upper-triangular tile grid (wld_set_partition).
+    merge            per-rank survivor shards are gathered on rank 0 and merged into the reference's
+                     output order (api.merge_shards).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_rows(n_seqs: int, rank: int, world: int) -> tuple[int, int, int]:
+    """(first row, one-past-last row, padded rows per rank) of this rank's slice of the alignment."""
+    per = -(-n_seqs // world)
+    lo = min(rank * per, n_seqs)
+    return lo, min(lo + per, n_seqs), per
+
+
+class ShardedLoader:
+    """Reusable buffers for the sharded host->device copy + all-gather of one alignment shape."""
+
+    def __init__(self, n_seqs: int, n_cols: int, rank: int, world: int, device, group=None):
+        import torch
+
+        self.n_seqs, self.n_cols, self.rank, self.world, self.group = n_seqs, n_cols, rank, world, group
+        self.lo, self.hi, self.per = shard_rows(n_seqs, rank, world)
+        self.pitch = -(-max(n_cols, 1) // 16) * 16  # 16-byte pitch: vectorised histogram path
+        self.full = torch.empty((self.per * world, self.pitch), dtype=torch.uint8, device=device)
+        self.h2d_bytes = (self.hi - self.lo) * n_cols
+
+    def load(self, host_rows):
+        """host_rows: (n_seqs, n_cols) uint8 torch tensor in (ideally pinned) host memory, identical on
+        every rank — or just this rank's rows [lo, hi).  Returns the full (n_seqs, n_cols) device view."""
+        import torch
+        import torch.distributed as dist
+
+        src = host_rows if host_rows.shape[0] == self.hi - self.lo else host_rows[self.lo:self.hi]
+        mine = self.full[self.rank * self.per: self.rank * self.per + (self.hi - self.lo), : self.n_cols]
+        mine.copy_(src, non_blocking=True)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.full, self.full[self.rank * self.per: (self.rank + 1) * self.per],
+                                        group=self.group)
+        return self.full[: self.n_seqs, : self.n_cols]
+
+
+def gather_pairs(shard: np.ndarray, n_kept: int, site_map: np.ndarray | None, rank: int, world: int, group=None):
+    """Gathers KEPT-index survivor shards on rank 0 and merges them into the reference's output order;
+    returns the merged array on rank 0 and None elsewhere."""
+    import torch.distributed as dist
+
+    from .api import merge_shards
+
+    if world == 1:
+        return merge_shards(n_kept, [shard], site_map)
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(shard, parts, dst=0, group=group)
+    return merge_shards(n_kept, parts, site_map) if rank == 0 else None
