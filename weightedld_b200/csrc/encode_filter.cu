@@ -274,10 +274,11 @@ __global__ void site_map_kernel(const uint8_t* __restrict__ keep, const int32_t*
 // ---------------------------------------------------------------------------------------------
 // Kernel 1d: encode + transpose + gather of the kept columns.
 // Tile = 128 sequences x 128 raw columns.  Global reads are 4-byte words arranged so that a warp
-// request covers four 32-byte sectors (8 lanes x 4 columns, 4 row groups); a 4x4 byte block is
+// request covers four 32-byte sectors (8 lanes x 4 columns, 4 row groups); a 4x4 block of RAW bytes is
 // transposed in registers with PRMT and stored conflict-free into a [128 cols][33 words] tile;
-// kept columns are then written as 128-byte rows of the site-major code matrix.  Rows beyond
-// n_seqs are padded with 5 (Unknown) so the pair operands see zeros there.
+// only the kept columns are then encoded (SWAR, 4 sequences per word — the ALU cost scales with the
+// keep ratio, 1/3 at config 4) and written as 128-byte rows of the site-major code matrix.  Rows
+// beyond n_seqs are padded with 0xff, which encodes to 5 (Unknown), so the pair operands see zeros there.
 // ---------------------------------------------------------------------------------------------
 constexpr int kGatherThreads = 256;
 
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(kGatherThreads) gather_kernel(const uint8_t* _
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr) {
       const int64_t seq = seq_tile + s_local + rr;
-      uint32_t w = 0x05050505u;  // pad rows: Unknown
+      uint32_t w = 0xffffffffu;  // pad rows: a byte that encodes to 5 (Unknown) in both input modes
       if (seq < n_seqs) {
         const uint8_t* p = raw + seq * row_stride + col;
         uint32_t x;
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(kGatherThreads) gather_kernel(const uint8_t* _
           for (int b = 0; b < 4; ++b)
             if (col + b < n_cols) x |= (uint32_t)p[b] << (8 * b);
         }
-        w = kAscii ? encode4_ascii(x) : encode4_codes(x);
+        w = x;
       }
       r[rr] = w;
     }
@@ -336,7 +337,8 @@ __global__ void __launch_bounds__(kGatherThreads) gather_kernel(const uint8_t* _
     const int64_t c = col_tile + cl;
     if (c < n_cols && keep[c]) {
       const int64_t k = rank[c];
-      *reinterpret_cast<uint32_t*>(codes + k * ldc + seq_tile + 4 * lane) = tile[cl][lane];
+      const uint32_t x = tile[cl][lane];
+      *reinterpret_cast<uint32_t*>(codes + k * ldc + seq_tile + 4 * lane) = kAscii ? encode4_ascii(x) : encode4_codes(x);
     }
   }
 }

@@ -108,55 +108,85 @@ __device__ __forceinline__ uint32_t elem_of(uint32_t v) {
   return kI8 ? v : (uint32_t)bf16_bits_of_small_int(v);
 }
 
-// 8 codes -> 8 operand elements: vals[k] where code == sym, else 0.  Stored as 16 B (bf16) or 8 B (u8).
+// One thread expands kSeq consecutive sequences of one site into 16-byte stores: 8 bf16 or 16 u8
+// elements per operand row.  c[] holds the codes as packed words (4 per word).
+template <bool kI8> struct Expand {
+  static constexpr int kSeq = kI8 ? 16 : 8;       // sequences per thread
+  static constexpr int kWords = kSeq / 4;         // 32-bit words of codes
+};
+
+// kSeq codes -> kSeq operand elements: vals[k] where code == sym, else 0; one 16-byte store.
 template <bool kI8>
-__device__ __forceinline__ void store_select8(void* dst, uint2 codes, int sym, const uint32_t* vals) {
-  uint32_t e[8];
+__device__ __forceinline__ void store_select(void* dst, const uint32_t* cw, int sym, const uint32_t* vals) {
+  constexpr int kSeq = Expand<kI8>::kSeq;
+  uint32_t e[kSeq];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const uint32_t word = k < 4 ? codes.x : codes.y;
-    const int c = (int)((word >> (8 * (k & 3))) & 0xffu);
+  for (int k = 0; k < kSeq; ++k) {
+    const int c = (int)((cw[k >> 2] >> (8 * (k & 3))) & 0xffu);
     e[k] = c == sym ? vals[k] : 0u;
   }
   if (kI8) {
-    *reinterpret_cast<uint2*>(dst) = make_uint2(e[0] | (e[1] << 8) | (e[2] << 16) | (e[3] << 24),
-                                                e[4] | (e[5] << 8) | (e[6] << 16) | (e[7] << 24));
+    *reinterpret_cast<uint4*>(dst) =
+        make_uint4(e[0] | (e[1] << 8) | (e[2] << 16) | (e[3] << 24), e[4] | (e[5] << 8) | (e[6] << 16) | (e[7] << 24),
+                   e[8 % kSeq] | (e[9 % kSeq] << 8) | (e[10 % kSeq] << 16) | (e[11 % kSeq] << 24),
+                   e[12 % kSeq] | (e[13 % kSeq] << 8) | (e[14 % kSeq] << 16) | (e[15 % kSeq] << 24));
   } else {
     *reinterpret_cast<uint4*>(dst) =
         make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
   }
 }
+// Indicator rows: the element is the constant 1, so whole words can be built with SWAR compares.
 template <bool kI8>
-__device__ __forceinline__ void store_zero8(void* dst) {
-  if (kI8) *reinterpret_cast<uint2*>(dst) = make_uint2(0, 0);
-  else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+__device__ __forceinline__ void store_indicator(void* dst, const uint32_t* cw, int sym) {
+  if (kI8) {
+    const uint32_t rep = sym < 0 ? 0xffffffffu : (uint32_t)sym * 0x01010101u;  // 0xff never matches a code
+    *reinterpret_cast<uint4*>(dst) =
+        make_uint4(__vcmpeq4(cw[0], rep) & 0x01010101u, __vcmpeq4(cw[1], rep) & 0x01010101u,
+                   __vcmpeq4(cw[2], rep) & 0x01010101u, __vcmpeq4(cw[3], rep) & 0x01010101u);
+  } else {
+    uint32_t ones[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ones[k] = elem_of<false>(1u);
+    store_select<false>(dst, cw, sym, ones);
+  }
+}
+__device__ __forceinline__ void store_zero16(void* dst) { *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0); }
+
+template <bool kI8>
+__device__ __forceinline__ void load_codes(const uint8_t* p, uint32_t* cw) {
+  if (kI8) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    cw[0] = v.x; cw[1] = v.y; cw[2] = v.z; cw[3] = v.w;
+  } else {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    cw[0] = v.x; cw[1] = v.y;
+  }
 }
 
-// opA: grid (K blocks of 2048, a_rows/2 sites).  Sites >= n_kept are zero rows.
+// opA: grid (K blocks of 256*kSeq, a_rows/2 sites).  Sites >= n_kept are zero rows.
 template <bool kI8>
 __global__ void __launch_bounds__(256) expand_a_kernel(const uint8_t* __restrict__ codes, int64_t ldc, int64_t n_kept,
                                                        const int8_t* __restrict__ maj, const int8_t* __restrict__ mnr,
                                                        int64_t kp, uint8_t* __restrict__ opA) {
   constexpr int ES = kI8 ? 1 : 2;
+  constexpr int kSeq = Expand<kI8>::kSeq;
   const int64_t i = blockIdx.y;
-  const int64_t s0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8;
+  const int64_t s0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * kSeq;
   if (s0 >= kp) return;
   uint8_t* r0 = opA + ((2 * i) * kp + s0) * ES;
   uint8_t* r1 = opA + ((2 * i + 1) * kp + s0) * ES;
   if (i < n_kept) {
-    const uint2 cw = __ldg(reinterpret_cast<const uint2*>(codes + i * ldc + s0));
-    uint32_t ones[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) ones[k] = elem_of<kI8>(1u);
-    store_select8<kI8>(r0, cw, maj[i], ones);  // maj/min == -1 never matches a code
-    store_select8<kI8>(r1, cw, mnr[i], ones);
+    uint32_t cw[Expand<kI8>::kWords];
+    load_codes<kI8>(codes + i * ldc + s0, cw);
+    store_indicator<kI8>(r0, cw, maj[i]);  // maj/min == -1 never matches a code
+    store_indicator<kI8>(r1, cw, mnr[i]);
   } else {
-    store_zero8<kI8>(r0);
-    store_zero8<kI8>(r1);
+    store_zero16(r0);
+    store_zero16(r1);
   }
 }
 
-// opB: grid (K blocks of 2048, groups*(SPG+1)).  blockIdx.y = g*(SPG+1) + r; r == SPG zero-fills the
+// opB: grid (K blocks of 256*kSeq, groups*(SPG+1)).  blockIdx.y = g*(SPG+1) + r; r == SPG zero-fills the
 // unused tail rows of the group.
 template <bool kI8>
 __global__ void __launch_bounds__(256) expand_b_kernel(const uint8_t* __restrict__ codes, int64_t ldc, int64_t n_kept,
@@ -164,31 +194,39 @@ __global__ void __launch_bounds__(256) expand_b_kernel(const uint8_t* __restrict
                                                        const uint16_t* __restrict__ limbs, int n_limbs, int spg,
                                                        int64_t kp, uint8_t* __restrict__ opB) {
   constexpr int ES = kI8 ? 1 : 2;
+  constexpr int kSeq = Expand<kI8>::kSeq;
   const int64_t g = blockIdx.y / (spg + 1);
   const int r = (int)(blockIdx.y % (spg + 1));
   const int rps = 2 * n_limbs;
-  const int64_t s0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8;
+  const int64_t s0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * kSeq;
   if (s0 >= kp) return;
   if (r == spg) {
-    for (int row = spg * rps; row < 128; ++row) store_zero8<kI8>(opB + ((g * 128 + row) * kp + s0) * ES);
+    for (int row = spg * rps; row < 128; ++row) store_zero16(opB + ((g * 128 + row) * kp + s0) * ES);
     return;
   }
   const int64_t j = g * spg + r;
   const int64_t row0 = g * 128 + (int64_t)r * rps;
   if (j >= n_kept) {
-    for (int t = 0; t < rps; ++t) store_zero8<kI8>(opB + ((row0 + t) * kp + s0) * ES);
+    for (int t = 0; t < rps; ++t) store_zero16(opB + ((row0 + t) * kp + s0) * ES);
     return;
   }
-  const uint2 cw = __ldg(reinterpret_cast<const uint2*>(codes + j * ldc + s0));
+  uint32_t cw[Expand<kI8>::kWords];
+  load_codes<kI8>(codes + j * ldc + s0, cw);
   const int sm = maj[j], sn = mnr[j];
   for (int l = 0; l < n_limbs; ++l) {
-    const uint4 lv = __ldg(reinterpret_cast<const uint4*>(limbs + (int64_t)l * ldc + s0));
-    uint32_t vals[8] = {lv.x & 0xffffu, lv.x >> 16, lv.y & 0xffffu, lv.y >> 16,
-                        lv.z & 0xffffu, lv.z >> 16, lv.w & 0xffffu, lv.w >> 16};
+    uint32_t vals[kSeq];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) vals[k] = elem_of<kI8>(vals[k]);
-    store_select8<kI8>(opB + ((row0 + l) * kp + s0) * ES, cw, sm, vals);
-    store_select8<kI8>(opB + ((row0 + n_limbs + l) * kp + s0) * ES, cw, sn, vals);
+    for (int h = 0; h < kSeq / 8; ++h) {
+      const uint4 lv = __ldg(reinterpret_cast<const uint4*>(limbs + (int64_t)l * ldc + s0 + 8 * h));
+      const uint32_t w[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        vals[8 * h + 2 * k] = elem_of<kI8>(w[k] & 0xffffu);
+        vals[8 * h + 2 * k + 1] = elem_of<kI8>(w[k] >> 16);
+      }
+    }
+    store_select<kI8>(opB + ((row0 + l) * kp + s0) * ES, cw, sm, vals);
+    store_select<kI8>(opB + ((row0 + n_limbs + l) * kp + s0) * ES, cw, sn, vals);
   }
 }
 
@@ -250,7 +288,7 @@ int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm) {
   const size_t es = (size_t)gm.elem_bytes;
   WLD_CUDA(c, c->opA.ensure(es * (size_t)gm.a_rows * (size_t)kp));
   WLD_CUDA(c, c->opB.ensure(es * (size_t)gm.b_groups * 128 * (size_t)kp));
-  const unsigned kblocks = (unsigned)((kp / 8 + 255) / 256);
+  const unsigned kblocks = (unsigned)((kp / (i8 ? 16 : 8) + 255) / 256);  // a thread expands 16 u8 / 8 bf16 elements
   {
     dim3 grid(kblocks, (unsigned)(gm.a_rows / 2));
     if (grid.y > 65535 * 32) return c->fail(WLD_ERR_UNSUPPORTED, "too many kept sites");
