@@ -312,7 +312,10 @@ def run_ours(args):
             "achieved_useful": useful_flop / (pair_ms * 1e-3) / 1e12,
             "executed": info.executed_flop / (pair_ms * 1e-3) / 1e12,
             "algorithmic_flop_per_pair": 8 * n_seqs * info.n_limbs, "n_limbs": info.n_limbs, "limb_bits": info.limb_bits,
-            "kernel_ms": pair_ms, "traffic": None}
+            "kernel_ms": pair_ms, "traffic": None,
+            "tile_schedule": {0: "round-robin", 1: "per-L2-die contiguous halves of the strip-rasterised tile list",
+                              2: "per-L2-die, dealt per round"}.get(info.die_schedule, "?"),
+            "die_sms": list(info.die_sms)}
     prof = ROOT / "profiles" / "pair_umma_traffic.json"
     if prof.exists():
         try:

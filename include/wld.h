@@ -219,6 +219,9 @@ typedef struct wld_pair_info {
   int64_t tile_sites_m;    /* kept sites per tile along a */
   int64_t tile_sites_n;    /* kept sites per tile along b */
   double executed_flop;    /* 2*M*N*K summed over MMA instructions issued */
+  int32_t die_schedule;    /* 0: plain round-robin tile schedule; 1/2: die-aware (SM -> L2 die map measured) */
+  int32_t die_sms[2];      /* SMs found on each L2 die (0, 0 when the map could not be established) */
+  int32_t reserved;
 } wld_pair_info;
 WLD_API int wld_get_pair_info(wld_ctx* ctx, wld_pair_info* out);
 

@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--strips", default="8,16,24")
     ap.add_argument("--hints", default="nn,fn,nl,fl")
+    ap.add_argument("--krots", default="0")
+    ap.add_argument("--dies", default="1")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
 
@@ -40,8 +42,11 @@ def main():
     dev = torch.from_numpy(chars).cuda()
     names = {"n": "normal", "f": "first", "l": "last"}
     rows = []
-    for strip, hint in itertools.product([int(x) for x in args.strips.split(",")], args.hints.split(",")):
+    for strip, hint, krot, die in itertools.product([int(x) for x in args.strips.split(",")], args.hints.split(","),
+                                                    args.krots.split(","), args.dies.split(",")):
+        os.environ["WLD_DIE"] = die
         os.environ["WLD_STRIP"] = str(strip)
+        os.environ["WLD_KROT"] = krot
         os.environ["WLD_HINT_A"] = names[hint[0]]
         os.environ["WLD_HINT_B"] = names[hint[1]]
         with wld.Context(0) as ctx:
@@ -55,8 +60,9 @@ def main():
                     n, done = ctx.ld_pairs(bench.R2_THRESHOLD)
                     if it >= args.warmup:
                         ms.append(ctx.stage_ms(wld.STAGE_PAIR))
-            row = {"strip": strip, "hint_a": names[hint[0]], "hint_b": names[hint[1]], "pair_ms": float(np.mean(ms)),
-                   "pair_ms_min": float(np.min(ms)), "survivors": n, "pairs": done, "clocks": clk.summary()}
+            row = {"die": int(die), "krot": int(krot), "strip": strip, "hint_a": names[hint[0]], "hint_b": names[hint[1]], "pair_ms": float(np.mean(ms)),
+                   "pair_ms_min": float(np.min(ms)), "survivors": n, "pairs": done, "die_schedule": ctx.pair_info().die_schedule,
+                   "die_sms": list(ctx.pair_info().die_sms), "clocks": clk.summary()}
         rows.append(row)
         print(json.dumps(row), flush=True)
     if args.out:

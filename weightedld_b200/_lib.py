@@ -32,7 +32,7 @@ class PairInfo(C.Structure):
     _fields_ = [
         ("kernel", C.c_int32), ("n_limbs", C.c_int32), ("limb_bits", C.c_int32), ("weight_bits", C.c_int32),
         ("k_padded", C.c_int64), ("tiles", C.c_int64), ("tile_sites_m", C.c_int64), ("tile_sites_n", C.c_int64),
-        ("executed_flop", C.c_double),
+        ("executed_flop", C.c_double), ("die_schedule", C.c_int32), ("die_sms", C.c_int32 * 2), ("reserved", C.c_int32),
     ]
 
 

@@ -79,6 +79,9 @@ struct wld_ctx {
   uint64_t pair_cap_opt = 0;
   int compat = WLD_COMPAT_RUST;    // numeric dialect (wld_set_compat)
   int cta_group = 2;               // CTAs cooperating on one MMA tile (tcgen05 cta_group::1 / ::2)
+  int die_aware = 1;               // give each L2 die its own part of the tile list (needs die_map); cleared on mismatch
+  wld::DevBuf die_of_sm;           // u8 [sm_count]
+  int die_used = 0;                // the last pair launch ran the die-aware schedule
 
   // stage 1
   int64_t n_seqs = 0, n_cols = 0, row_stride = 0;
@@ -183,6 +186,7 @@ int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm);                       // pa
 int run_pair_simt(wld_ctx* c, float thr);                                  // pair_simt.cu
 int run_pair_umma(wld_ctx* c, float thr);                                  // pair_umma.cu
 int run_pair_order(wld_ctx* c, bool ordered, bool parent);                 // pair_order.cu
+const std::vector<uint8_t>& die_map(wld_ctx* c);                            // die_map.cu: SM -> L2 die (empty = unknown)
 int run_pair_python_prepare(wld_ctx* c);                                   // pair_python.cu
 int run_pair_python_fixup(wld_ctx* c, float thr);                          // pair_python.cu
 

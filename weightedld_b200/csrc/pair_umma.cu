@@ -73,6 +73,15 @@ struct UmmaParams {
   float thr_lo_f;     // fp32 pre-filter threshold (lowered, see ld_prefilter_f32)
   int thr_negative;   // threshold below zero: every pair with non-empty marginals is a candidate
   int sum_shift;      // fp32 pre-filter works on sums scaled by 2^-sum_shift so that T <= 2^21
+  // die-aware schedule (die_of_sm == nullptr: plain round-robin over the whole list).  Tiles [0, die_split) belong
+  // to the CTA pairs on die 0, [die_split, n_tiles) to those on die 1; a pair finds its die from %smid and
+  // its rank among the die's pairs from die_counter.
+  const uint8_t* die_of_sm;
+  unsigned int* die_counter;  // [2], zeroed before the launch
+  int die_pairs[2];
+  int die_split;
+  int die_mode;               // 1: front/back split of the list; 2: every round of n0+n1 tiles is dealt die 0 first
+  int k_rot;                // K-loop rotation stride: tile t starts at K block (t * k_rot) % k_blocks (0 = off)
   uint64_t hint_a, hint_b;  // L2 eviction policy of the indicator (streamed) and limb (strip-resident) panels
   const uint2* py_aux; // WLD_COMPAT_PYTHON only (else null): per-site {n5, margin}, see py_flagged
   PairOut out;
@@ -389,7 +398,33 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = kCtas == 2 ? cluster_ctarank() : 0u;  // rank 0 = leader: issues the MMAs
-  const int first_tile = (int)(blockIdx.x / kCtas), tile_step = (int)(gridDim.x / kCtas);
+  int first_tile = (int)(blockIdx.x / kCtas), tile_step = (int)(gridDim.x / kCtas), tile_end = p.n_tiles;
+  int* sched = reinterpret_cast<int*>(smem + kStages * Cfg::kBytes + 8 * (2 * kStages + 4) + 8);  // [3], leader CTA
+  static_assert(8 * (2 * kStages + 4) + 8 + 12 <= 256, "barrier block overflows its 256 bytes");
+  if (p.die_of_sm != nullptr && cta_rank == 0 && threadIdx.x == 96) {  // warp 3 is otherwise idle
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const int d = p.die_of_sm[smid] ? 1 : 0;
+    const int k = (int)atomicAdd(&p.die_counter[d], 1u);
+    int lo, hi, step;
+    if (p.die_mode == 2) {
+      lo = d ? p.die_pairs[0] : 0;
+      hi = p.n_tiles;
+      step = p.die_pairs[0] + p.die_pairs[1];
+    } else {
+      lo = d ? p.die_split : 0;
+      hi = d ? p.n_tiles : p.die_split;
+      step = p.die_pairs[d];
+    }
+    if (k >= p.die_pairs[d]) {  // more pairs on this die than the host planned for: report, compute nothing
+      atomicExch(p.error_flag, 7);
+      sched[0] = hi;
+    } else {
+      sched[0] = lo + k;
+    }
+    sched[1] = step;
+    sched[2] = hi;
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -415,17 +450,33 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.die_of_sm != nullptr) {
+    if (kCtas == 2 && cta_rank != 0) {  // the peer follows its leader: read the leader's schedule over DSMEM
+      uint32_t remote;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(smem_u32(sched)));
+      asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(first_tile) : "r"(remote));
+      asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(tile_step) : "r"(remote + 4));
+      asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(tile_end) : "r"(remote + 8));
+    } else {
+      first_tile = sched[0];
+      tile_step = sched[1];
+      tile_end = sched[2];
+    }
+  }
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs of a pair) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = first_tile; t < p.n_tiles; t += tile_step) {
+      for (int t = first_tile; t < tile_end; t += tile_step) {
         const uint2 tile = p.tiles[t];
         const int m_row = (int)tile.x * (kBlockM * kCtas) + (int)cta_rank * kBlockM;
         const int n_row = (int)tile.y * kBlockN + (int)cta_rank * Cfg::kBRows;
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
+        // Tiles that share a panel run concurrently; starting each at a different K block keeps them from
+        // requesting the same lines in the same instant (one fetches, the others hit in L2).
+        int kb = p.k_rot ? (int)(((long long)t * p.k_rot) % p.k_blocks) : 0;
+        for (int it = 0; it < p.k_blocks; ++it, kb = (kb + 1 == p.k_blocks) ? 0 : kb + 1) {
           mbar_wait(empty_bar(stage), phase ^ 1u, p.error_flag, 1);
           if constexpr (kCtas == 2) {
             if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::kBytes);
@@ -447,7 +498,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
       int stage = 0;
       uint32_t phase = 0;
       uint32_t tcount = 0;
-      for (int t = first_tile; t < p.n_tiles; t += tile_step, ++tcount) {
+      for (int t = first_tile; t < tile_end; t += tile_step, ++tcount) {
         const uint32_t buf = tcount & 1u, bphase = (tcount >> 1) & 1u;
         mbar_wait(tempty_bar(buf), bphase ^ 1u, p.error_flag, 2);  // epilogues drained this accumulator
         tc_fence_after();
@@ -486,7 +537,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
     queue.init(smem + Cfg::kQueueOffset + (warp - kEpiWarp0) * kQueueBytesPerWarp);
     unsigned long long done = 0;
     uint32_t tcount = 0;
-    for (int t = first_tile; t < p.n_tiles; t += tile_step, ++tcount) {
+    for (int t = first_tile; t < tile_end; t += tile_step, ++tcount) {
       const uint2 tile = p.tiles[t];
       const uint32_t buf = tcount & 1u, bphase = (tcount >> 1) & 1u;
       const int i_min = ((int)tile.x * kCtas + (int)cta_rank) * (kBlockM / 2) + quarter * 16;
@@ -740,6 +791,8 @@ int run_pair_umma(wld_ctx* c, float thr) {
       if (!e) return dflt;
       return e[0] == 'f' ? kL2EvictFirst : e[0] == 'l' ? kL2EvictLast : kL2EvictNormal;
     };
+    prm.k_rot = 0;
+    if (const char* e = std::getenv("WLD_KROT")) prm.k_rot = std::max(0, std::atoi(e));
     prm.hint_a = policy("WLD_HINT_A", kL2EvictNormal);
     prm.hint_b = policy("WLD_HINT_B", kL2EvictNormal);
   }
@@ -759,7 +812,42 @@ int run_pair_umma(wld_ctx* c, float thr) {
   prm.pairs_done = c->counters.as<unsigned long long>() + 1;
   prm.error_flag = reinterpret_cast<int*>(c->counters.as<unsigned long long>() + 2);
 
-  const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)(c->sm_count / ctas)) * ctas;
+  int grid = (int)std::min<int64_t>(n_tiles, (int64_t)(c->sm_count / ctas)) * ctas;
+  // Die-aware schedule: each L2 die works on its own contiguous part of the (strip-rasterised) tile list, so
+  // the panels a die's L2 holds are only the ones its own SMs reuse.  WLD_DIE=0 disables (experiments).
+  prm.die_of_sm = nullptr;
+  prm.die_counter = reinterpret_cast<unsigned int*>(c->counters.as<unsigned long long>() + 3);
+  prm.die_pairs[0] = prm.die_pairs[1] = 0;
+  prm.die_split = 0;
+  prm.die_mode = 1;
+  c->die_used = 0;
+  {
+    const char* e = std::getenv("WLD_DIE");
+    if (c->die_aware && !(e && e[0] == '0') && n_tiles >= 4 * (int64_t)(c->sm_count / ctas)) {
+      const std::vector<uint8_t>& dm = die_map(c);
+      if ((int)dm.size() == c->sm_count) {
+        int sms[2] = {0, 0};
+        for (uint8_t d : dm) ++sms[d ? 1 : 0];
+        const int n0 = sms[0] / ctas, n1 = sms[1] / ctas;
+        if (n0 > 0 && n1 > 0) {
+          if (c->die_of_sm.bytes < dm.size() || !c->die_of_sm.p) {
+            WLD_CUDA(c, c->die_of_sm.ensure(dm.size()));
+            WLD_CUDA(c, cudaMemcpyAsync(c->die_of_sm.p, dm.data(), dm.size(), cudaMemcpyHostToDevice, c->stream));
+            WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+          }
+          prm.die_of_sm = c->die_of_sm.as<uint8_t>();
+          prm.die_pairs[0] = n0;
+          prm.die_pairs[1] = n1;
+          prm.die_split = (int)((n_tiles * n0 + (n0 + n1) / 2) / (n0 + n1));
+          prm.die_mode = (e && e[0] == '2') ? 2 : 1;
+          grid = (n0 + n1) * ctas;
+          c->die_used = prm.die_mode;
+          c->info.die_sms[0] = sms[0];
+          c->info.die_sms[1] = sms[1];
+        }
+      }
+    }
+  }
   const bool i8 = gm.elem_bytes == 1;
   if (gm.n_limbs < 1 || gm.n_limbs > 4) return c->fail(WLD_ERR_INVALID, "n_limbs must be 1..4");
   ScopedStageTimer tm(c, WLD_STAGE_PAIR);  // kernel only

@@ -56,7 +56,7 @@ void wld_destroy(wld_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->raw_own, &c->hist, &c->keep, &c->rank, &c->maj_raw, &c->min_raw, &c->site_map, &c->maj,
                     &c->mnr, &c->kept_count, &c->codes, &c->table, &c->partial, &c->w64, &c->w32, &c->scalars,
-                    &c->q, &c->limbs, &c->opA, &c->opB, &c->tiles, &c->pairs, &c->counters, &c->py_aux,
+                    &c->q, &c->limbs, &c->opA, &c->opB, &c->tiles, &c->pairs, &c->counters, &c->py_aux, &c->die_of_sm,
                     &c->sorted, &c->sort_keys, &c->sort_idx, &c->sort_temp};
   for (DevBuf* b : bufs) b->release();
   for (auto& t : c->timers) {
@@ -320,6 +320,7 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
     }
     for (int attempt = 0; attempt < 3; ++attempt) {
       WLD_CUDA(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 8, c->stream));
+      c->die_used = 0;
       {
         int rc = c->pair_kernel == WLD_PAIR_KERNEL_SIMT ? run_pair_simt(c, r2_threshold) : run_pair_umma(c, r2_threshold);
         // pairs whose per-pair allele call may differ from the per-site call (WeightedLD.py:186-211)
@@ -332,6 +333,12 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
       if (e != cudaSuccess)
         return c->fail(WLD_ERR_CUDA, "pair kernel failed: %s (pipeline watchdog code %d)", cudaGetErrorString(e),
                        (int)cnt[2]);
+      if (c->die_used && ((int)cnt[2] == 7 || cnt[1] != c->plan_pairs)) {
+        // the CTA pairs did not land on the dies as planned (GPU shared with other work?): plain schedule
+        c->die_aware = 0;
+        --attempt;
+        continue;
+      }
       c->pairs_computed = cnt[1];
       if (cnt[0] <= c->pair_cap) {
         c->n_survivors = cnt[0];
@@ -344,6 +351,7 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
       if (attempt == 2) return c->fail(WLD_ERR_NOMEM, "survivor buffer kept overflowing");
     }
     c->info.kernel = c->pair_kernel;
+    c->info.die_schedule = c->die_used;
     c->info.n_limbs = c->geom.n_limbs;
     c->info.limb_bits = c->geom.limb_bits;
     c->info.weight_bits = c->geom.n_limbs * c->geom.limb_bits;
