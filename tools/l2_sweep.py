@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--hints", default="nn,fn,nl,fl")
     ap.add_argument("--krots", default="0")
     ap.add_argument("--dies", default="1")
+    ap.add_argument("--promos", default="3")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
 
@@ -42,9 +43,11 @@ def main():
     dev = torch.from_numpy(chars).cuda()
     names = {"n": "normal", "f": "first", "l": "last"}
     rows = []
-    for strip, hint, krot, die in itertools.product([int(x) for x in args.strips.split(",")], args.hints.split(","),
-                                                    args.krots.split(","), args.dies.split(",")):
+    for strip, hint, krot, die, promo in itertools.product([int(x) for x in args.strips.split(",")], args.hints.split(","),
+                                                           args.krots.split(","), args.dies.split(","),
+                                                           args.promos.split(",")):
         os.environ["WLD_DIE"] = die
+        os.environ["WLD_L2PROMO"] = promo
         os.environ["WLD_STRIP"] = str(strip)
         os.environ["WLD_KROT"] = krot
         os.environ["WLD_HINT_A"] = names[hint[0]]
@@ -60,7 +63,7 @@ def main():
                     n, done = ctx.ld_pairs(bench.R2_THRESHOLD)
                     if it >= args.warmup:
                         ms.append(ctx.stage_ms(wld.STAGE_PAIR))
-            row = {"die": int(die), "krot": int(krot), "strip": strip, "hint_a": names[hint[0]], "hint_b": names[hint[1]], "pair_ms": float(np.mean(ms)),
+            row = {"promo": int(promo), "die": int(die), "krot": int(krot), "strip": strip, "hint_a": names[hint[0]], "hint_b": names[hint[1]], "pair_ms": float(np.mean(ms)),
                    "pair_ms_min": float(np.min(ms)), "survivors": n, "pairs": done, "die_schedule": ctx.pair_info().die_schedule,
                    "die_sms": list(ctx.pair_info().die_sms), "clocks": clk.summary()}
         rows.append(row)

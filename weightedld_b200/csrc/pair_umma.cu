@@ -661,9 +661,13 @@ bool make_tensor_map(CUtensorMap* map, void* base, uint64_t rows, uint64_t kp, u
   const cuuint64_t gstride[1] = {kp * (uint64_t)elem_bytes};
   const cuuint32_t box[2] = {(cuuint32_t)(kBlockKBytes / elem_bytes), box_rows};
   const cuuint32_t estr[2] = {1, 1};
+  CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  if (const char* e = std::getenv("WLD_L2PROMO"))  // experiments: 0 none, 1 64 B, 2 128 B, 3 256 B
+    promo = e[0] == '0' ? CU_TENSOR_MAP_L2_PROMOTION_NONE : e[0] == '1' ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+          : e[0] == '2' ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   return fn(map, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim,
             gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_SWIZZLE_128B, promo,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
