@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <future>
 #include <iostream>
 #include <string>
 
@@ -164,11 +165,13 @@ int main(int argc, char** argv) {
     for (int g = 0; g < std::max(1, opt.gpus); ++g) devices.push_back(g);
 
     auto sw = Clock::now();
+    // CUDA initialisation takes seconds and is independent of the input: do it while the file is read
+    auto opened = std::async(std::launch::async, [&] { return SiteSet::open_devices(devices); });
     const bool vcf = !opt.vcf_input.empty();
     MultiSequence multiseq = vcf ? read_vcf(opt.vcf_input)                // WeightedLD.py:311-379
                                  : opt.python_compat ? read_fasta_python(opt.fasta_input)  // WeightedLD.py:21-41
                                                      : read_fasta(opt.fasta_input);        // main.rs:129
-    SiteSet siteset = SiteSet::from_multiseq(multiseq, devices);          // main.rs:130
+    SiteSet siteset = SiteSet::from_multiseq(multiseq, opened.get());     // main.rs:130
     INFO(std::string("Loaded ") + (vcf ? "vcf" : "fasta") + " file in " + fmt_duration(Clock::now() - sw));  // main.rs:131
     INFO("    " + std::to_string(siteset.n_seqs()) + " sequences, " + std::to_string(siteset.n_sites()) + " sites");
     siteset.set_python_compat(opt.python_compat);

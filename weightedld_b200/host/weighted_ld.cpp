@@ -272,11 +272,8 @@ struct SiteSet::Impl {
 SiteSet::~SiteSet() = default;
 SiteSet::SiteSet(SiteSet&&) noexcept = default;
 
-SiteSet SiteSet::from_multiseq(const MultiSequence& ms, const std::vector<int>& devices) {
-  if (ms.n_seqs == 0) throw Panic("index out of bounds: the len is 0 but the index is 0");  // lib.rs:178
-  if (ms.ragged) throw Panic("Not all sequences have the same number of symbols");        // lib.rs:181
-  SiteSet s;
-  s.impl = std::make_shared<Impl>();
+std::shared_ptr<SiteSet::Impl> SiteSet::open_devices(const std::vector<int>& devices) {
+  auto impl = std::make_shared<Impl>();
   for (int dev : devices) {
     wld_ctx* c = nullptr;
     int rc = wld_create(dev, &c);
@@ -285,8 +282,22 @@ SiteSet SiteSet::from_multiseq(const MultiSequence& ms, const std::vector<int>& 
       if (c) wld_destroy(c);
       throw WldError(rc, msg);
     }
-    s.impl->ctx.push_back(c);
+    impl->ctx.push_back(c);
   }
+  return impl;
+}
+
+SiteSet SiteSet::from_multiseq(const MultiSequence& ms, const std::vector<int>& devices) {
+  if (ms.n_seqs == 0) throw Panic("index out of bounds: the len is 0 but the index is 0");  // lib.rs:178
+  if (ms.ragged) throw Panic("Not all sequences have the same number of symbols");        // lib.rs:181
+  return from_multiseq(ms, open_devices(devices));
+}
+
+SiteSet SiteSet::from_multiseq(const MultiSequence& ms, std::shared_ptr<Impl> opened) {
+  if (ms.n_seqs == 0) throw Panic("index out of bounds: the len is 0 but the index is 0");  // lib.rs:178
+  if (ms.ragged) throw Panic("Not all sequences have the same number of symbols");        // lib.rs:181
+  SiteSet s;
+  s.impl = std::move(opened);
   const int n = (int)s.impl->ctx.size();
   std::vector<std::thread> th;
   std::vector<std::string> errs((size_t)n);
@@ -382,7 +393,7 @@ PairStore all_weighted_ld_pairs(const SiteSet& site_set, const std::vector<float
     for (auto d : u->sh->done) total += d;
     if (total > 0 && *u->sh->cb) (*u->sh->cb)((size_t)total);
   };
-  std::vector<std::vector<wld_pair>> parts((size_t)n);
+  std::vector<PairVec> parts((size_t)n);
   std::vector<uint64_t> computed((size_t)n, 0);
   std::vector<std::string> errs((size_t)n);
   std::vector<User> users;
@@ -434,10 +445,36 @@ PairStore all_weighted_ld_pairs(const SiteSet& site_set, const std::vector<float
 // Writers, main.rs:70-119.  Rust `{:.3}`: exact value rounded half-to-even (glibc %.3f agrees for
 // finite values), `NaN`, `inf`, `-inf`, negative zero keeps its sign.
 // ---------------------------------------------------------------------------------------------
+static inline int fmt_u64(unsigned long long v, char* buf) {
+  char tmp[24];
+  int n = 0;
+  do {
+    tmp[n++] = (char)('0' + v % 10);
+    v /= 10;
+  } while (v);
+  for (int i = 0; i < n; ++i) buf[i] = tmp[n - 1 - i];
+  return n;
+}
+// `{:.3}` of an f32.  x*1000 is exact in f64 (24-bit significand times a 10-bit integer), so rounding it
+// to the nearest integer, ties to even, IS round-half-even of the exact binary value — what Rust's
+// float formatting (and glibc's %.3f) produce.  Values too large for the integer path go through printf.
 static int fmt_f3(float v, char* buf) {
   if (std::isnan(v)) return std::sprintf(buf, "NaN");
   if (std::isinf(v)) return std::sprintf(buf, v < 0 ? "-inf" : "inf");
-  return std::sprintf(buf, "%.3f", (double)v);
+  const double x = (double)v;
+  if (std::fabs(x) >= 1e15) return std::sprintf(buf, "%.3f", x);
+  const double r = std::nearbyint(std::fabs(x) * 1000.0);
+  const unsigned long long m = (unsigned long long)r;
+  int k = 0;
+  if (std::signbit(v)) buf[k++] = '-';
+  k += fmt_u64(m / 1000, buf + k);
+  const unsigned f = (unsigned)(m % 1000);
+  buf[k++] = '.';
+  buf[k++] = (char)('0' + f / 100);
+  buf[k++] = (char)('0' + f / 10 % 10);
+  buf[k++] = (char)('0' + f % 10);
+  buf[k] = 0;
+  return k;
 }
 std::string format_f3(float v) {
   char b[64];
@@ -495,7 +532,7 @@ void write_pair_stats_python(const std::string& path, const PairStore& store, co
   if (!f) throw std::ios_base::failure(std::string(std::strerror(errno)) + " (os error " + std::to_string(errno) + ")");
   std::fputs("posa\tposb\tD\tD'\tR2\n", f);
   // WeightedLD.py:177-179 prints in plain row-major order of the upper triangle
-  std::vector<wld_pair> sorted = store.pairs;
+  PairVec sorted = store.pairs;
   std::sort(sorted.begin(), sorted.end(), [](const wld_pair& x, const wld_pair& y) {
     return x.site_a != y.site_a ? x.site_a < y.site_a : x.site_b < y.site_b;
   });
@@ -541,8 +578,15 @@ void write_pair_stats(const std::string& path, const PairStore& store, const std
         s.reserve((up - lo) * 40);
         for (size_t i = lo; i < up; ++i) {
           const wld_pair& p = store.pairs[i];
-          int k = labels.empty() ? std::sprintf(line, "%u\t%u\t", p.site_a, p.site_b)
-                                 : std::sprintf(line, "%lld\t%lld\t", (long long)labels[p.site_a], (long long)labels[p.site_b]);
+          int k = 0;
+          if (labels.empty()) {
+            k += fmt_u64(p.site_a, line + k);
+            line[k++] = '\t';
+            k += fmt_u64(p.site_b, line + k);
+            line[k++] = '\t';
+          } else {
+            k = std::sprintf(line, "%lld\t%lld\t", (long long)labels[p.site_a], (long long)labels[p.site_b]);
+          }
           k += fmt_f3(p.d, line + k);
           line[k++] = '\t';
           k += fmt_f3(p.d_prime, line + k);

@@ -15,6 +15,9 @@
 #include <cstdint>
 #include <functional>
 #include <memory>
+#include <new>
+#include <type_traits>
+#include <utility>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -50,9 +53,20 @@ MultiSequence read_vcf(const std::string& path);
 
 struct LdStats { float r2, d, d_prime; };          // lib.rs:382-387
 
+// std::allocator that leaves trivially constructible elements uninitialised on resize(): the survivor
+// buffer (up to tens of GB) is filled by the device-to-host copy, zeroing it first would be a wasted pass
+template <class T>
+struct default_init_allocator : std::allocator<T> {
+  template <class U> struct rebind { using other = default_init_allocator<U>; };
+  using std::allocator<T>::allocator;
+  template <class U> void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value) { ::new (static_cast<void*>(p)) U; }
+  template <class U, class... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+};
+using PairVec = std::vector<wld_pair, default_init_allocator<wld_pair>>;
+
 class PairStore {                                   // lib.rs:529-576
  public:
-  std::vector<wld_pair> pairs;                      // reference order, parent indices
+  PairVec pairs;                                    // reference order, parent indices
   uint64_t pairs_computed = 0;
   size_t len() const { return pairs.size(); }
 };
@@ -60,7 +74,12 @@ class PairStore {                                   // lib.rs:529-576
 class SiteSet {                                     // lib.rs:158-275
  public:
   // One context per GPU; the alignment is replicated to each.
+  struct Impl;
+  // Creates the library contexts (CUDA initialisation takes seconds): callable from a background thread
+  // while the input file is being read; pass the result to from_multiseq.
+  static std::shared_ptr<Impl> open_devices(const std::vector<int>& devices = {0});
   static SiteSet from_multiseq(const MultiSequence& ms, const std::vector<int>& devices = {0});
+  static SiteSet from_multiseq(const MultiSequence& ms, std::shared_ptr<Impl> opened);
   SiteSet filter_by(float min_acgt_frac, float min_minor, float max_minor) const;  // main.rs:139-143
   SiteSet filter_by_python(double min_acgt, double min_variability) const;         // WeightedLD.py:44-98
   SiteSet keep_all() const;                        // no site filter (the VCF path of WeightedLD.py:385-386)
@@ -73,7 +92,6 @@ class SiteSet {                                     // lib.rs:158-275
   SiteSet(SiteSet&&) noexcept;
   SiteSet(const SiteSet&) = delete;
 
-  struct Impl;
   std::shared_ptr<Impl> impl;                       // shared with the filtered view (same contexts)
   bool filtered = false;
  private:
