@@ -48,7 +48,7 @@ def main():
     for r in range(args.repeat):
         t0 = time.perf_counter()
         p = subprocess.run([str(ROOT / "weightedld_b200" / "weighted_ld"), "--fasta-input", str(fasta), "--pair-output",
-                            str(d / "pairs.tsv"), "--weights-output", str(d / "w.tsv"), "--gpus", str(args.gpus)],
+                            str(d / "pairs.tsv"), "--weights-output", str(d / "w.tsv"), "--gpus", str(args.gpus)], env=dict(os.environ, RUST_LOG="debug"),
                            capture_output=True, text=True)
         wall = time.perf_counter() - t0
         lines = [ln.split("] ", 1)[-1] for ln in p.stderr.splitlines()]

@@ -141,9 +141,14 @@ int wld_load_alignment(wld_ctx* c, const uint8_t* data, int64_t n_seqs, int64_t 
       const size_t bytes = (size_t)pitch * (size_t)std::max<int64_t>(n_seqs, 1);
       WLD_CUDA(c, c->raw_own.ensure(bytes));
       if (pitch != n_cols) WLD_CUDA(c, cudaMemsetAsync(c->raw_own.p, 0, bytes, c->stream));
-      if (n_seqs > 0 && n_cols > 0)
-        WLD_CUDA(c, cudaMemcpy2DAsync(c->raw_own.p, (size_t)pitch, data, (size_t)row_stride, (size_t)n_cols,
-                                      (size_t)n_seqs, cudaMemcpyHostToDevice, c->stream));
+      if (n_seqs > 0 && n_cols > 0) {
+        if (row_stride == pitch)  // same pitch on both sides: one linear copy (a pageable 2-D copy goes row by row)
+          WLD_CUDA(c, cudaMemcpyAsync(c->raw_own.p, data, (size_t)(n_seqs - 1) * (size_t)pitch + (size_t)n_cols,
+                                      cudaMemcpyHostToDevice, c->stream));
+        else
+          WLD_CUDA(c, cudaMemcpy2DAsync(c->raw_own.p, (size_t)pitch, data, (size_t)row_stride, (size_t)n_cols,
+                                        (size_t)n_seqs, cudaMemcpyHostToDevice, c->stream));
+      }
       c->d_raw = c->raw_own.as<uint8_t>();
       c->row_stride = pitch;
     }

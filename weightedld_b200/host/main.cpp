@@ -171,7 +171,10 @@ int main(int argc, char** argv) {
     MultiSequence multiseq = vcf ? read_vcf(opt.vcf_input)                // WeightedLD.py:311-379
                                  : opt.python_compat ? read_fasta_python(opt.fasta_input)  // WeightedLD.py:21-41
                                                      : read_fasta(opt.fasta_input);        // main.rs:129
-    SiteSet siteset = SiteSet::from_multiseq(multiseq, opened.get());     // main.rs:130
+    DEBUG("parsed input in " + fmt_duration(Clock::now() - sw));
+    auto impl = opened.get();
+    DEBUG("devices ready after " + fmt_duration(Clock::now() - sw));
+    SiteSet siteset = SiteSet::from_multiseq(multiseq, impl);             // main.rs:130
     INFO(std::string("Loaded ") + (vcf ? "vcf" : "fasta") + " file in " + fmt_duration(Clock::now() - sw));  // main.rs:131
     INFO("    " + std::to_string(siteset.n_seqs()) + " sequences, " + std::to_string(siteset.n_sites()) + " sites");
     siteset.set_python_compat(opt.python_compat);

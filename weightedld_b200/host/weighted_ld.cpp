@@ -274,16 +274,31 @@ SiteSet::SiteSet(SiteSet&&) noexcept = default;
 
 std::shared_ptr<SiteSet::Impl> SiteSet::open_devices(const std::vector<int>& devices) {
   auto impl = std::make_shared<Impl>();
-  for (int dev : devices) {
-    wld_ctx* c = nullptr;
-    int rc = wld_create(dev, &c);
-    if (rc != WLD_OK) {
-      std::string msg = c ? wld_last_error(c) : "allocation failed";
-      if (c) wld_destroy(c);
-      throw WldError(rc, msg);
+  impl->ctx.assign(devices.size(), nullptr);
+  std::vector<int> rcs(devices.size(), WLD_OK);
+  std::vector<std::string> msgs(devices.size());
+  std::vector<std::thread> th;  // one context per GPU, created concurrently
+  for (size_t g = 0; g < devices.size(); ++g)
+    th.emplace_back([&, g] {
+      wld_ctx* c = nullptr;
+      rcs[g] = wld_create(devices[g], &c);
+      if (rcs[g] != WLD_OK) {
+        msgs[g] = c ? wld_last_error(c) : "allocation failed";
+        if (c) wld_destroy(c);
+        c = nullptr;
+      }
+      impl->ctx[g] = c;
+    });
+  for (auto& t : th) t.join();
+  for (size_t g = 0; g < devices.size(); ++g)
+    if (rcs[g] != WLD_OK) {
+      for (auto*& c : impl->ctx) {
+        if (c) wld_destroy(c);
+        c = nullptr;
+      }
+      impl->ctx.clear();
+      throw WldError(rcs[g], msgs[g]);
     }
-    impl->ctx.push_back(c);
-  }
   return impl;
 }
 
