@@ -48,8 +48,11 @@ def test_plan_is_balanced_at_config5():
             plans = [wld.plan_tiles(48601, 3, p, nparts, cta_group=ctas) for p in range(nparts)]
             pairs = [p[1] for p in plans]
             tiles = [len(p[0]) for p in plans]
-            assert max(pairs) / min(pairs) < 1.01                 # site pairs
-            assert max(tiles) - min(tiles) <= 2 * (148 // ctas)   # MMA work: at most one block of tiles apart
+            assert max(tiles) - min(tiles) <= 1                   # MMA work: contiguous ranges of equal tile count
+            assert max(pairs) / min(pairs) < 1.02                 # site pairs (diagonal tiles hold fewer)
+            ranges = [(int(tl[:, 1].min()), int(tl[:, 1].max())) for tl, _ in plans]
+            for (lo0, hi0), (lo1, hi1) in zip(ranges, ranges[1:]):  # contiguous runs: neighbours share at most one strip
+                assert lo0 <= lo1 and hi0 <= hi1 and lo1 >= hi0 - 7
 
 
 def _worker(rank, world, port, n_kept, q):

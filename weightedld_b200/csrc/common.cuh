@@ -127,6 +127,7 @@ struct wld_ctx {
   int64_t plan_key[5] = {-1, -1, -1, -1, -1};
   int64_t plan_tiles_n = 0;
   uint64_t plan_pairs = 0;
+  int64_t plan_x[2] = {0, -1}, plan_y[2] = {0, -1};  // min / max M-tile and N-tile index of this partition's tiles
   double weight_sum = 0.0;         // sum of the fixed-point weights q (upper bound of every pair's T)
 
   wld::StageTimer timers[WLD_STAGE_COUNT];
@@ -185,6 +186,7 @@ int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm);                       // pa
 // planning and the tile-list upload happen before the start event).
 int run_pair_simt(wld_ctx* c, float thr);                                  // pair_simt.cu
 int run_pair_umma(wld_ctx* c, float thr);                                  // pair_umma.cu
+int ensure_tile_plan(wld_ctx* c);                                          // pair_umma.cu (needs c->geom.n_limbs)
 int run_pair_order(wld_ctx* c, bool ordered, bool parent);                 // pair_order.cu
 const std::vector<uint8_t>& die_map(wld_ctx* c);                            // die_map.cu: SM -> L2 die (empty = unknown)
 int run_pair_python_prepare(wld_ctx* c);                                   // pair_python.cu

@@ -289,12 +289,26 @@ int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm) {
   WLD_CUDA(c, c->opA.ensure(es * (size_t)gm.a_rows * (size_t)kp));
   WLD_CUDA(c, c->opB.ensure(es * (size_t)gm.b_groups * 128 * (size_t)kp));
   const unsigned kblocks = (unsigned)((kp / (i8 ? 16 : 8) + 255) / 256);  // a thread expands 16 u8 / 8 bf16 elements
+  // Only the operand rows this partition's tiles read are expanded (multi-GPU: a contiguous range of the tile
+  // list touches a slice of the limb operand and, in the early strips, a prefix of the indicator operand).
+  int64_t site_lo = 0, site_hi = gm.a_rows / 2;     // sites whose indicator rows are needed
+  int64_t grp_lo = 0, grp_hi = gm.b_groups;         // 128-row groups of the limb operand that are needed
+  if (c->pair_kernel != WLD_PAIR_KERNEL_SIMT) {
+    const int rc = ensure_tile_plan(c);
+    if (rc != WLD_OK) return rc;
+    if (c->plan_tiles_n == 0) return WLD_OK;
+    const int64_t tile_m = 64 * c->cta_group;
+    site_lo = c->plan_x[0] * tile_m;
+    site_hi = std::min<int64_t>(site_hi, (c->plan_x[1] + 1) * tile_m);
+    grp_lo = c->plan_y[0] * 2;
+    grp_hi = std::min<int64_t>(grp_hi, (c->plan_y[1] + 1) * 2);
+  } else {
+    return WLD_OK;  // the CUDA-core verification kernel reads the code matrix and q directly
+  }
   {
-    dim3 grid(kblocks, (unsigned)(gm.a_rows / 2));
-    if (grid.y > 65535 * 32) return c->fail(WLD_ERR_UNSUPPORTED, "too many kept sites");
     // grid.y limit is 65535: fold larger site counts into several launches
-    for (int64_t y0 = 0; y0 < gm.a_rows / 2; y0 += 65535) {
-      const unsigned ny = (unsigned)std::min<int64_t>(65535, gm.a_rows / 2 - y0);
+    for (int64_t y0 = site_lo; y0 < site_hi; y0 += 65535) {
+      const unsigned ny = (unsigned)std::min<int64_t>(65535, site_hi - y0);
       auto kern = i8 ? expand_a_kernel<true> : expand_a_kernel<false>;
       kern<<<dim3(kblocks, ny), 256, 0, c->stream>>>(
           c->codes.as<uint8_t>() + y0 * c->ldc, c->ldc, std::max<int64_t>(L - y0, 0), c->maj.as<int8_t>() + y0,
@@ -305,8 +319,8 @@ int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm) {
   {
     const int spg = gm.sites_per_group;
     const int64_t groups_per_launch = 65535 / (spg + 1);
-    for (int64_t g0 = 0; g0 < gm.b_groups; g0 += groups_per_launch) {
-      const int64_t ng = std::min<int64_t>(groups_per_launch, gm.b_groups - g0);
+    for (int64_t g0 = grp_lo; g0 < grp_hi; g0 += groups_per_launch) {
+      const int64_t ng = std::min<int64_t>(groups_per_launch, grp_hi - g0);
       auto kern = i8 ? expand_b_kernel<true> : expand_b_kernel<false>;
       kern<<<dim3(kblocks, (unsigned)(ng * (spg + 1))), 256, 0, c->stream>>>(
           c->codes.as<uint8_t>() + g0 * spg * c->ldc, c->ldc, std::max<int64_t>(L - g0 * spg, 0),

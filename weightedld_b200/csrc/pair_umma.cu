@@ -27,6 +27,7 @@
 //
 // Roofline: tensor pipe.  Algorithmic flop per site pair per launch = 8*N*NL (4 weighted dot
 // products of length N per limb); executed = 2*128*256*Kp per tile.
+#include <climits>
 #include <cmath>
 #include <cstdlib>
 
@@ -711,10 +712,9 @@ cudaError_t launch_any(int n_limbs, bool i8, int grid, cudaStream_t stream, cons
 
 }  // namespace
 
-// Upper-triangular tile list, rasterised in strips of 8 N tiles so that the ~148 tiles in flight
-// share operand panels through L2 (about 18 A panels x 8 B panels); for multi-GPU runs blocks of
-// 2*SM consecutive tiles are dealt round-robin (load-balanced, no collective; replaces rayon's
-// fan-out over triu_index, lib.rs:623-637).
+// Upper-triangular tile list, rasterised in strips of 8 N tiles so that the tiles in flight share
+// operand panels through L2; for multi-GPU runs every partition takes one contiguous range of that
+// list (load-balanced, no collective; replaces rayon's fan-out over triu_index, lib.rs:623-637).
 TilePlan plan_tiles(int64_t L, int n_limbs, int part, int nparts, int sm_count, int ctas) {
   TilePlan plan;
   plan.tile_m = (kBlockM / 2) * ctas;
@@ -736,11 +736,13 @@ TilePlan plan_tiles(int64_t L, int n_limbs, int part, int nparts, int sm_count, 
   if (nparts <= 1) {
     plan.tiles.swap(all);
   } else {
-    const size_t blk = (size_t)std::max(sm_count / ctas, 1) * 2;  // two waves of tiles per block
-    for (size_t b0 = 0, bi = 0; b0 < all.size(); b0 += blk, ++bi)
-      if ((int)(bi % (size_t)nparts) == part)
-        plan.tiles.insert(plan.tiles.end(), all.begin() + b0, all.begin() + std::min(all.size(), b0 + blk));
+    // Contiguous ranges of the rasterised list: equal tile counts (= equal tensor work; every strip holds its own
+    // share of the diagonal, so the epilogue work is balanced too), each partition keeps whole strips together
+    // (its limb panels stay in L2 across waves) and touches only its own slice of the operands.
+    const size_t lo = all.size() * (size_t)part / (size_t)nparts, hi = all.size() * (size_t)(part + 1) / (size_t)nparts;
+    plan.tiles.assign(all.begin() + lo, all.begin() + hi);
   }
+  (void)sm_count;
   for (const uint2& t : plan.tiles) {  // pairs a < b inside the tile
     const int64_t i0 = (int64_t)t.x * tile_m, i1 = std::min(L, i0 + tile_m);
     const int64_t j0 = (int64_t)t.y * tile_n, j1 = std::min(L, j0 + tile_n);
@@ -749,22 +751,42 @@ TilePlan plan_tiles(int64_t L, int n_limbs, int part, int nparts, int sm_count, 
   return plan;
 }
 
+// The schedule only depends on (n_kept, n_limbs, partition, cta_group): it is planned once, kept on the
+// device between calls, and its extent (which M / N tiles this partition touches) tells pair_prep which
+// operand rows to expand.
+int ensure_tile_plan(wld_ctx* c) {
+  const PairGeom& gm = c->geom;
+  const int64_t L = c->n_kept;
+  const int ctas = c->cta_group;
+  const int64_t key[5] = {L, gm.n_limbs, c->part, c->nparts, ctas};
+  if (std::memcmp(key, c->plan_key, sizeof key) == 0) return WLD_OK;
+  TilePlan plan = plan_tiles(L, gm.n_limbs, c->part, c->nparts, c->sm_count, ctas);
+  WLD_CUDA(c, c->tiles.ensure(sizeof(uint2) * std::max<size_t>(plan.tiles.size(), 1)));
+  if (!plan.tiles.empty())
+    WLD_CUDA(c, cudaMemcpyAsync(c->tiles.p, plan.tiles.data(), sizeof(uint2) * plan.tiles.size(),
+                                cudaMemcpyHostToDevice, c->stream));
+  WLD_CUDA(c, cudaStreamSynchronize(c->stream));  // the host vector dies at the end of this function
+  std::memcpy(c->plan_key, key, sizeof key);
+  c->plan_tiles_n = (int64_t)plan.tiles.size();
+  c->plan_pairs = plan.pairs;
+  c->plan_x[0] = c->plan_y[0] = INT64_MAX;
+  c->plan_x[1] = c->plan_y[1] = -1;
+  for (const uint2& t : plan.tiles) {
+    c->plan_x[0] = std::min<int64_t>(c->plan_x[0], t.x);
+    c->plan_x[1] = std::max<int64_t>(c->plan_x[1], t.x);
+    c->plan_y[0] = std::min<int64_t>(c->plan_y[0], t.y);
+    c->plan_y[1] = std::max<int64_t>(c->plan_y[1], t.y);
+  }
+  return WLD_OK;
+}
+
 int run_pair_umma(wld_ctx* c, float thr) {
   const PairGeom& gm = c->geom;
   const int64_t L = c->n_kept;
-  // The schedule only depends on (n_kept, n_limbs, partition): keep it on the device between calls.
   const int ctas = c->cta_group;
-  const int64_t key[5] = {L, gm.n_limbs, c->part, c->nparts, ctas};
-  if (std::memcmp(key, c->plan_key, sizeof key) != 0) {
-    TilePlan plan = plan_tiles(L, gm.n_limbs, c->part, c->nparts, c->sm_count, ctas);
-    WLD_CUDA(c, c->tiles.ensure(sizeof(uint2) * std::max<size_t>(plan.tiles.size(), 1)));
-    if (!plan.tiles.empty())
-      WLD_CUDA(c, cudaMemcpyAsync(c->tiles.p, plan.tiles.data(), sizeof(uint2) * plan.tiles.size(),
-                                  cudaMemcpyHostToDevice, c->stream));
-    WLD_CUDA(c, cudaStreamSynchronize(c->stream));  // the host vector dies at the end of this block
-    std::memcpy(c->plan_key, key, sizeof key);
-    c->plan_tiles_n = (int64_t)plan.tiles.size();
-    c->plan_pairs = plan.pairs;
+  {
+    const int rc = ensure_tile_plan(c);
+    if (rc != WLD_OK) return rc;
   }
   const int64_t n_tiles = c->plan_tiles_n;
   c->info.tiles = n_tiles;
