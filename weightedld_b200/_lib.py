@@ -9,7 +9,9 @@ from pathlib import Path
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libwld.so"
+import os as _os
+
+LIB_PATH = Path(_os.environ.get("WLD_LIBRARY", _HERE / "libwld.so"))  # WLD_LIBRARY: A/B builds of the same ABI
 
 PAIR_DTYPE = np.dtype(
     [("site_a", "<u4"), ("site_b", "<u4"), ("d", "<f4"), ("d_prime", "<f4"), ("r2", "<f4")]

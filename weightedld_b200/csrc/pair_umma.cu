@@ -527,8 +527,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
     __syncwarp();
   } else if (warp >= kEpiWarp0) {
     // ===================== epilogue =====================
-    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
-    const int half = (warp - kEpiWarp0) >> 2; // which 128-column group of the accumulator
+    const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
+    constexpr int kParts = kNumEpiWarps / 8;        // epilogue warps per (lane quarter, column group)
+    const int half = (warp - kEpiWarp0) / (4 * kParts);       // which 128-column group of the accumulator
+    const int part = ((warp - kEpiWarp0) >> 2) % kParts;      // which share of the group's site-pair steps
+    constexpr int kSteps = (SPG + 1) / 2;           // two sites j per step
+    const int jp_begin = (kSteps * part + kParts - 1) / kParts, jp_end = (kSteps * (part + 1) + kParts - 1) / kParts;
     const int alpha = lane & 1;
     float scale_f[NL];  // limb weights 2^(b*(NL-1-l)), pre-scaled by 2^-sum_shift, for the fp32 pre-filter
 #pragma unroll
@@ -548,10 +552,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * kBlockN + half * 128;
       // whole tile below the diagonal band for this warp?  (i >= every j) -> nothing to do
-      const bool any_work = i_min < min(site_j0 + SPG, p.n_kept) && site_j0 < p.n_kept;
+      const bool any_work = i_min < min(site_j0 + min(2 * jp_end, SPG), p.n_kept) && site_j0 + 2 * jp_begin < p.n_kept;
       if (any_work) {
 #pragma unroll 1
-        for (int jp = 0; jp < (SPG + 1) / 2; ++jp) {
+        for (int jp = jp_begin; jp < jp_end; ++jp) {
           uint32_t v[2 * RPS];
           const bool has2 = (2 * jp + 1) < SPG;
           if (has2) {
@@ -609,7 +613,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
             const long long own1 = alpha ? S[1][1] : S[0][1];
             queue.push(keep, alpha ? recv0 : own0, alpha ? recv1 : own1, alpha ? own0 : recv0, alpha ? own1 : recv1,
                        (uint32_t)site_i, (uint32_t)site_j);
-            if (queue.count >= 32) queue.drain32(p.thr, p.out, p.py_aux);  // f64 statistics, lib.rs:482-518, 32 at a time
+            if (queue.count > kQueueCap - 32) queue.drain32(p.thr, p.out, p.py_aux);  // f64 statistics, lib.rs:482-518
           }
         }
       }
