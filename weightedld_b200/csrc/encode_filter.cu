@@ -42,12 +42,24 @@ __device__ __forceinline__ uint32_t encode1(uint32_t c, bool ascii) {
 // ---------------------------------------------------------------------------------------------
 // Kernel 1a: per-column histogram, vectorised path (base and pitch 16-byte aligned).
 // A warp owns 512 consecutive columns (16 per lane, one 16-byte load per row); the 8 warps of a
-// block take interleaved rows of the block's row chunk.  Counts live in byte lanes of 32-bit
-// registers (5 symbols x 4 words) and are flushed to a block-shared histogram before any byte
-// lane can exceed 255; one global atomicAdd per (symbol, column) per block follows.
+// block take interleaved rows of the block's row chunk.  Classification is ONE shared-memory lookup per
+// byte: a 256-entry table maps the byte to 1 << (6 * code) (0 for Unknown), so adding the looked-up words
+// accumulates all five counts of a column at once in 6-bit fields of one register — about 4 instructions
+// per byte instead of ~10 for five SWAR compares, which had this kernel ALU-bound at a quarter of HBM
+// bandwidth.  Fields are flushed into the block's shared histogram (bank-conflict-free layout) before
+// any can exceed 63; one global atomicAdd per (symbol, column) per block follows.
+// DNA bytes fall into different banks of the table (A C G T - N: 1 3 7 20 13 14), so the lookups are
+// conflict-free on real data; adversarial bytes only cost replays.
 // ---------------------------------------------------------------------------------------------
 constexpr int kHistThreads = 256;
 constexpr int kHistColsPerBlock = 512;
+constexpr int kHistFlushRows = 63;   // 6-bit count fields
+constexpr int kHistUnroll = 4;       // rows in flight per warp
+
+__device__ __forceinline__ uint32_t hist_lut_entry(uint32_t byte, bool ascii) {
+  const uint32_t code = encode1(byte, ascii);
+  return code < 5u ? (1u << (6u * code)) : 0u;
+}
 
 template <bool kAscii>
 __global__ void __launch_bounds__(kHistThreads) hist_vec16_kernel(const uint8_t* __restrict__ raw,
@@ -55,8 +67,10 @@ __global__ void __launch_bounds__(kHistThreads) hist_vec16_kernel(const uint8_t*
                                                                   int64_t row_stride, int rows_per_block,
                                                                   uint32_t* __restrict__ hist,
                                                                   int64_t cols_padded) {
-  __shared__ uint32_t s_hist[5][kHistColsPerBlock];
+  __shared__ uint32_t s_hist[5][kHistColsPerBlock];  // index j*32 + lane  <->  column lane*16 + j
+  __shared__ uint32_t s_lut[256];
   for (int i = threadIdx.x; i < 5 * kHistColsPerBlock; i += kHistThreads) (&s_hist[0][0])[i] = 0;
+  s_lut[threadIdx.x] = hist_lut_entry(threadIdx.x, kAscii);
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -65,61 +79,52 @@ __global__ void __launch_bounds__(kHistThreads) hist_vec16_kernel(const uint8_t*
   const int64_t row_end = min(row_begin + rows_per_block, n_seqs);
   const bool active = col0 < cols_padded;  // cols_padded is a multiple of 16 and <= row_stride
 
-  uint32_t cnt[5][4];
+  uint32_t acc[16];
 #pragma unroll
-  for (int k = 0; k < 5; ++k)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) cnt[k][j] = 0;
+  for (int j = 0; j < 16; ++j) acc[j] = 0;
   int since_flush = 0;
 
   auto flush = [&]() {
 #pragma unroll
-    for (int k = 0; k < 5; ++k)
+    for (int j = 0; j < 16; ++j) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t v = cnt[k][j];
-        if (v) {
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            uint32_t c = (v >> (8 * b)) & 0xffu;
-            if (c) atomicAdd(&s_hist[k][lane * 16 + j * 4 + b], c);
-          }
-        }
-        cnt[k][j] = 0;
-      }
+      for (int k = 0; k < 5; ++k) atomicAdd(&s_hist[k][j * 32 + lane], (acc[j] >> (6 * k)) & 63u);
+      acc[j] = 0;
+    }
     since_flush = 0;
+  };
+  auto count16 = [&](const uint4& v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[4 * q + b] += s_lut[(w[q] >> (8 * b)) & 0xffu];
   };
 
   if (active) {
-    for (int64_t r = row_begin + warp; r < row_end; r += kHistThreads / 32) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(raw + r * row_stride + col0));
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    constexpr int kStep = kHistThreads / 32;  // rows between two loads of a warp
+    const uint8_t* p = raw + col0;
+    int64_t r = row_begin + warp;
+    for (; r + (kHistUnroll - 1) * kStep < row_end; r += kHistUnroll * kStep) {
+      uint4 v[kHistUnroll];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (kAscii) {
-          const uint32_t y = w[j] | 0x20202020u;
-          cnt[0][j] += __vcmpeq4(y, 0x61616161u) & 0x01010101u;
-          cnt[1][j] += __vcmpeq4(y, 0x63636363u) & 0x01010101u;
-          cnt[2][j] += __vcmpeq4(y, 0x67676767u) & 0x01010101u;
-          cnt[3][j] += __vcmpeq4(y, 0x74747474u) & 0x01010101u;
-          cnt[4][j] += __vcmpeq4(w[j], 0x2d2d2d2du) & 0x01010101u;
-        } else {
-          cnt[0][j] += __vcmpeq4(w[j], 0x00000000u) & 0x01010101u;
-          cnt[1][j] += __vcmpeq4(w[j], 0x01010101u) & 0x01010101u;
-          cnt[2][j] += __vcmpeq4(w[j], 0x02020202u) & 0x01010101u;
-          cnt[3][j] += __vcmpeq4(w[j], 0x03030303u) & 0x01010101u;
-          cnt[4][j] += __vcmpeq4(w[j], 0x04040404u) & 0x01010101u;
-        }
-      }
-      if (++since_flush == 255) flush();
+      for (int u = 0; u < kHistUnroll; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(p + (r + u * kStep) * row_stride));
+#pragma unroll
+      for (int u = 0; u < kHistUnroll; ++u) count16(v[u]);
+      since_flush += kHistUnroll;
+      if (since_flush > kHistFlushRows - kHistUnroll) flush();
+    }
+    for (; r < row_end; r += kStep) {
+      count16(__ldg(reinterpret_cast<const uint4*>(p + r * row_stride)));
+      if (++since_flush == kHistFlushRows) flush();
     }
     flush();
   }
   __syncthreads();
   const int64_t cb = (int64_t)blockIdx.x * kHistColsPerBlock;
   for (int i = threadIdx.x; i < 5 * kHistColsPerBlock; i += kHistThreads) {
-    const int k = i / kHistColsPerBlock, c = i % kHistColsPerBlock;
-    const uint32_t v = s_hist[k][c];
+    const int k = i / kHistColsPerBlock, c = i % kHistColsPerBlock;  // c = column within the block
+    const uint32_t v = s_hist[k][(c & 15) * 32 + (c >> 4)];
     if (v && cb + c < cols_padded) atomicAdd(&hist[(int64_t)k * cols_padded + cb + c], v);
   }
 }
@@ -273,73 +278,86 @@ __global__ void site_map_kernel(const uint8_t* __restrict__ keep, const int32_t*
 
 // ---------------------------------------------------------------------------------------------
 // Kernel 1d: encode + transpose + gather of the kept columns.
-// Tile = 128 sequences x 128 raw columns.  Global reads are 4-byte words arranged so that a warp
-// request covers four 32-byte sectors (8 lanes x 4 columns, 4 row groups); a 4x4 block of RAW bytes is
-// transposed in registers with PRMT and stored conflict-free into a [128 cols][33 words] tile;
-// only the kept columns are then encoded (SWAR, 4 sequences per word — the ALU cost scales with the
-// keep ratio, 1/3 at config 4) and written as 128-byte rows of the site-major code matrix.  Rows
-// beyond n_seqs are padded with 0xff, which encodes to 5 (Unknown), so the pair operands see zeros there.
+// Tile = 128 sequences x 128 raw columns, 256 threads.  Thread (strip = t % 8, row group = t / 8) loads 4
+// rows x 16 columns with four 16-byte loads (a warp request = 128 contiguous bytes of 4 rows each), transposes
+// four 4x4 blocks of RAW bytes in registers with PRMT and stores one 16-byte word group per block:
+// tile[row group][strip*20 + column%16] holds, per column, the 4 sequences of that row group.  The 4 pad words
+// per strip and the 164-word pitch make both the 16-byte stores and the 16-byte loads of the second phase
+// bank-conflict free.  Second phase: a warp takes 4 columns at a time, lane = row group, one 16-byte load, and
+// only KEPT columns are encoded (one shared-memory table lookup per byte — the cost scales with the keep ratio,
+// 1/3 at config 4) and written as 128-byte rows of the site-major code matrix.  Rows beyond n_seqs are padded with
+// 0xff, which encodes to 5 (Unknown), so the pair operands see zeros there.  Interior tiles take a path
+// without any per-element bounds checks.
 // ---------------------------------------------------------------------------------------------
 constexpr int kGatherThreads = 256;
+constexpr int kTilePitch = 164;  // words: 8 strips x (16 columns + 4 pad), + 4 so that the pitch is 4 mod 32
 
-template <bool kAscii, bool kAligned4>
+template <bool kAscii>
 __global__ void __launch_bounds__(kGatherThreads) gather_kernel(const uint8_t* __restrict__ raw, int64_t n_seqs,
-                                                                int64_t n_cols, int64_t row_stride,
+                                                                int64_t n_cols, int64_t row_stride, bool aligned16,
                                                                 const uint8_t* __restrict__ keep,
                                                                 const int32_t* __restrict__ rank,
                                                                 uint8_t* __restrict__ codes, int64_t ldc) {
-  __shared__ uint32_t tile[128][33];
+  __shared__ __align__(16) uint32_t tile[32][kTilePitch];
+  __shared__ uint32_t s_code[256];  // byte -> symbol code (lib.rs:53-64, or min(byte, 5) for pre-encoded input)
   const int64_t col_tile = (int64_t)blockIdx.x * 128;
   const int64_t seq_tile = (int64_t)blockIdx.y * 128;
   const int64_t col_hi = min(col_tile + 128, n_cols);
   // rank is an exclusive prefix, rank[x] for x in [0, cols_padded]; cols_padded >= n_cols.
   if (rank[col_hi] == rank[col_tile]) return;  // nothing kept in this column tile
+  s_code[threadIdx.x] = encode1(threadIdx.x, kAscii);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cs = warp & 3, rh = warp >> 2;
-  const int c8 = lane & 7, g = lane >> 3;
-  const int64_t col = col_tile + 32 * cs + 4 * c8;
+  const int strip = threadIdx.x & 7, rg = threadIdx.x >> 3;
+  const int64_t col = col_tile + 16 * strip;
+  const int64_t seq0 = seq_tile + 4 * rg;
+  uint4 r[4];
+  if (aligned16 && seq_tile + 128 <= n_seqs && col_tile + 128 <= row_stride) {
+    // interior tile: bytes between n_cols and the pitch are junk, but those columns are never kept
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const int s_local = 64 * rh + 16 * t + 4 * g;
-    uint32_t r[4];
+    for (int rr = 0; rr < 4; ++rr) r[rr] = __ldg(reinterpret_cast<const uint4*>(raw + (seq0 + rr) * row_stride + col));
+  } else {
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr) {
-      const int64_t seq = seq_tile + s_local + rr;
-      uint32_t w = 0xffffffffu;  // pad rows: a byte that encodes to 5 (Unknown) in both input modes
-      if (seq < n_seqs) {
-        const uint8_t* p = raw + seq * row_stride + col;
-        uint32_t x;
-        if (kAligned4 && col + 3 < row_stride) {
-          // bytes between n_cols and the pitch are junk, but those columns are never kept
-          x = __ldg(reinterpret_cast<const uint32_t*>(p));
-        } else {
-          x = 0;
+      uint32_t w[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};  // pad: encodes to 5 in both input modes
+      if (seq0 + rr < n_seqs) {
+        const uint8_t* p = raw + (seq0 + rr) * row_stride + col;
 #pragma unroll
-          for (int b = 0; b < 4; ++b)
-            if (col + b < n_cols) x |= (uint32_t)p[b] << (8 * b);
-        }
-        w = x;
+        for (int b = 0; b < 16; ++b)
+          if (col + b < n_cols) w[b >> 2] = (w[b >> 2] & ~(0xffu << (8 * (b & 3)))) | ((uint32_t)p[b] << (8 * (b & 3)));
       }
-      r[rr] = w;
+      r[rr] = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    const uint32_t t0 = __byte_perm(r[0], r[1], 0x5140), t1 = __byte_perm(r[0], r[1], 0x7362);
-    const uint32_t t2 = __byte_perm(r[2], r[3], 0x5140), t3 = __byte_perm(r[2], r[3], 0x7362);
-    const int word = s_local >> 2;
-    const int cl = 32 * cs + 4 * c8;
-    tile[cl + 0][word] = __byte_perm(t0, t2, 0x5410);
-    tile[cl + 1][word] = __byte_perm(t0, t2, 0x7632);
-    tile[cl + 2][word] = __byte_perm(t1, t3, 0x5410);
-    tile[cl + 3][word] = __byte_perm(t1, t3, 0x7632);
+  }
+  const uint32_t a[4] = {r[0].x, r[0].y, r[0].z, r[0].w}, b4[4] = {r[1].x, r[1].y, r[1].z, r[1].w};
+  const uint32_t c4[4] = {r[2].x, r[2].y, r[2].z, r[2].w}, d4[4] = {r[3].x, r[3].y, r[3].z, r[3].w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {  // 4x4 byte transpose: rows (a, b, c, d) x columns 4q..4q+3
+    const uint32_t t0 = __byte_perm(a[q], b4[q], 0x5140), t1 = __byte_perm(a[q], b4[q], 0x7362);
+    const uint32_t t2 = __byte_perm(c4[q], d4[q], 0x5140), t3 = __byte_perm(c4[q], d4[q], 0x7362);
+    *reinterpret_cast<uint4*>(&tile[rg][strip * 20 + 4 * q]) =
+        make_uint4(__byte_perm(t0, t2, 0x5410), __byte_perm(t0, t2, 0x7632), __byte_perm(t1, t3, 0x5410),
+                   __byte_perm(t1, t3, 0x7632));
   }
   __syncthreads();
-  for (int cl = warp; cl < 128; cl += kGatherThreads / 32) {
-    const int64_t c = col_tile + cl;
-    if (c < n_cols && keep[c]) {
-      const int64_t k = rank[c];
-      const uint32_t x = tile[cl][lane];
-      *reinterpret_cast<uint32_t*>(codes + k * ldc + seq_tile + 4 * lane) = kAscii ? encode4_ascii(x) : encode4_codes(x);
-    }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int quad = warp; quad < 32; quad += kGatherThreads / 32) {
+    const int64_t c0 = col_tile + 4 * quad;
+    if (c0 >= n_cols) break;
+    const uint32_t k4 = *reinterpret_cast<const uint32_t*>(keep + c0);  // keep[] is padded and zero beyond n_cols
+    if (k4 == 0u) continue;
+    const uint4 v = *reinterpret_cast<const uint4*>(&tile[lane][(quad >> 2) * 20 + 4 * (quad & 3)]);
+    const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if ((k4 >> (8 * j)) & 0xffu) {
+        const int64_t k = rank[c0 + j];
+        // one table lookup per byte: a third of the instructions of five SWAR compares
+        const uint32_t e0 = s_code[x[j] & 0xffu], e1 = s_code[(x[j] >> 8) & 0xffu];
+        const uint32_t e2 = s_code[(x[j] >> 16) & 0xffu], e3 = s_code[x[j] >> 24];
+        *reinterpret_cast<uint32_t*>(codes + k * ldc + seq_tile + 4 * lane) =
+            __byte_perm(__byte_perm(e0, e1, 0x0040), __byte_perm(e2, e3, 0x0040), 0x5410);
+      }
   }
 }
 
@@ -433,18 +451,17 @@ int run_filter(wld_ctx* c, int mode, float min_acgt, float min_minor, float max_
       c->site_map.as<int32_t>(), c->maj.as<int8_t>(), c->mnr.as<int8_t>());
   tm.launched();
 
-  const bool aligned4 = (reinterpret_cast<uintptr_t>(c->d_raw) % 4 == 0) && (c->row_stride % 4 == 0);
+  const bool aligned16 = (reinterpret_cast<uintptr_t>(c->d_raw) % 16 == 0) && (c->row_stride % 16 == 0);
   dim3 grid((unsigned)((c->n_cols + 127) / 128), (unsigned)(c->ldc / 128));
   if (grid.y > 65535) return c->fail(WLD_ERR_UNSUPPORTED, "n_seqs %lld too large for the gather grid", (long long)c->n_seqs);
-#define WLD_LAUNCH_GATHER(A, B)                                                                              \
-  gather_kernel<A, B><<<grid, kGatherThreads, 0, c->stream>>>(c->d_raw, c->n_seqs, c->n_cols, c->row_stride, \
-                                                             c->keep.as<uint8_t>(), c->rank.as<int32_t>(),   \
-                                                             c->codes.as<uint8_t>(), c->ldc)
-  if (ascii && aligned4) WLD_LAUNCH_GATHER(true, true);
-  else if (ascii) WLD_LAUNCH_GATHER(true, false);
-  else if (aligned4) WLD_LAUNCH_GATHER(false, true);
-  else WLD_LAUNCH_GATHER(false, false);
-#undef WLD_LAUNCH_GATHER
+  if (ascii)
+    gather_kernel<true><<<grid, kGatherThreads, 0, c->stream>>>(c->d_raw, c->n_seqs, c->n_cols, c->row_stride, aligned16,
+                                                               c->keep.as<uint8_t>(), c->rank.as<int32_t>(),
+                                                               c->codes.as<uint8_t>(), c->ldc);
+  else
+    gather_kernel<false><<<grid, kGatherThreads, 0, c->stream>>>(c->d_raw, c->n_seqs, c->n_cols, c->row_stride, aligned16,
+                                                                c->keep.as<uint8_t>(), c->rank.as<int32_t>(),
+                                                                c->codes.as<uint8_t>(), c->ldc);
   tm.launched();
   WLD_CUDA(c, cudaGetLastError());
   return WLD_OK;

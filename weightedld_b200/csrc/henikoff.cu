@@ -57,33 +57,48 @@ __global__ void table_kernel(const uint32_t* __restrict__ hist, int64_t cols_pad
 }
 
 // grid (seq blocks of 1024, site chunks of 256); each thread owns four consecutive sequences.
+// The gather-sum is bound by shared-memory lookups (one 8-byte load per cell), so sites are taken two at a
+// time: s_tab2[pair][6*code_a + code_b] = table[a][code_a] + table[b][code_b] — one lookup and one f64 add per
+// TWO cells.  (Summation order per sequence: pairs of sites in ascending order; deterministic.)
 __global__ void __launch_bounds__(kAccThreads) accumulate_kernel(const uint8_t* __restrict__ codes, int64_t ldc,
                                                                  int64_t n_kept, int64_t n_seqs,
                                                                  const double* __restrict__ table,
                                                                  double* __restrict__ partial) {
-  __shared__ double s_tab[kSiteChunk][8];
+  __shared__ double s_tab2[kSiteChunk / 2][36];
   const int64_t k0 = (int64_t)blockIdx.y * kSiteChunk;
   const int nk = (int)min((int64_t)kSiteChunk, n_kept - k0);
-  for (int i = threadIdx.x; i < nk * 8; i += kAccThreads) (&s_tab[0][0])[i] = table[k0 * 8 + i];
+  const int npairs = (nk + 1) / 2;
+  for (int i = threadIdx.x; i < npairs * 36; i += kAccThreads) {
+    const int pr = i / 36, e = i % 36;
+    const double ta = table[(k0 + 2 * pr) * 8 + e / 6];
+    const double tb = 2 * pr + 1 < nk ? table[(k0 + 2 * pr + 1) * 8 + e % 6] : 0.0;
+    (&s_tab2[0][0])[i] = __dadd_rn(ta, tb);
+  }
   __syncthreads();
   const int64_t s0 = ((int64_t)blockIdx.x * kAccThreads + threadIdx.x) * 4;
   if (s0 >= ldc) return;
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   const uint8_t* p = codes + k0 * ldc + s0;
-  int k = 0;
-  for (; k + 4 <= nk; k += 4) {
-    uint32_t w[4];
+  auto add_pair = [&](int pr, uint32_t wa, uint32_t wb) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) w[u] = __ldg(reinterpret_cast<const uint32_t*>(p + (int64_t)(k + u) * ldc));
+    for (int b = 0; b < 4; ++b) {
+      const uint32_t ca = min((wa >> (8 * b)) & 0xffu, 5u), cb = min((wb >> (8 * b)) & 0xffu, 5u);
+      acc[b] = __dadd_rn(acc[b], s_tab2[pr][ca * 6u + cb]);
+    }
+  };
+  int pr = 0;
+  for (; 2 * pr + 8 <= nk; pr += 4) {  // four pairs = eight site rows in flight (the loop is latency-bound)
+    uint32_t w[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < 8; ++u) w[u] = __ldg(reinterpret_cast<const uint32_t*>(p + (int64_t)(2 * pr + u) * ldc));
 #pragma unroll
-      for (int b = 0; b < 4; ++b) acc[b] = __dadd_rn(acc[b], s_tab[k + u][(w[u] >> (8 * b)) & 7u]);
+    for (int u = 0; u < 4; ++u) add_pair(pr + u, w[2 * u], w[2 * u + 1]);
   }
-  for (; k < nk; ++k) {
-    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p + (int64_t)k * ldc));
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[b] = __dadd_rn(acc[b], s_tab[k][(w >> (8 * b)) & 7u]);
+  for (; pr < npairs; ++pr) {
+    const uint32_t wa = __ldg(reinterpret_cast<const uint32_t*>(p + (int64_t)(2 * pr) * ldc));
+    // odd tail: the partner row does not exist; code 0 selects table[a][code_a] + 0
+    const uint32_t wb = 2 * pr + 1 < nk ? __ldg(reinterpret_cast<const uint32_t*>(p + (int64_t)(2 * pr + 1) * ldc)) : 0u;
+    add_pair(pr, wa, wb);
   }
 #pragma unroll
   for (int b = 0; b < 4; ++b)
