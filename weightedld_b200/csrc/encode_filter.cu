@@ -222,45 +222,58 @@ __global__ void decide_kernel(uint32_t* __restrict__ hist, int64_t cols_padded, 
 // kept sites' major/minor symbols.
 // ---------------------------------------------------------------------------------------------
 constexpr int kScanThreads = 1024;
+// One block: every thread counts a contiguous segment of the flags, the 1024 segment sums are scanned once,
+// and the segment is walked again to write the ranks (two passes, three barriers in total).
 __global__ void __launch_bounds__(kScanThreads) scan_kernel(const uint8_t* __restrict__ keep,
                                                             int64_t cols_padded, int32_t* __restrict__ rank,
                                                             int32_t* __restrict__ kept_count) {
   __shared__ int32_t s_warp[kScanThreads / 32];
-  __shared__ int32_t s_base;
-  if (threadIdx.x == 0) s_base = 0;
-  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int64_t base = 0; base < cols_padded; base += kScanThreads) {
-    const int64_t col = base + threadIdx.x;
-    const int flag = col < cols_padded ? keep[col] : 0;
-    int incl = flag;
+  // segments are multiples of 16 flags (cols_padded is one): 16-byte loads, flags are 0/1 so popcount sums them
+  const int64_t seg = ((cols_padded / 16 + kScanThreads - 1) / kScanThreads) * 16;
+  const int64_t lo = min((int64_t)threadIdx.x * seg, cols_padded), hi = min(lo + seg, cols_padded);
+  int sum = 0;
+  for (int64_t c = lo; c < hi; c += 16) {
+    const uint4 v = *reinterpret_cast<const uint4*>(keep + c);
+    sum += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+  }
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int v = s_warp[lane];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
+      const int t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
     }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      int v = s_warp[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += t;
-      }
-      s_warp[lane] = v;  // inclusive over warps
-    }
-    __syncthreads();
-    const int warp_off = warp ? s_warp[warp - 1] : 0;
-    const int excl = s_base + warp_off + incl - flag;
-    if (col < cols_padded) rank[col] = excl;
-    __syncthreads();
-    if (threadIdx.x == 0) s_base += s_warp[kScanThreads / 32 - 1];
-    __syncthreads();
+    s_warp[lane] = v;  // inclusive over warps
   }
-  if (threadIdx.x == 0) {
-    rank[cols_padded] = s_base;
-    *kept_count = s_base;
+  __syncthreads();
+  int run = (warp ? s_warp[warp - 1] : 0) + incl - sum;  // exclusive prefix of this thread's segment
+  for (int64_t c = lo; c < hi; c += 16) {
+    const uint4 v = *reinterpret_cast<const uint4*>(keep + c);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int4 r;
+      r.x = run;
+      r.y = r.x + (int)(w[q] & 1u);
+      r.z = r.y + (int)((w[q] >> 8) & 1u);
+      r.w = r.z + (int)((w[q] >> 16) & 1u);
+      run = r.w + (int)((w[q] >> 24) & 1u);
+      *reinterpret_cast<int4*>(rank + c + 4 * q) = r;
+    }
+  }
+  if (threadIdx.x == kScanThreads - 1) {
+    const int total = s_warp[kScanThreads / 32 - 1];
+    rank[cols_padded] = total;
+    *kept_count = total;
   }
 }
 

@@ -34,7 +34,7 @@ __device__ __forceinline__ uint16_t bf16_bits_of_small_int(uint32_t v) {
 // limb_sums[l] = sum over sequences of limb l (u64) — an upper bound of every Gram entry of that limb.
 __global__ void __launch_bounds__(1024) quantize_kernel(const float* __restrict__ w, int64_t n_seqs, int64_t ldc,
                                                         int n_limbs, int limb_bits, double* __restrict__ q,
-                                                        uint16_t* __restrict__ limbs,
+                                                        uint16_t* __restrict__ limbs, uint8_t* __restrict__ limbs8,
                                                         unsigned long long* __restrict__ limb_sums,
                                                         int* __restrict__ flags) {
   __shared__ float s_red[32], s_min[32];
@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(1024) quantize_kernel(const float* __restrict_
       const int shift = limb_bits * (n_limbs - 1 - l);
       uint32_t v = (uint32_t)(qi >> shift) & (limb_bits > 0 ? limb_mask : 1u);
       limbs[(int64_t)l * ldc + s] = (uint16_t)v;  // raw limb value 0..255; converted at expansion
+      limbs8[(int64_t)l * ldc + s] = (uint8_t)v;  // the same as bytes for the u8 operands (SWAR expansion)
       sums[l] += v;
     }
   }
@@ -213,6 +214,24 @@ __global__ void __launch_bounds__(256) expand_b_kernel(const uint8_t* __restrict
   uint32_t cw[Expand<kI8>::kWords];
   load_codes<kI8>(codes + j * ldc + s0, cw);
   const int sm = maj[j], sn = mnr[j];
+  if constexpr (kI8) {
+    // u8 operands: indicator masks by SWAR compare once, then row = mask & limb bytes (4 elements per AND)
+    const uint8_t* limbs8 = reinterpret_cast<const uint8_t*>(limbs) + sizeof(uint16_t) * 4 * (size_t)ldc;
+    const uint32_t rm = sm < 0 ? 0xffffffffu : (uint32_t)sm * 0x01010101u;  // 0xff never matches a code
+    const uint32_t rn = sn < 0 ? 0xffffffffu : (uint32_t)sn * 0x01010101u;
+    uint32_t mm[4], mn[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      mm[w] = __vcmpeq4(cw[w], rm);
+      mn[w] = __vcmpeq4(cw[w], rn);
+    }
+    for (int l = 0; l < n_limbs; ++l) {
+      const uint4 lv = __ldg(reinterpret_cast<const uint4*>(limbs8 + (int64_t)l * ldc + s0));
+      *reinterpret_cast<uint4*>(opB + (row0 + l) * kp + s0) = make_uint4(lv.x & mm[0], lv.y & mm[1], lv.z & mm[2], lv.w & mm[3]);
+      *reinterpret_cast<uint4*>(opB + (row0 + n_limbs + l) * kp + s0) =
+          make_uint4(lv.x & mn[0], lv.y & mn[1], lv.z & mn[2], lv.w & mn[3]);
+    }
+  } else {
   for (int l = 0; l < n_limbs; ++l) {
     uint32_t vals[kSeq];
 #pragma unroll
@@ -228,6 +247,7 @@ __global__ void __launch_bounds__(256) expand_b_kernel(const uint8_t* __restrict
     store_select<kI8>(opB + ((row0 + l) * kp + s0) * ES, cw, sm, vals);
     store_select<kI8>(opB + ((row0 + n_limbs + l) * kp + s0) * ES, cw, sn, vals);
   }
+  }
 }
 
 }  // namespace
@@ -241,7 +261,7 @@ int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm) {
   const unsigned long long exact_limit = i8 ? ((1ull << 31) - 1) : (1ull << 24);
 
   WLD_CUDA(c, c->q.ensure(sizeof(double) * (size_t)c->ldc));
-  WLD_CUDA(c, c->limbs.ensure(sizeof(uint16_t) * 4 * (size_t)c->ldc));
+  WLD_CUDA(c, c->limbs.ensure((sizeof(uint16_t) + 1) * 4 * (size_t)c->ldc));  // u16 [4][ldc] then u8 [4][ldc]
   WLD_CUDA(c, c->counters.ensure(sizeof(unsigned long long) * 16));
   WLD_CUDA(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream));
 
@@ -253,6 +273,7 @@ int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm) {
   for (;;) {
     quantize_kernel<<<1, 1024, 0, c->stream>>>(c->w32.as<float>(), n, c->ldc, gm.n_limbs, bits,
                                                c->q.as<double>(), c->limbs.as<uint16_t>(),
+                                               c->limbs.as<uint8_t>() + sizeof(uint16_t) * 4 * (size_t)c->ldc,
                                                c->counters.as<unsigned long long>() + 8,
                                                reinterpret_cast<int*>(c->counters.as<unsigned long long>() + 12));
     tm.launched();
