@@ -312,6 +312,7 @@ def run_ours(args):
             "achieved_useful": useful_flop / (pair_ms * 1e-3) / 1e12,
             "executed": info.executed_flop / (pair_ms * 1e-3) / 1e12,
             "algorithmic_flop_per_pair": 8 * n_seqs * info.n_limbs, "n_limbs": info.n_limbs, "limb_bits": info.limb_bits,
+            "frac_of_nominal_dense_int8": (achieved / 4500.0) if info.kernel == 2 else None,  # 4.5 POP/s data-sheet figure
             "kernel_ms": pair_ms, "traffic": None,
             "tile_schedule": {0: "round-robin", 1: "per-L2-die contiguous halves of the strip-rasterised tile list",
                               2: "per-L2-die, dealt per round"}.get(info.die_schedule, "?"),
@@ -323,6 +324,15 @@ def run_ours(args):
         except Exception:
             pass
 
+    # HBM-bound stages: algorithmic bytes over the stage timers of the library (CUDA events; the filter
+    # stage includes its small decision / scan kernels and one host round trip for the kept count).
+    es = 1 if info.kernel == 2 else 2
+    cells_raw, cells_kept = float(n_seqs) * n_cols, float(n_seqs) * n_kept
+    hbm_bytes = {"histogram": cells_raw, "filter": cells_raw + cells_kept, "henikoff": cells_kept,
+                 "pair_prep": 2 * cells_kept + cells_kept * es * (2 + 2 * info.n_limbs) / max(world, 1)}
+    hbm = {k: {"bytes": b, "ms": stages[k] / args.steps, "gbs": b / (stages[k] / args.steps * 1e-3) / 1e9,
+               "frac_of_measured_hbm": b / (stages[k] / args.steps * 1e-3) / 1e9 / pk["hbm"]}
+           for k, b in hbm_bytes.items() if stages[k] > 0}
     if rank == 0:
         line = {
             "metric": "weighted LD site-pairs/sec", "value": total_pairs / (ms * 1e-3), "unit": "site-pairs/s",
@@ -337,6 +347,7 @@ def run_ours(args):
                        "parallelism": f"triangle-partition x{world}", "l2": "inputs larger than L2 (no flush needed)"},
             "stages_ms": {k: v / args.steps for k, v in stages.items()},
             "roofline": roof,
+            "hbm_stages": hbm,
             "e2e": {"value": total_pairs / (ms_e2e * 1e-3), "unit": "site-pairs/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(chars_np.nbytes),  # whole job: each rank copies 1/N of the rows
                     "d2h_bytes_per_step": int(20 * surv_all + 64 * world),

@@ -19,8 +19,8 @@
 namespace wld {
 namespace {
 
-constexpr int kProbeAddr = 32;
-constexpr int kProbeReps = 4;
+constexpr int kProbeAddr = 16;
+constexpr int kProbeReps = 3;
 constexpr int kProbeStrideWords = (4096 + 256) / 4;
 
 __global__ void die_probe_kernel(unsigned int* buf, unsigned int* sync, unsigned short* lat, unsigned zero) {
@@ -105,7 +105,7 @@ bool measure(int sm_count, cudaStream_t stream, std::vector<uint8_t>& out) {
     ++used;
     for (int s = 0; s < sm_count; ++s) bit[(size_t)s].push_back(h[(size_t)s * kProbeAddr + a] * 2 > lo + hi);
   }
-  if (used < 8) return false;
+  if (used < 6) return false;
   out.assign((size_t)sm_count, 0);
   int n1 = 0;
   for (int s = 0; s < sm_count; ++s) {
