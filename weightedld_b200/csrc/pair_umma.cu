@@ -7,26 +7,32 @@
 //
 // Math.  opA rows (2i+alpha) are the 0/1 indicators of site i's major (alpha=0) / minor (alpha=1)
 // symbol, opB rows (site j, beta, limb l) are indicator_beta(j) * limb_l(weight); see
-// pair_prep.cu.  One output tile is
-//     D[128 x 256] = opA[mi*128 .. +128, :] * opB[nj*256 .. +256, :]^T        (K = sequences)
-// i.e. 64 sites i  x  2*SPG sites j.  D[(i,alpha)][(j,beta,l)] is an exact integer in fp32; the
-// epilogue recombines limbs in f64:  S = sum_l D_l * 2^(b*(NL-1-l))  and gets
+// pair_prep.cu.  One output tile of a CTA pair (cta_group::2; kCtas = 1 halves M) is
+//     D[256 x 256] = opA[mi*256 .. +256, :] * opB[nj*256 .. +256, :]^T        (K = sequences)
+// i.e. 128 sites i  x  2*SPG sites j.  D[(i,alpha)][(j,beta,l)] is an exact integer (s32 for u8
+// operands, fp32 below 2^24 for bf16 operands); the epilogue recombines limbs
+//     S = sum_l D_l * 2^(b*(NL-1-l))   and gets
 //     AB = S[i,0][j,0]  Ab = S[i,0][j,1]  aB = S[i,1][j,0]  ab = S[i,1][j,1].
 //
-// Kernel shape (persistent, one CTA per SM, 384 threads, 1 CTA/SM because TMEM is fully used):
-//   warp 0      TMA producer: 4-stage ring of {A 128x64, B 256x64} bf16 tiles (48 KB/stage),
-//               128B-swizzled, completion on `full[stage]` mbarriers
-//   warp 1      MMA issuer: one lane issues 4 x tcgen05.mma (M128 N256 K16) per stage into one of
-//               two 256-column TMEM accumulators; tcgen05.commit frees the stage / publishes the tile
-//   warp 2      TMEM allocator (512 columns)
-//   warps 4-11  epilogue: warp w reads TMEM lanes 32*(w%4).. (tcgen05.ld 32x32b) and the column
-//               half (w-4)/4 (= one 128-row group of opB); adjacent lanes (alpha=0/1 of a site)
-//               swap halves of the 2x2 table by shuffle; division-free pre-filter; exact f64
-//               statistics only for candidates; warp-aggregated atomic compaction.
+// Kernel shape (persistent, one CTA per SM because TMEM is fully used, 384 threads, clusters of 2):
+//   warp 0      TMA producer (both CTAs): 6-stage ring of {A 128 rows x 128 B, B-half 128 rows x 128 B}
+//               (32 KB / stage / CTA), 128B-swizzled; the bytes of both CTAs complete the leader's
+//               `full[stage]` mbarrier
+//   warp 1      MMA issuer (leader CTA): one lane issues 4 x tcgen05.mma.cta_group::2 (M256 N256 K32
+//               for kind::i8, K16 for kind::f16) per stage into one of two 256-column TMEM accumulators;
+//               tcgen05.commit (multicast to both CTAs) frees the stage / publishes the tile
+//   warp 2      TMEM allocator (512 columns);  warp 3: die-aware schedule set-up
+//   warps 4-11  epilogue (each CTA on its own 128 accumulator rows): warp w reads TMEM lanes
+//               32*(w%4).. (tcgen05.ld 32x32b) and the column half (w-4)/4 (= one 128-row group of opB);
+//               adjacent lanes (alpha=0/1 of a site) swap halves of the 2x2 table by shuffle; fp32
+//               conservative pre-filter; candidates are queued and the exact f64 statistics run on full
+//               groups of 32; warp-aggregated atomic compaction.
 //   The accumulator is double-buffered, so the epilogue of tile t overlaps the MMAs of tile t+1.
+//   Tile order: strips of 8 N tiles; each L2 die's CTA pairs walk their own contiguous part of the
+//   list (die_map.cu) so the limb strip a die's L2 holds is reused only by that die's SMs.
 //
-// Roofline: tensor pipe.  Algorithmic flop per site pair per launch = 8*N*NL (4 weighted dot
-// products of length N per limb); executed = 2*128*256*Kp per tile.
+// Roofline: tensor pipe.  Algorithmic op per site pair per launch = 8*N*NL (4 weighted dot
+// products of length N per limb); executed = 2*256*256*Kp per tile.
 #include <climits>
 #include <cmath>
 #include <cstdlib>
