@@ -108,6 +108,21 @@ def test_config3_full_size_properties(c3, oracle):
         assert passes == ((a_col, b_col) in have)
 
 
+def test_progress_reports_are_monotonic_at_full_size(c3):
+    """lib.rs:582-584,670-674: first report 0 on the caller's thread, then running pair counts while tiles
+    finish (polled from the device), never decreasing, the last one = every pair."""
+    import weightedld_b200 as wld
+    seen = []
+    with wld.Context(0) as ctx:
+        ctx.load_alignment(c3)
+        L = ctx.filter_sites()
+        ctx.henikoff()
+        for _ in range(3):
+            seen.clear()
+            n, done = ctx.ld_pairs(0.1, seen.append)
+            assert seen[0] == 0 and seen[-1] == done == L * (L - 1) // 2 and seen == sorted(seen)
+
+
 def test_config5_shape_properties(oracle):
     """10,000 sequences (config 5's K), 6,000 sites: all pairs computed, permutation invariance, variants agree."""
     import weightedld_b200 as wld

@@ -68,6 +68,7 @@ struct wld_ctx {
   int device = 0;
   int sm_count = 0;
   cudaStream_t own_stream = nullptr;
+  cudaStream_t poll_stream = nullptr;   // progress polling while the pair kernel runs (created on first use)
   cudaStream_t stream = nullptr;
   wld::Stage stage = wld::Stage::Created;
   std::string err;

@@ -629,6 +629,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
         if constexpr (kCtas == 2) mbar_arrive_cluster(tempty_bar(buf) & kPeerBitMask);  // the leader's barrier
         else mbar_arrive(tempty_bar(buf));
       }
+      if ((tcount & 31u) == 31u) {  // publish progress every 32 tiles (polled by wld_ld_pairs for the callback, lib.rs:670-674)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) done += __shfl_xor_sync(0xffffffffu, done, o);
+        if (lane == 0 && done) atomicAdd(p.pairs_done, done);
+        done = 0;
+      }
     }
     while (queue.count > 0) queue.drain32(p.thr, p.out, p.py_aux);  // tail
 #pragma unroll

@@ -1,6 +1,8 @@
 // wld_api.cu — the C ABI declared in include/wld.h (stage orchestration, ownership, errors,
 // result ordering).  No torch types, no CPU fallback: every stage is a CUDA kernel in this library
 // and every failure is reported through wld_status + wld_last_error.
+#include <time.h>
+
 #include <algorithm>
 #include <cmath>
 #include <new>
@@ -63,6 +65,7 @@ void wld_destroy(wld_ctx* c) {
     if (t.beg) cudaEventDestroy(t.beg);
     if (t.end) cudaEventDestroy(t.end);
   }
+  if (c->poll_stream) cudaStreamDestroy(c->poll_stream);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -323,6 +326,7 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
       int rc = run_pair_python_prepare(c);
       if (rc != WLD_OK) return rc;
     }
+    unsigned long long progress_last = 0;
     for (int attempt = 0; attempt < 3; ++attempt) {
       WLD_CUDA(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 8, c->stream));
       c->die_used = 0;
@@ -331,6 +335,23 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
         // pairs whose per-pair allele call may differ from the per-site call (WeightedLD.py:186-211)
         if (rc == WLD_OK && c->compat == WLD_COMPAT_PYTHON) rc = run_pair_python_fixup(c, r2_threshold);
         if (rc != WLD_OK) return rc;
+      }
+      if (progress) {
+        // all_weighted_ld_pairs reports the running pair count while tiles finish (lib.rs:670-674).  The kernel
+        // publishes its count every few tiles; it is polled here, on the caller's thread, over a second stream.
+        if (!c->poll_stream) WLD_CUDA(c, cudaStreamCreateWithFlags(&c->poll_stream, cudaStreamNonBlocking));
+        while (cudaStreamQuery(c->stream) == cudaErrorNotReady) {
+          unsigned long long v = 0;
+          if (cudaMemcpyAsync(&v, c->counters.as<unsigned long long>() + 1, sizeof v, cudaMemcpyDeviceToHost,
+                              c->poll_stream) != cudaSuccess || cudaStreamSynchronize(c->poll_stream) != cudaSuccess)
+            break;
+          if (v > progress_last) {  // never decreases, also across a re-run of the stage
+            progress(v, user);
+            progress_last = v;
+          }
+          struct timespec ts = {0, 2000000};  // 2 ms
+          nanosleep(&ts, nullptr);
+        }
       }
       unsigned long long cnt[4] = {0, 0, 0, 0};
       cudaError_t e = cudaMemcpyAsync(cnt, c->counters.p, sizeof cnt, cudaMemcpyDeviceToHost, c->stream);
