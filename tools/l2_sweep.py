@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Sweeps the pair stage's L2 knobs on one workload in ONE process (the 500 MB synthetic input is
 generated once): rasterisation strip width (WLD_STRIP) x TMA L2 eviction hints for the indicator (A)
-and limb (B) panels (WLD_HINT_A / WLD_HINT_B = normal|first|last).
+and limb (B) panels (WLD_HINT_A / WLD_HINT_B = normal|first|last) x die-aware schedule (WLD_DIE = 0|1|2).
+(K-loop rotation and the TMA L2-promotion size were swept with earlier versions of this tool and removed:
+profiles/r01_l2_sweep_c5_die_schedule*.)
 
     python tools/l2_sweep.py --workload c5 --steps 5 --warmup 3 --out gpurun_out/l2_sweep.json
     ncu --metrics dram__bytes_read.sum,gpu__time_duration.sum -k regex:pair_umma --csv --log-file x.csv \
@@ -28,9 +30,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--strips", default="8,16,24")
     ap.add_argument("--hints", default="nn,fn,nl,fl")
-    ap.add_argument("--krots", default="0")
     ap.add_argument("--dies", default="1")
-    ap.add_argument("--promos", default="3")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
 
@@ -43,13 +43,10 @@ def main():
     dev = torch.from_numpy(chars).cuda()
     names = {"n": "normal", "f": "first", "l": "last"}
     rows = []
-    for strip, hint, krot, die, promo in itertools.product([int(x) for x in args.strips.split(",")], args.hints.split(","),
-                                                           args.krots.split(","), args.dies.split(","),
-                                                           args.promos.split(",")):
+    for strip, hint, die in itertools.product([int(x) for x in args.strips.split(",")], args.hints.split(","),
+                                              args.dies.split(",")):
         os.environ["WLD_DIE"] = die
-        os.environ["WLD_L2PROMO"] = promo
         os.environ["WLD_STRIP"] = str(strip)
-        os.environ["WLD_KROT"] = krot
         os.environ["WLD_HINT_A"] = names[hint[0]]
         os.environ["WLD_HINT_B"] = names[hint[1]]
         with wld.Context(0) as ctx:
@@ -63,7 +60,7 @@ def main():
                     n, done = ctx.ld_pairs(bench.R2_THRESHOLD)
                     if it >= args.warmup:
                         ms.append(ctx.stage_ms(wld.STAGE_PAIR))
-            row = {"promo": int(promo), "die": int(die), "krot": int(krot), "strip": strip, "hint_a": names[hint[0]], "hint_b": names[hint[1]], "pair_ms": float(np.mean(ms)),
+            row = {"die": int(die), "strip": strip, "hint_a": names[hint[0]], "hint_b": names[hint[1]], "pair_ms": float(np.mean(ms)),
                    "pair_ms_min": float(np.min(ms)), "survivors": n, "pairs": done, "die_schedule": ctx.pair_info().die_schedule,
                    "die_sms": list(ctx.pair_info().die_sms), "clocks": clk.summary()}
         rows.append(row)

@@ -88,7 +88,6 @@ struct UmmaParams {
   int die_pairs[2];
   int die_split;
   int die_mode;               // 1: front/back split of the list; 2: every round of n0+n1 tiles is dealt die 0 first
-  int k_rot;                // K-loop rotation stride: tile t starts at K block (t * k_rot) % k_blocks (0 = off)
   uint64_t hint_a, hint_b;  // L2 eviction policy of the indicator (streamed) and limb (strip-resident) panels
   const uint2* py_aux; // WLD_COMPAT_PYTHON only (else null): per-site {n5, margin}, see py_flagged
   PairOut out;
@@ -480,10 +479,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
         const uint2 tile = p.tiles[t];
         const int m_row = (int)tile.x * (kBlockM * kCtas) + (int)cta_rank * kBlockM;
         const int n_row = (int)tile.y * kBlockN + (int)cta_rank * Cfg::kBRows;
-        // Tiles that share a panel run concurrently; starting each at a different K block keeps them from
-        // requesting the same lines in the same instant (one fetches, the others hit in L2).
-        int kb = p.k_rot ? (int)(((long long)t * p.k_rot) % p.k_blocks) : 0;
-        for (int it = 0; it < p.k_blocks; ++it, kb = (kb + 1 == p.k_blocks) ? 0 : kb + 1) {
+        // (Tiles that share a panel run in lockstep through K: one fetches a line, the others hit in L2.  Starting
+        // concurrent tiles at different K blocks was tried and raises DRAM traffic, profiles/r01_l2_sweep_*.)
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, p.error_flag, 1);
           if constexpr (kCtas == 2) {
             if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::kBytes);
@@ -678,10 +676,7 @@ bool make_tensor_map(CUtensorMap* map, void* base, uint64_t rows, uint64_t kp, u
   const cuuint64_t gstride[1] = {kp * (uint64_t)elem_bytes};
   const cuuint32_t box[2] = {(cuuint32_t)(kBlockKBytes / elem_bytes), box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
-  if (const char* e = std::getenv("WLD_L2PROMO"))  // experiments: 0 none, 1 64 B, 2 128 B, 3 256 B
-    promo = e[0] == '0' ? CU_TENSOR_MAP_L2_PROMOTION_NONE : e[0] == '1' ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-          : e[0] == '2' ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  const CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;  // none / 128 B / 256 B measured equal
   return fn(map, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim,
             gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, promo,
@@ -833,8 +828,6 @@ int run_pair_umma(wld_ctx* c, float thr) {
       if (!e) return dflt;
       return e[0] == 'f' ? kL2EvictFirst : e[0] == 'l' ? kL2EvictLast : kL2EvictNormal;
     };
-    prm.k_rot = 0;
-    if (const char* e = std::getenv("WLD_KROT")) prm.k_rot = std::max(0, std::atoi(e));
     prm.hint_a = policy("WLD_HINT_A", kL2EvictNormal);
     prm.hint_b = policy("WLD_HINT_B", kL2EvictNormal);
   }
