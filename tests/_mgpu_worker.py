@@ -1,0 +1,52 @@
+"""Worker of tests/test_multi_gpu.py: run under torchrun, one process per GPU."""
+import json
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import weightedld_b200 as wld  # noqa: E402
+from weightedld_b200.multi_gpu import ShardedLoader, gather_pairs  # noqa: E402
+from weightedld_b200.synth import make_alignment  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    chars = make_alignment(700, 5000, seed=41, block=120, clonal=True)
+    host = torch.from_numpy(chars).pin_memory()
+    loader = ShardedLoader(chars.shape[0], chars.shape[1], rank, world, torch.device("cuda", local))
+    full = loader.load(host)                       # own rows over PCIe + all-gather over NVLink
+    assert torch.equal(full.cpu(), torch.from_numpy(chars))
+    with wld.Context(local) as ctx:
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        ctx.set_partition(rank, world)
+        ctx.load_alignment(full)
+        n_kept = ctx.filter_sites()
+        ctx.henikoff()
+        n, done = ctx.ld_pairs(0.1)
+        shard = ctx.fetch_pairs(n, wld.FETCH_KEPT_INDEX | wld.FETCH_UNORDERED)
+        site_map = ctx.site_map()
+    t = torch.tensor([done], device="cuda", dtype=torch.int64)
+    dist.all_reduce(t)
+    merged = gather_pairs(shard, n_kept, site_map, rank, world)
+    if rank == 0:
+        with wld.Context(local) as ctx:            # the whole triangle on one GPU
+            ctx.load_alignment(chars)
+            assert ctx.filter_sites() == n_kept
+            ctx.henikoff()
+            n1, done1 = ctx.ld_pairs(0.1)
+            whole = ctx.fetch_pairs(n1)
+        print(json.dumps({"world": world, "pairs": int(t.item()), "expected": n_kept * (n_kept - 1) // 2, "done1": done1,
+                          "survivors": len(merged), "identical": merged.tobytes() == whole.tobytes()}))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
