@@ -14,6 +14,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
 
+def pytest_sessionstart(session):
+    """Built artefacts are not in the history: build them (nvcc cross-compiles without a GPU) when a fresh
+    checkout runs the tests before __graft_entry__.build()."""
+    needed = [ROOT / "weightedld_b200" / "libwld.so", ROOT / "weightedld_b200" / "weighted_ld",
+              ROOT / "oracle" / "_build" / "liboracle.so"]
+    if not all(p.exists() for p in needed):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
 @pytest.fixture(scope="session")
 def golden():
     return {

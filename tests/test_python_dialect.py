@@ -270,3 +270,51 @@ def test_cli_vcf_input_rust_dialect(golden, tmp_path, oracle):
         f"{pos[p['a']]}\t{pos[p['b']]}\t{oracle.format_f3(p['d'])}\t{oracle.format_f3(p['d_prime'])}\t{oracle.format_f3(p['r2'])}"
         for p in pairs]
     assert (tmp_path / "p.tsv").read_text().splitlines() == want and len(want) > 5
+
+
+# ------------------------------------------------------------------------------------------ C++ readers (host only)
+def _fnv1a(data: bytes) -> int:
+    h = 1469598103934665603
+    for b in data:
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def _parse_only(*args):
+    import subprocess
+    r = subprocess.run([str(_cli()), "--parse-only", *args], capture_output=True, text=True)
+    return r.returncode, r.stdout.split(), r.stderr
+
+
+def test_cpp_readers_match_python_readers(golden, tmp_path):
+    """`weighted_ld --parse-only` (no GPU): the C++ FASTA (Rust and Biopython semantics) and VCF readers deliver
+    byte for byte what the Python host readers / the oracle deliver."""
+    import weightedld_b200 as wld
+    from weightedld_b200 import pycompat
+    for name, text in golden["fixtures"].items():
+        f = tmp_path / f"{name}.fasta"
+        f.write_text(text)
+        codes = pycompat.read_fasta(f)
+        rc, out, _ = _parse_only("--fasta-input", str(f), "--python-compat")
+        assert rc == 0 and out[:4] == [str(codes.shape[0]), str(codes.shape[1]), f"{_fnv1a(codes.tobytes()):016x}", "codes"], name
+        rc, out, err = _parse_only("--fasta-input", str(f))
+        if name.startswith("t1_"):
+            assert rc == 101 and "Not all sequences have the same number of symbols" in err   # lib.rs:180-182
+        else:
+            chars = wld.read_fasta(f).chars
+            assert rc == 0 and out[:4] == [str(chars.shape[0]), str(chars.shape[1]), f"{_fnv1a(chars.tobytes()):016x}", "ascii"]
+    f = tmp_path / "t7.vcf"
+    for text in (t7_text(), t7_text() + "\n"):
+        f.write_text(text)
+        aln, pos = pycompat.handle_vcf(f)
+        rc, out, _ = _parse_only("--vcf-input", str(f))
+        assert rc == 0 and out == [str(aln.shape[0]), str(aln.shape[1]), f"{_fnv1a(aln.tobytes()):016x}", "codes",
+                                   f"{_fnv1a(pos.astype('<i8').tobytes()):016x}"]
+    head = "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(f"s{k}" for k in range(4))
+    f.write_text(head + "\n1\t100\t.\tA\tC\t.\t.\t.\tGT\t0|1\t1/0\t.|1\t0|0\n1\t200\t.\tA\tC,G\t.\t.\t.\tGT\t2|1\t0|0\t1|1\t0|10\n")
+    aln, pos = pycompat.handle_vcf(f)
+    rc, out, _ = _parse_only("--vcf-input", str(f))
+    assert rc == 0 and out[2] == f"{_fnv1a(aln.tobytes()):016x}" and out[:2] == ["8", "2"]
+    f.write_text("no header here\n")
+    rc, out, err = _parse_only("--vcf-input", str(f))
+    assert rc == 1 and "No #CHROM header block identified" in err

@@ -77,7 +77,7 @@ struct Opt {  // main.rs:19-68
   std::string fasta_input, vcf_input, weights_output, pair_output;
   float min_acgt = 0.8f, min_minor = 0.02f, max_minor = 0.5f, r2_threshold = 0.1f;
   double min_acgt_f64 = 0.8, min_variability = 0.02;  // --python-compat parses these as Python floats
-  bool unweighted = false, python_compat = false;
+  bool unweighted = false, python_compat = false, parse_only = false;
   int gpus = 1;
 };
 
@@ -98,6 +98,7 @@ void usage(FILE* f) {
       "        --gpus <gpus>                        (B200 build) number of GPUs for the pair stage [default: 1]\n"
       "        --vcf-input <vcf-input>              (B200 build) phased diploid VCF instead of --fasta-input (WeightedLD.py reader)\n"
       "        --python-compat                      (B200 build) numeric dialect and output of WeightedLD.py\n"
+      "        --parse-only                         (B200 build) read the input, print its shape and an FNV-1a checksum, exit (no GPU needed)\n"
       "        --min-variability <v>                (B200 build, --python-compat) minimum non-major fraction [default: 0.02]\n",
       f);
 }
@@ -127,6 +128,7 @@ bool parse(int argc, char** argv, Opt& o) {
     }
     if (!std::strcmp(a, "--unweighted")) o.unweighted = true;
     else if (!std::strcmp(a, "--python-compat")) o.python_compat = true;
+    else if (!std::strcmp(a, "--parse-only")) o.parse_only = true;
     else if (is(a, "--fasta-input")) o.fasta_input = need(i, "--fasta-input");
     else if (is(a, "--vcf-input")) o.vcf_input = need(i, "--vcf-input");
     else if (is(a, "--min-variability")) o.min_variability = std::strtod(need(i, "--min-variability"), nullptr);
@@ -147,6 +149,7 @@ bool parse(int argc, char** argv, Opt& o) {
     }
   }
   if (!o.vcf_input.empty() && o.fasta_input.empty()) o.fasta_input = o.vcf_input;  // one of the two is required
+  if (o.parse_only && !o.fasta_input.empty()) return true;
   if (o.fasta_input.empty() || o.pair_output.empty()) {
     std::fprintf(stderr, "error: The following required arguments were not provided:\n%s%s\nUSAGE:\n    weighted_ld [FLAGS] [OPTIONS] --fasta-input <fasta-input> --pair-output <pair-output>\n\nFor more information try --help\n",
                  o.fasta_input.empty() ? "    --fasta-input <fasta-input>\n" : "", o.pair_output.empty() ? "    --pair-output <pair-output>\n" : "");
@@ -161,6 +164,21 @@ int main(int argc, char** argv) {
   Opt opt;
   if (!parse(argc, argv, opt)) return 1;
   try {
+    if (opt.parse_only) {  // host-side ingest only: shape + checksum of the byte matrix (row-major, without pitch padding)
+      const bool is_vcf = !opt.vcf_input.empty();
+      MultiSequence ms = is_vcf ? read_vcf(opt.vcf_input)
+                                : opt.python_compat ? read_fasta_python(opt.fasta_input) : read_fasta(opt.fasta_input);
+      if (ms.ragged) throw Panic("Not all sequences have the same number of symbols");
+      uint64_t h = 1469598103934665603ull;
+      for (int64_t r = 0; r < ms.n_seqs; ++r)
+        for (int64_t c = 0; c < ms.n_cols; ++c) h = (h ^ ms.chars[(size_t)(r * ms.row_stride + c)]) * 1099511628211ull;
+      uint64_t hl = 1469598103934665603ull;
+      for (int64_t v : ms.site_labels)
+        for (int b = 0; b < 8; ++b) hl = (hl ^ (uint8_t)((uint64_t)v >> (8 * b))) * 1099511628211ull;
+      std::printf("%lld %lld %016llx %s %016llx\n", (long long)ms.n_seqs, (long long)ms.n_cols, (unsigned long long)h,
+                  ms.codes ? "codes" : "ascii", (unsigned long long)hl);
+      return 0;
+    }
     std::vector<int> devices;
     for (int g = 0; g < std::max(1, opt.gpus); ++g) devices.push_back(g);
 
