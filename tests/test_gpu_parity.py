@@ -361,3 +361,26 @@ def test_empty_and_degenerate_inputs(wld):
         ctx.henikoff()
         ctx.ld_pairs(0.1, progress.append)
     assert progress[0] == 0 and progress[-1] == k * (k - 1) // 2 and progress == sorted(progress)
+
+
+def test_two_contexts_in_two_threads_are_independent(wld):
+    """A context is not thread-safe, but distinct contexts are independent (include/wld.h): two host threads
+    drive two contexts on the same GPU concurrently and get the single-thread results."""
+    import threading
+    inputs = [synth(600, 3000, seed=s, block=90, clonal=True) for s in (101, 202)]
+    want = [run_gpu_pairs(wld, c, "i8", 0.1)[0].tobytes() for c in inputs]
+    got, errs = [None, None], []
+
+    def work(k):
+        try:
+            for _ in range(3):
+                got[k] = run_gpu_pairs(wld, inputs[k], "i8", 0.1)[0].tobytes()
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs and got == want
