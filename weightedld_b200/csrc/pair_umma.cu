@@ -757,7 +757,11 @@ TilePlan plan_tiles(int64_t L, int n_limbs, int part, int nparts, int sm_count, 
   for (const uint2& t : plan.tiles) {  // pairs a < b inside the tile
     const int64_t i0 = (int64_t)t.x * tile_m, i1 = std::min(L, i0 + tile_m);
     const int64_t j0 = (int64_t)t.y * tile_n, j1 = std::min(L, j0 + tile_n);
-    for (int64_t i = i0; i < i1; ++i) plan.pairs += (uint64_t)std::max<int64_t>(0, j1 - std::max(j0, i + 1));
+    if (i1 <= j0) {  // entirely above the diagonal: every (i, j) of the tile is a pair
+      plan.pairs += (uint64_t)((i1 - i0) * (j1 - j0));
+    } else {
+      for (int64_t i = i0; i < i1; ++i) plan.pairs += (uint64_t)std::max<int64_t>(0, j1 - std::max(j0, i + 1));
+    }
   }
   return plan;
 }
