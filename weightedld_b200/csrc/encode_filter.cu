@@ -88,7 +88,10 @@ __global__ void __launch_bounds__(kHistThreads) hist_vec16_kernel(const uint8_t*
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
 #pragma unroll
-      for (int k = 0; k < 5; ++k) atomicAdd(&s_hist[k][j * 32 + lane], (acc[j] >> (6 * k)) & 63u);
+      for (int k = 0; k < 5; ++k) {
+        const uint32_t f = (acc[j] >> (6 * k)) & 63u;
+        if (f) atomicAdd(&s_hist[k][j * 32 + lane], f);  // most columns hold two or three symbols: skip empty fields
+      }
       acc[j] = 0;
     }
     since_flush = 0;
