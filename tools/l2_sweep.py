@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--strips", default="8,16,24")
     ap.add_argument("--hints", default="nn,fn,nl,fl")
     ap.add_argument("--dies", default="1")
+    ap.add_argument("--wavesync", default="", help="comma list of 0/1 (WLD_WAVESYNC); empty = library default")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
 
@@ -43,9 +44,11 @@ def main():
     dev = torch.from_numpy(chars).cuda()
     names = {"n": "normal", "f": "first", "l": "last"}
     rows = []
-    for strip, hint, die in itertools.product([int(x) for x in args.strips.split(",")], args.hints.split(","),
-                                              args.dies.split(",")):
+    for strip, hint, die, ws in itertools.product([int(x) for x in args.strips.split(",")], args.hints.split(","),
+                                                  args.dies.split(","), args.wavesync.split(",")):
         os.environ["WLD_DIE"] = die
+        if ws:
+            os.environ["WLD_WAVESYNC"] = ws
         os.environ["WLD_STRIP"] = str(strip)
         os.environ["WLD_HINT_A"] = names[hint[0]]
         os.environ["WLD_HINT_B"] = names[hint[1]]
@@ -60,7 +63,7 @@ def main():
                     n, done = ctx.ld_pairs(bench.R2_THRESHOLD)
                     if it >= args.warmup:
                         ms.append(ctx.stage_ms(wld.STAGE_PAIR))
-            row = {"die": int(die), "strip": strip, "hint_a": names[hint[0]], "hint_b": names[hint[1]], "pair_ms": float(np.mean(ms)),
+            row = {"wavesync": ws, "die": int(die), "strip": strip, "hint_a": names[hint[0]], "hint_b": names[hint[1]], "pair_ms": float(np.mean(ms)),
                    "pair_ms_min": float(np.min(ms)), "survivors": n, "pairs": done, "die_schedule": ctx.pair_info().die_schedule,
                    "die_sms": list(ctx.pair_info().die_sms), "clocks": clk.summary()}
         rows.append(row)

@@ -88,6 +88,10 @@ struct UmmaParams {
   int die_pairs[2];
   int die_split;
   int die_mode;               // 1: front/back split of the list; 2: every round of n0+n1 tiles is dealt die 0 first
+  // Long-K runs (a wave's panels are far larger than L2): the CTA pairs of a die start every wave of tiles
+  // together, so that they stream through K in lockstep and share each panel line while it is in L2.
+  int wave_sync;
+  unsigned int* wave_counter; // [2]: tiles whose loads have all been issued, per die; zeroed before the launch
   uint64_t hint_a, hint_b;  // L2 eviction policy of the indicator (streamed) and limb (strip-resident) panels
   const uint2* py_aux; // WLD_COMPAT_PYTHON only (else null): per-site {n5, margin}, see py_flagged
   PairOut out;
@@ -405,8 +409,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = kCtas == 2 ? cluster_ctarank() : 0u;  // rank 0 = leader: issues the MMAs
   int first_tile = (int)(blockIdx.x / kCtas), tile_step = (int)(gridDim.x / kCtas), tile_end = p.n_tiles;
-  int* sched = reinterpret_cast<int*>(smem + kStages * Cfg::kBytes + 8 * (2 * kStages + 4) + 8);  // [3], leader CTA
-  static_assert(8 * (2 * kStages + 4) + 8 + 12 <= 256, "barrier block overflows its 256 bytes");
+  int* sched = reinterpret_cast<int*>(smem + kStages * Cfg::kBytes + 8 * (2 * kStages + 4) + 8);  // [4], leader CTA
+  static_assert(8 * (2 * kStages + 4) + 8 + 16 <= 256, "barrier block overflows its 256 bytes");
   if (p.die_of_sm != nullptr && cta_rank == 0 && threadIdx.x == 96) {  // warp 3 is otherwise idle
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -430,6 +434,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
     }
     sched[1] = step;
     sched[2] = hi;
+    sched[3] = d;
   }
 
   if (warp == 0 && lane == 0) {
@@ -475,7 +480,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = first_tile; t < tile_end; t += tile_step) {
+      const bool wave_sync = p.wave_sync != 0 && p.die_of_sm != nullptr && p.die_mode == 1 && cta_rank == 0;
+      const int my_die = wave_sync ? sched[3] : 0;
+      bool sync_ok = true;
+      unsigned wave = 0;
+      for (int t = first_tile; t < tile_end; t += tile_step, ++wave) {
+        if (wave_sync && sync_ok) {
+          // tiles of all earlier waves of this die have had their loads issued (bounded: if a pair of the die is
+          // missing, synchronisation is abandoned rather than the GPU hung)
+          const unsigned target = wave * (unsigned)tile_step;
+          const long long t0 = clock64();
+          while (*(volatile unsigned int*)&p.wave_counter[my_die] < target) {
+            if (clock64() - t0 > 400000000ll) { sync_ok = false; break; }
+            __nanosleep(32);
+          }
+        }
         const uint2 tile = p.tiles[t];
         const int m_row = (int)tile.x * (kBlockM * kCtas) + (int)cta_rank * kBlockM;
         const int n_row = (int)tile.y * kBlockN + (int)cta_rank * Cfg::kBRows;
@@ -494,6 +513,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
+        if (wave_sync) atomicAdd(&p.wave_counter[my_die], 1u);
       }
     }
     __syncwarp();
@@ -859,6 +879,8 @@ int run_pair_umma(wld_ctx* c, float thr) {
   prm.die_pairs[0] = prm.die_pairs[1] = 0;
   prm.die_split = 0;
   prm.die_mode = 1;
+  prm.wave_sync = 0;
+  prm.wave_counter = reinterpret_cast<unsigned int*>(c->counters.as<unsigned long long>() + 4);
   c->die_used = 0;
   {
     const char* e = std::getenv("WLD_DIE");
@@ -881,6 +903,11 @@ int run_pair_umma(wld_ctx* c, float thr) {
           prm.die_mode = (e && e[0] == '2') ? 2 : 1;
           grid = (n0 + n1) * ctas;
           c->die_used = prm.die_mode;
+          {  // a die-wave of tiles holds (pairs/8 + 8) panels of 256 rows: synchronise waves once that exceeds the L2 half
+            const double wave_bytes = (double)(std::max(n0, n1) / 8 + 8) * 256.0 * (double)gm.k_padded * gm.elem_bytes;
+            const char* ws = std::getenv("WLD_WAVESYNC");
+            prm.wave_sync = ws ? (ws[0] != '0') : (wave_bytes > 60e6);
+          }
           c->info.die_sms[0] = sms[0];
           c->info.die_sms[1] = sms[1];
         }
