@@ -903,10 +903,12 @@ int run_pair_umma(wld_ctx* c, float thr) {
           prm.die_mode = (e && e[0] == '2') ? 2 : 1;
           grid = (n0 + n1) * ctas;
           c->die_used = prm.die_mode;
-          {  // a die-wave of tiles holds (pairs/8 + 8) panels of 256 rows: synchronise waves once that exceeds the L2 half
+          {  // A die-wave of tiles streams (pairs/8 + 8) panels of 256 rows.  Measured on one box each (pair kernel,
+            // same run): config 4 (307 MB per wave) 33.1 -> 29.8 ms and DRAM reads 120 -> 81 GB, config 5 (31 MB)
+            // 88.3 -> 79.7 ms; config 3 (6 MB) 2.56 -> 2.61 ms — so waves are synchronised from 16 MB up.
             const double wave_bytes = (double)(std::max(n0, n1) / 8 + 8) * 256.0 * (double)gm.k_padded * gm.elem_bytes;
             const char* ws = std::getenv("WLD_WAVESYNC");
-            prm.wave_sync = ws ? (ws[0] != '0') : (wave_bytes > 60e6);
+            prm.wave_sync = ws ? (ws[0] != '0') : (wave_bytes > 16e6);
           }
           c->info.die_sms[0] = sms[0];
           c->info.die_sms[1] = sms[1];
