@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define WLD_ABI_VERSION 1
+#define WLD_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define WLD_API __attribute__((visibility("default")))
@@ -66,7 +66,12 @@ enum {
   WLD_INPUT_CODES = 1,   /* bytes are already 0..5 codes (values > 5 are read as 5 = Unknown);
                             the VCF path of WeightedLD.py:311-379 produces these */
   WLD_INPUT_DEVICE = 2   /* `data` is a device pointer on the context's GPU (borrowed until the
-                            next load/destroy); otherwise a host pointer (copied) */
+                            next load/destroy); otherwise a host pointer (copied).  ORDERING: the
+                            buffer is read on the context's stream (wld_set_stream; by default a
+                            private non-blocking stream), which is NOT ordered after the stream that
+                            filled it — either pass that stream with wld_set_stream before loading, or
+                            synchronise it first.  EXTENT: readable for (n_seqs-1)*row_stride + n_cols
+                            bytes; nothing beyond that is touched. */
 };
 
 /* wld_fetch_pairs flags */
@@ -114,10 +119,21 @@ WLD_API int wld_set_stream(wld_ctx* ctx, void* cuda_stream);
  * tile grid (load-balanced, no collective).  Replaces rayon's tile fan-out, lib.rs:635-637. */
 WLD_API int wld_set_partition(wld_ctx* ctx, int part, int nparts);
 
-/* Weight limbs of the exact split-bf16 Gram (1..4, default 3 = 24-bit fixed-point weights;
- * limbs are 8 bits wide, or narrower when n_seqs is so large that fp32 accumulation of 8-bit
- * limbs could round — see DESIGN.md "precision contract"). */
+/* Weight limbs of the exact split Gram: 1..4, or 0 = automatic (the default): 3 limbs (24-bit
+ * mantissa), 4 when some nonzero weight is below 2^-8 of the largest.  Limbs are 8 bits wide, or
+ * narrower when n_seqs is so large that fp32 accumulation of 8-bit limbs could round (bf16 kernel
+ * only) — see DESIGN.md "precision contract". */
 WLD_API int wld_set_limbs(wld_ctx* ctx, int n_limbs);
+/* Block-exponent ("gain") bits G of the fixed-point weights: a weight u = w/max(w) is stored as a
+ * B-bit mantissa m = rint(u * 2^e * (2^B - 1)), e = clamp(-exponent(u), 0, G), and enters every sum
+ * as the integer q = m * 2^(G-e); the power of two rides in the 0/1 indicator operand, so it costs
+ * no tensor work.  Every weight >= 2^-G * max keeps B relative bits, as the reference's f32 weights
+ * do (lib.rs:469-479).  0..7, or -1 = automatic (the default): just enough for the smallest
+ * nonzero weight, lowered if a Gram entry could leave the exact range of the accumulator. */
+WLD_API int wld_set_gain_bits(wld_ctx* ctx, int gain_bits);
+/* Width of one limb: 1..8, or 0 = automatic (the default): 8, lowered only when the fp32 accumulator of
+ * the bf16 kernel could otherwise round (a limb column sum above 2^24, possible from n_seqs > 65 793). */
+WLD_API int wld_set_limb_bits(wld_ctx* ctx, int limb_bits);
 WLD_API int wld_set_pair_kernel(wld_ctx* ctx, int kind);
 /* Numeric dialect.  WLD_COMPAT_RUST (default): the Rust crate, normative for this library.
  * WLD_COMPAT_PYTHON: the reference's WeightedLD.py where the two differ —
@@ -190,6 +206,9 @@ WLD_API int wld_ld_pairs(wld_ctx* ctx, float r2_threshold, wld_progress_fn progr
  * output order (tile rows bottom-up, columns ascending, then a, then b — lib.rs:623-679).
  * flags: WLD_FETCH_*. */
 WLD_API int wld_fetch_pairs(wld_ctx* ctx, wld_pair* out, uint64_t cap, int flags, uint64_t* n_written);
+/* The integer weights q[s] the last wld_ld_pairs summed (exact in a double); the statistics of
+ * lib.rs:482-518 are invariant to their common scale.  For verification against an oracle. */
+WLD_API int wld_get_pair_weights(wld_ctx* ctx, double* out, int64_t cap);
 /* Sort key of the reference's output order for a pair of KEPT indices (for merging shards):
  * lexicographic (key, a, b) ascending == reference order. */
 WLD_API uint64_t wld_pair_order_key(int64_t n_kept, uint32_t kept_a, uint32_t kept_b);
@@ -221,7 +240,12 @@ typedef struct wld_pair_info {
   double executed_flop;    /* 2*M*N*K summed over MMA instructions issued */
   int32_t die_schedule;    /* 0: plain round-robin tile schedule; 1/2: die-aware (SM -> L2 die map measured) */
   int32_t die_sms[2];      /* SMs found on each L2 die (0, 0 when the map could not be established) */
+  int32_t gain_bits;       /* G, see wld_set_gain_bits */
+  int32_t weight_span_log2;/* x: the smallest nonzero weight lies in [2^-(x+1), 2^-x) of the largest */
   int32_t reserved;
+  double weight_rel_err;   /* realised max over nonzero weights of |q/scale - w/max| / (w/max).  A priori:
+                              <= 2^-B when x <= G, else <= 2^(x-G-B).  Every weighted sum of lib.rs:469-479
+                              (all terms >= 0) carries at most this relative error before the f64 epilogue. */
 } wld_pair_info;
 WLD_API int wld_get_pair_info(wld_ctx* ctx, wld_pair_info* out);
 

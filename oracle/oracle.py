@@ -78,6 +78,7 @@ def lib(native: bool = False) -> C.CDLL:
             fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                            i64, C.POINTER(st)]
         L.wldo_quantize_weights.argtypes = [C.c_void_p, i64, C.c_int, C.c_void_p]
+        L.wldo_quantize_weights_gain.argtypes = [C.c_void_p, i64, C.c_int, C.c_int, C.c_void_p]
         L.wldo_triu_index.argtypes = [u64, u64, C.POINTER(u64), C.POINTER(u64)]
         L.wldo_all_pairs.restype = u64
         L.wldo_all_pairs.argtypes = [C.c_void_p, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -221,11 +222,27 @@ def single_weighted_ld_pair(a: np.ndarray, b: np.ndarray, weights: np.ndarray, f
     return (st.r2, st.d, st.d_prime) if ok else None
 
 
-def quantize_weights(w: np.ndarray, bits: int = 24) -> np.ndarray:
+def quantize_weights(w: np.ndarray, bits: int = 24, gain_bits: int = 0) -> np.ndarray:
+    """Integer weights of the B200 pair stage (not in the reference; DESIGN.md "precision contract"):
+    `bits` mantissa bits and `gain_bits` block-exponent bits, as wld_pair_info reports them."""
     w = np.ascontiguousarray(w, np.float32)
     out = np.empty(len(w), np.float64)
-    lib().wldo_quantize_weights(_p(w), len(w), bits, _p(out))
+    if gain_bits:
+        lib().wldo_quantize_weights_gain(_p(w), len(w), bits, gain_bits, _p(out))
+    else:
+        lib().wldo_quantize_weights(_p(w), len(w), bits, _p(out))
     return out
+
+
+def auto_quant_params(w: np.ndarray) -> tuple[int, int]:
+    """(mantissa bits, gain bits) the library picks on its own for these f32 weights when no limb sum
+    overflows (include/wld.h wld_set_limbs / wld_set_gain_bits): all equal -> (0, 0); else x = -exponent of
+    min_nonzero/max, 4 limbs if x > 7 else 3, gain bits min(7, x)."""
+    w = np.asarray(w, np.float32)
+    if w.min() == w.max():
+        return 0, 0
+    x = max(0, -int(np.frexp(np.float64(w[w > 0].min()) / np.float64(w.max()))[1]))
+    return (32 if x > 7 else 24), min(7, x)
 
 
 def all_weighted_ld_pairs(ss: SiteSet, weights: np.ndarray, r2_threshold: float = 0.1,

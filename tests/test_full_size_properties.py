@@ -21,10 +21,11 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def run(wld, chars, weights=None, kernel="i8", ctas=2, partition=None, thr=0.1, codes=False):
+def run(wld, chars, weights=None, kernel="i8", ctas=2, partition=None, thr=0.1, codes=False, gain_bits=-1):
     with wld.Context(0) as ctx:
         ctx.set_pair_kernel(kernel)
         ctx.set_cta_group(ctas)
+        ctx.set_gain_bits(gain_bits)
         if partition:
             ctx.set_partition(*partition)
         ctx.load_alignment(chars, codes=codes)
@@ -35,7 +36,8 @@ def run(wld, chars, weights=None, kernel="i8", ctas=2, partition=None, thr=0.1, 
             ctx.set_weights(weights)
         n, done = ctx.ld_pairs(thr)
         return {"pairs": ctx.fetch_pairs(n), "kept": ctx.fetch_pairs(n, wld.FETCH_KEPT_INDEX), "done": done,
-                "n_kept": n_kept, "w": ctx.weights(), "site_map": ctx.site_map(), "info": ctx.pair_info()}
+                "n_kept": n_kept, "w": ctx.weights(), "site_map": ctx.site_map(), "info": ctx.pair_info(),
+                "wq": ctx.pair_weights()}
 
 
 @pytest.fixture(scope="module")
@@ -68,8 +70,16 @@ def test_config3_full_size_properties(c3, oracle):
     assert len(common) >= 0.999 * len(r)
 
     # every tensor-core variant agrees byte for byte
-    for kernel, ctas in (("i8", 1), ("bf16", 2), ("bf16", 1)):
-        assert run(wld, c3, weights=w, kernel=kernel, ctas=ctas)["pairs"].tobytes() == ref, (kernel, ctas)
+    # (gain bits pinned to what the fp32 accumulator of the bf16 kernel allows: the automatic choice depends on the
+    # accumulator type, and different integer weights are different inputs)
+    vb = run(wld, c3, weights=w, kernel="bf16", ctas=2)
+    g = vb["info"].gain_bits
+    assert g <= base["info"].gain_bits
+    for kernel, ctas in (("i8", 2), ("i8", 1), ("bf16", 1)):
+        v = run(wld, c3, weights=w, kernel=kernel, ctas=ctas, gain_bits=g)
+        assert v["info"].gain_bits == g and np.array_equal(v["wq"], vb["wq"])
+        assert v["pairs"].tobytes() == vb["pairs"].tobytes(), (kernel, ctas)
+    assert run(wld, c3, weights=w, kernel="i8", ctas=1)["pairs"].tobytes() == ref
 
     # union of partitions == whole
     parts = [run(wld, c3, weights=w, partition=(g, 4)) for g in range(4)]
@@ -90,7 +100,8 @@ def test_config3_full_size_properties(c3, oracle):
     assert np.array_equal(rev["pairs"]["r2"][order_rev].view(np.uint32), r["r2"][order_ref].view(np.uint32))
 
     # oracle spot checks on the raw columns (f64 flavour on the same fixed-point weights)
-    wq = oracle.quantize_weights(w, base["info"].weight_bits)
+    wq = oracle.quantize_weights(w, base["info"].weight_bits, base["info"].gain_bits)
+    assert np.array_equal(wq, base["wq"])
     codes = oracle.encode(c3)
     have = {(int(x["site_a"]), int(x["site_b"])): x for x in r}
     sample = r[rng.choice(len(r), 300, replace=False)]
@@ -135,8 +146,11 @@ def test_config5_shape_properties(oracle):
     ref = run(wld, chars, weights=w)["pairs"]
     perm = np.random.default_rng(9).permutation(10_000)
     assert run(wld, np.ascontiguousarray(chars[perm]), weights=w[perm])["pairs"].tobytes() == ref.tobytes()
-    assert run(wld, chars, weights=w, kernel="bf16")["pairs"].tobytes() == ref.tobytes()
-    wq = oracle.quantize_weights(w, 24)
+    vb = run(wld, chars, weights=w, kernel="bf16")
+    v = run(wld, chars, weights=w, kernel="i8", gain_bits=vb["info"].gain_bits)
+    assert np.array_equal(v["wq"], vb["wq"]) and v["pairs"].tobytes() == vb["pairs"].tobytes()
+    wq = oracle.quantize_weights(w, 24, base["info"].gain_bits)
+    assert np.array_equal(wq, base["wq"])
     codes = oracle.encode(chars)
     rng = np.random.default_rng(1)
     for x in ref[rng.choice(len(ref), min(200, len(ref)), replace=False)]:

@@ -82,6 +82,26 @@ def test_stage1_device_input_unaligned_and_codes(wld, oracle):
         assert np.array_equal(ctx.codes(), ref.codes)
 
 
+def test_borrowed_device_buffer_exact_extent_and_stream_order(wld, oracle):
+    """include/wld.h, WLD_INPUT_DEVICE: a borrowed buffer is only readable up to (n_seqs-1)*row_stride + n_cols
+    (the vector kernels must not touch the pitch padding of the LAST row), and a context without an explicit
+    stream adopts the torch stream that produced the tensor (non_blocking H2D copy just before the load)."""
+    import torch
+    n_seqs, n_cols, stride = 513, 1000, 1024  # 16-byte pitch -> vector kernels; n_cols % 16 != 0
+    chars = synth(n_seqs, n_cols, seed=33, block=64)
+    ss = oracle.filter_sites(oracle.siteset_from_chars(chars))
+    host = torch.zeros((n_seqs - 1) * stride + n_cols, dtype=torch.uint8).pin_memory()
+    view = host.as_strided((n_seqs, n_cols), (stride, 1))
+    view.copy_(torch.from_numpy(chars))
+    for _ in range(3):
+        with wld.Context(0) as ctx:  # no set_stream
+            dev = host.to("cuda", non_blocking=True)  # exact extent: the allocation ends with the last row's data
+            ctx.load_alignment(dev.as_strided((n_seqs, n_cols), (stride, 1)))
+            assert ctx.filter_sites() == ss.n_sites
+            assert np.array_equal(ctx.histograms().astype(np.uint64), oracle.siteset_from_chars(chars).hists)
+            assert np.array_equal(ctx.site_map(), ss.site_map) and np.array_equal(ctx.codes(), ss.codes)
+
+
 def test_filter_edge_cases(wld, oracle):
     # all-Unknown, invariant, exact ties at the filter bounds (f32 compares, lib.rs:328-331)
     rows = ["ANAC-A", "ANAC-C", "ANCC-A", "ANCA-C"]
@@ -123,11 +143,13 @@ def test_henikoff_rust_kats(wld, golden):
 
 # ------------------------------------------------------------------------------------------ stage 3
 def run_gpu_pairs(wld, chars, kernel, thr, n_limbs=3, weights=None, partition=None, cap=None, filt=(0.8, 0.02, 0.5),
-                  ctas=2):
+                  ctas=2, gain_bits=-1):
+    """-> (pairs, pairs computed, pair_info, f32 weights, pairs with kept indices, integer weights q)"""
     with wld.Context(0) as ctx:
         ctx.set_pair_kernel(kernel)
         ctx.set_cta_group(ctas)
         ctx.set_limbs(n_limbs)
+        ctx.set_gain_bits(gain_bits)
         if cap:
             ctx.set_pair_capacity(cap)
         if partition:
@@ -139,12 +161,16 @@ def run_gpu_pairs(wld, chars, kernel, thr, n_limbs=3, weights=None, partition=No
         else:
             ctx.set_weights(weights)
         n, done = ctx.ld_pairs(thr)
-        return ctx.fetch_pairs(n), done, ctx.pair_info(), ctx.weights(), ctx.fetch_pairs(n, 1)
+        return ctx.fetch_pairs(n), done, ctx.pair_info(), ctx.weights(), ctx.fetch_pairs(n, 1), ctx.pair_weights()
 
 
-def oracle_pairs(oracle, chars, w32, bits, thr, filt=(0.8, 0.02, 0.5)):
+def oracle_pairs(oracle, chars, w32, info, thr, filt=(0.8, 0.02, 0.5), wq_gpu=None):
+    """f64 restatement of lib.rs:455-521 on the fixed-point weights the library reports it used
+    (mantissa bits + gain bits of wld_pair_info); wq_gpu: the library's own integers, which must be those."""
     fs = oracle.filter_sites(oracle.siteset_from_chars(chars), *filt)
-    wq = oracle.quantize_weights(w32, bits)
+    wq = oracle.quantize_weights(w32, info.weight_bits, info.gain_bits)
+    if wq_gpu is not None:
+        assert np.array_equal(wq, wq_gpu)
     pairs, computed = oracle.all_weighted_ld_pairs(fs, wq, thr, oracle.F64)
     return fs, pairs, computed
 
@@ -157,8 +183,8 @@ PAIR_CASES = [  # n_seqs, n_cols, thr
 @pytest.mark.parametrize("n_seqs,n_cols,thr", PAIR_CASES)
 def test_pairs_simt_bit_exact(wld, oracle, n_seqs, n_cols, thr):
     chars = synth(n_seqs, n_cols, seed=n_seqs + n_cols, block=60, clonal=True)
-    gpu, done, info, w32, _ = run_gpu_pairs(wld, chars, "simt", thr)
-    fs, ref, computed = oracle_pairs(oracle, chars, w32, info.weight_bits, thr)
+    gpu, done, info, w32, _, wq = run_gpu_pairs(wld, chars, "simt", thr)
+    fs, ref, computed = oracle_pairs(oracle, chars, w32, info, thr, wq_gpu=wq)
     assert info.kernel == 1 and info.weight_bits == 24
     assert done == computed == fs.n_sites * (fs.n_sites - 1) // 2
     assert_pairs_identical(gpu, ref)
@@ -170,9 +196,10 @@ def test_pairs_simt_bit_exact(wld, oracle, n_seqs, n_cols, thr):
 @pytest.mark.parametrize("n_seqs,n_cols,thr", PAIR_CASES)
 def test_pairs_umma_bit_exact(wld, oracle, n_seqs, n_cols, thr, n_limbs, kernel, ctas):
     chars = synth(n_seqs, n_cols, seed=n_seqs + n_cols, block=60, clonal=True)
-    gpu, done, info, w32, _ = run_gpu_pairs(wld, chars, kernel, thr, n_limbs=n_limbs, ctas=ctas)
+    gpu, done, info, w32, _, wq = run_gpu_pairs(wld, chars, kernel, thr, n_limbs=n_limbs, ctas=ctas)
     assert info.kernel == {"bf16": 0, "i8": 2}[kernel] and info.n_limbs == n_limbs and info.weight_bits == 8 * n_limbs
-    fs, ref, computed = oracle_pairs(oracle, chars, w32, info.weight_bits, thr)
+    assert 0 <= info.gain_bits <= min(7, info.weight_span_log2)
+    fs, ref, computed = oracle_pairs(oracle, chars, w32, info, thr, wq_gpu=wq)
     assert done == computed
     assert_pairs_identical(gpu, ref)
 
@@ -183,7 +210,7 @@ def test_pairs_close_to_reference_faithful_f32(wld, oracle):
     quantisation), identical pair set except pairs whose r2 is within 2e-5 of the threshold."""
     chars = synth(1200, 800, seed=21, block=60, clonal=True)
     thr = 0.1
-    gpu, _, _, w32, _ = run_gpu_pairs(wld, chars, "umma", thr)
+    gpu, _, _, w32, _, _ = run_gpu_pairs(wld, chars, "umma", thr)
     fs = oracle.filter_sites(oracle.siteset_from_chars(chars))
     ref, _ = oracle.all_weighted_ld_pairs(fs, w32, -1.0, oracle.F32_SCALAR)
     refmap = {(int(p["a"]), int(p["b"])): p for p in ref}
@@ -202,8 +229,10 @@ def test_pairs_close_to_reference_faithful_f32(wld, oracle):
 def test_umma_matches_simt_all_pairs_multi_tile(wld, kernel, ctas):
     # several M and N tiles, ragged edges, K not a multiple of the K block, every pair emitted
     chars = synth(1111, 1900, seed=77, block=100)
-    a = run_gpu_pairs(wld, chars, kernel, -1.0, ctas=ctas)
-    b = run_gpu_pairs(wld, chars, "simt", -1.0)
+    # (same gain bits on both sides: the automatic choice depends on the accumulator of the kernel)
+    a = run_gpu_pairs(wld, chars, kernel, -1.0, ctas=ctas, gain_bits=2)
+    b = run_gpu_pairs(wld, chars, "simt", -1.0, gain_bits=2)
+    assert a[2].gain_bits == b[2].gain_bits == 2 and np.array_equal(a[5], b[5])
     assert a[1] == b[1] and len(a[0]) == len(b[0]) > 500000
     assert a[0].tobytes() == b[0].tobytes()
 
@@ -218,7 +247,7 @@ def test_fp32_accumulation_exact_at_the_limit(wld):
     w[-1] = 0.75
     a = run_gpu_pairs(wld, chars, "umma", -1.0, weights=w)
     b = run_gpu_pairs(wld, chars, "simt", -1.0, weights=w)
-    assert a[2].n_limbs == 3 and a[2].limb_bits == 8
+    assert a[2].n_limbs == 3 and a[2].limb_bits == 8 and a[2].gain_bits == 0 and b[2].gain_bits == 0
     assert len(a[0]) > 1000 and a[0].tobytes() == b[0].tobytes()
     c = run_gpu_pairs(wld, chars, "i8", -1.0, weights=w)  # s32 accumulation: exact with room to spare
     assert c[2].limb_bits == 8 and c[0].tobytes() == b[0].tobytes()
@@ -228,9 +257,9 @@ def test_fp32_accumulation_exact_at_the_limit(wld):
 def test_unweighted_uses_one_limb_and_matches(wld, oracle, kernel):
     chars = synth(500, 400, seed=4, block=50)
     w = np.ones(500, np.float32)  # main.rs:150-153
-    gpu, done, info, _, _ = run_gpu_pairs(wld, chars, kernel, 0.1, weights=w)
-    assert info.n_limbs == 1 and info.weight_bits == 0
-    fs, ref, computed = oracle_pairs(oracle, chars, w, 0, 0.1)
+    gpu, done, info, _, _, wq = run_gpu_pairs(wld, chars, kernel, 0.1, weights=w)
+    assert info.n_limbs == 1 and info.weight_bits == 0 and info.gain_bits == 0 and np.all(wq == 1.0)
+    fs, ref, computed = oracle_pairs(oracle, chars, w, info, 0.1)
     assert done == computed
     assert_pairs_identical(gpu, ref)
 
@@ -259,8 +288,8 @@ def test_overflow_protocol_grows_buffer(wld):
 
 def test_output_order_is_reference_order(wld, oracle):
     chars = synth(64, 1400, seed=12, block=400)  # > 4 reference tiles of 256 per edge
-    gpu, _, info, w32, _ = run_gpu_pairs(wld, chars, "umma", 0.3)
-    fs, ref, _ = oracle_pairs(oracle, chars, w32, info.weight_bits, 0.3)
+    gpu, _, info, w32, _, wq = run_gpu_pairs(wld, chars, "umma", 0.3)
+    fs, ref, _ = oracle_pairs(oracle, chars, w32, info, 0.3, wq_gpu=wq)
     assert fs.n_sites > 1024
     assert_pairs_identical(gpu, ref)  # includes the order (lib.rs:623-679)
 

@@ -264,7 +264,8 @@ def test_cli_vcf_input_rust_dialect(golden, tmp_path, oracle):
     codes = np.ascontiguousarray(golden["t7"]["alleles"][::-1].T)  # site-major, haplotypes reversed like np.rot90
     fs = oracle.filter_sites(oracle.siteset_from_codes(codes), 0.8, 0.0, 0.5)
     w = oracle.henikoff_weights(fs, f64=True)
-    pairs, _ = oracle.all_weighted_ld_pairs(fs, oracle.quantize_weights(w.astype(np.float32), 24), -1.0, oracle.F64)
+    w32 = w.astype(np.float32)
+    pairs, _ = oracle.all_weighted_ld_pairs(fs, oracle.quantize_weights(w32, *oracle.auto_quant_params(w32)), -1.0, oracle.F64)
     pos = golden["t7"]["pos"]
     want = ["site_a\tsite_b\td\td'\tr2"] + [
         f"{pos[p['a']]}\t{pos[p['b']]}\t{oracle.format_f3(p['d'])}\t{oracle.format_f3(p['d_prime'])}\t{oracle.format_f3(p['r2'])}"

@@ -34,7 +34,8 @@ class PairInfo(C.Structure):
     _fields_ = [
         ("kernel", C.c_int32), ("n_limbs", C.c_int32), ("limb_bits", C.c_int32), ("weight_bits", C.c_int32),
         ("k_padded", C.c_int64), ("tiles", C.c_int64), ("tile_sites_m", C.c_int64), ("tile_sites_n", C.c_int64),
-        ("executed_flop", C.c_double), ("die_schedule", C.c_int32), ("die_sms", C.c_int32 * 2), ("reserved", C.c_int32),
+        ("executed_flop", C.c_double), ("die_schedule", C.c_int32), ("die_sms", C.c_int32 * 2), ("gain_bits", C.c_int32),
+        ("weight_span_log2", C.c_int32), ("reserved", C.c_int32), ("weight_rel_err", C.c_double),
     ]
 
 
@@ -54,6 +55,9 @@ SIGNATURES = {
     "wld_set_stream": (_int, [_vp, _vp]),
     "wld_set_partition": (_int, [_vp, _int, _int]),
     "wld_set_limbs": (_int, [_vp, _int]),
+    "wld_set_gain_bits": (_int, [_vp, _int]),
+    "wld_set_limb_bits": (_int, [_vp, _int]),
+    "wld_get_pair_weights": (_int, [_vp, _vp, _i64]),
     "wld_set_pair_kernel": (_int, [_vp, _int]),
     "wld_set_pair_capacity": (_int, [_vp, _u64]),
     "wld_load_alignment": (_int, [_vp, _vp, _i64, _i64, _i64, _int]),

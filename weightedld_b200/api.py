@@ -49,6 +49,7 @@ class Context:
                 self._h = C.c_void_p()
             raise WldError(rc, msg)
         self._keepalive = None
+        self._stream_set = False  # set_stream called by the user: never override it
 
     def close(self):
         if getattr(self, "_h", None):
@@ -73,6 +74,7 @@ class Context:
 
     # ---- options
     def set_stream(self, cuda_stream_ptr: int | None):
+        self._stream_set = True
         self._check(self._lib.wld_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
 
     def set_partition(self, part: int, nparts: int):
@@ -80,6 +82,12 @@ class Context:
 
     def set_limbs(self, n_limbs: int):
         self._check(self._lib.wld_set_limbs(self._h, n_limbs))
+
+    def set_gain_bits(self, gain_bits: int):
+        self._check(self._lib.wld_set_gain_bits(self._h, gain_bits))
+
+    def set_limb_bits(self, limb_bits: int):
+        self._check(self._lib.wld_set_limb_bits(self._h, limb_bits))
 
     def set_pair_kernel(self, kind: int | str):
         if isinstance(kind, str):
@@ -122,6 +130,11 @@ class Context:
                 raise ValueError("alignment tensor must be 2-D uint8 with unit inner stride")
             if t.is_cuda:
                 flags |= L.INPUT_DEVICE
+                if not self._stream_set:
+                    # A borrowed device buffer is read on the context's stream (include/wld.h, WLD_INPUT_DEVICE): run on
+                    # the torch stream that produced the tensor unless the caller chose a stream, so that the kernels are
+                    # ordered after the copy / collective that filled it.
+                    self._check(self._lib.wld_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)))
             self._keepalive = t
             stride = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
             self._check(self._lib.wld_load_alignment(self._h, C.c_void_p(t.data_ptr()), t.shape[0], t.shape[1],
@@ -210,6 +223,12 @@ class Context:
         got = C.c_uint64()
         self._check(self._lib.wld_fetch_pairs(self._h, _ptr(out), len(out), flags, C.byref(got)))
         return out[: got.value]
+
+    def pair_weights(self) -> np.ndarray:
+        """The integer weights q[s] the last pair stage summed (wld_get_pair_weights)."""
+        out = np.empty(self.n_seqs, np.float64)
+        self._check(self._lib.wld_get_pair_weights(self._h, _ptr(out), len(out)))
+        return out
 
     # ---- introspection
     def stage_ms(self, stage: int) -> float:

@@ -57,9 +57,21 @@ struct PairGeom {
   int rows_per_site = 6; // RPS = 2*NL   rows of the limb operand per kept site
   int sites_per_group = 21; // SPG = floor(128 / RPS) kept sites per 128-row group of the limb operand
   int elem_bytes = 2;    // operand element: 2 = bf16, 1 = u8
+  int gain_bits = 0;     // G: block-exponent bits carried by the indicator operand (pair_prep.cu)
   int64_t k_padded = 0;  // sequences rounded up to one K block (64 bf16 / 128 u8)
   int64_t a_rows = 0;    // indicator operand rows, padded to 128 (2 rows per site)
   int64_t b_groups = 0;  // 128-row groups of the limb operand
+};
+
+// What quantize_kernel (pair_prep.cu) decided and measured; read back once per pair stage.
+struct QuantDecision {
+  int32_t flags;       // bit0: invalid weights (negative, NaN, inf, all zero); bit1: all equal; bit2: cannot be made exact
+  int32_t n_limbs, limb_bits, gain_bits;
+  int32_t span_log2;   // x: the smallest nonzero weight lies in [2^-(x+1), 2^-x) of the maximum
+  int32_t pad;
+  double weight_sum;   // sum of q
+  double rel_err;      // max over nonzero weights of |q / (2^G (2^B - 1)) - u| / u  (realised)
+  unsigned long long limb_sums[4];
 };
 
 }  // namespace wld
@@ -75,7 +87,9 @@ struct wld_ctx {
 
   // options
   int part = 0, nparts = 1;
-  int n_limbs_opt = 3;
+  int n_limbs_opt = 0;             // 0 = automatic (3, or 4 for weights spanning more than 2^8)
+  int gain_opt = -1;               // -1 = automatic
+  int limb_bits_opt = 0;           // 0 = automatic (8, narrower only when the fp32 accumulator requires it)
   int pair_kernel = WLD_PAIR_KERNEL_UMMA_I8;  // fastest exact path on sm_100a; bf16 and SIMT selectable
   uint64_t pair_cap_opt = 0;
   int compat = WLD_COMPAT_RUST;    // numeric dialect (wld_set_compat)
@@ -111,7 +125,12 @@ struct wld_ctx {
   // stage 3
   wld::PairGeom geom;
   wld::DevBuf q;                   // f64 [ldc]      fixed-point weights (integers <= 2^32)
-  wld::DevBuf limbs;               // u16 [NL][ldc]  bf16 bit patterns of the limbs
+  wld::DevBuf limbs;               // u16 [4][ldc] limb values, then u8 [4][ldc] the same as bytes
+  wld::DevBuf gain8;               // u8 [ldc]       per-sequence gain 2^(G-e) carried by the indicator operand
+  wld::DevBuf quant;               // QuantDecision (device)
+  wld::QuantDecision* quant_host = nullptr;  // pinned mirror
+  int quant_span_log2 = 0;
+  double quant_rel_err = 0.0;
   wld::DevBuf opA;                 // bf16 [a_rows][k_padded]
   wld::DevBuf opB;                 // bf16 [b_groups*128][k_padded]
   wld::DevBuf tiles;               // uint2 [n_tiles]

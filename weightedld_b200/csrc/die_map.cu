@@ -23,11 +23,15 @@ constexpr int kProbeAddr = 16;
 constexpr int kProbeReps = 3;
 constexpr int kProbeStrideWords = (4096 + 256) / 4;
 
-__global__ void die_probe_kernel(unsigned int* buf, unsigned int* sync, unsigned short* lat, unsigned zero) {
+__global__ void die_probe_kernel(unsigned int* buf, unsigned int* sync, unsigned short* lat, unsigned zero,
+                                 unsigned sm_count) {
   extern __shared__ unsigned char one_block_per_sm[];
   if (threadIdx.x != 0) return;
   unsigned smid;
   asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  // %smid is not guaranteed dense or below multiProcessorCount (floor-swept parts, MIG, green contexts):
+  // such a device gets no map (and the pair kernel its die-unaware schedule) rather than an out-of-bounds write
+  if (smid >= sm_count) { sync[2] = 3; return; }
   // every block resident (hence one per SM) before anyone measures; bounded waits: never hang the GPU
   atomicAdd(&sync[0], 1u);
   long long t0 = clock64();
@@ -78,7 +82,7 @@ bool measure(int sm_count, cudaStream_t stream, std::vector<uint8_t>& out) {
     cudaMemsetAsync(lat, 0, h.size() * 2, stream);
     ok = cudaFuncSetAttribute(die_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess;
     if (ok) {
-      die_probe_kernel<<<sm_count, 32, smem, stream>>>(buf, sync, lat, 0u);
+      die_probe_kernel<<<sm_count, 32, smem, stream>>>(buf, sync, lat, 0u, (unsigned)sm_count);
       ok = cudaMemcpyAsync(h.data(), lat, h.size() * 2, cudaMemcpyDeviceToHost, stream) == cudaSuccess &&
            cudaMemcpyAsync(hs, sync, 16, cudaMemcpyDeviceToHost, stream) == cudaSuccess &&
            cudaStreamSynchronize(stream) == cudaSuccess && hs[2] == 0;

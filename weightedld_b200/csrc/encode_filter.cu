@@ -133,13 +133,13 @@ __global__ void __launch_bounds__(kHistThreads) hist_vec16_kernel(const uint8_t*
 }
 
 // Kernel 1a', generic path for unaligned input: one column per thread, byte loads.
-__global__ void __launch_bounds__(256) hist_generic_kernel(const uint8_t* __restrict__ raw, int64_t n_seqs,
+__global__ void __launch_bounds__(256) hist_generic_kernel(const uint8_t* __restrict__ raw, int64_t row0, int64_t n_seqs,
                                                            int64_t n_cols, int64_t row_stride,
                                                            int rows_per_block, bool ascii,
                                                            uint32_t* __restrict__ hist, int64_t cols_padded) {
   const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= n_cols) return;
-  const int64_t row_begin = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t row_begin = row0 + (int64_t)blockIdx.y * rows_per_block;
   const int64_t row_end = min(row_begin + rows_per_block, n_seqs);
   uint32_t h[5] = {0, 0, 0, 0, 0};
   for (int64_t r = row_begin; r < row_end; ++r) {
@@ -327,8 +327,10 @@ __global__ void __launch_bounds__(kGatherThreads) gather_kernel(const uint8_t* _
   const int64_t col = col_tile + 16 * strip;
   const int64_t seq0 = seq_tile + 4 * rg;
   uint4 r[4];
-  if (aligned16 && seq_tile + 128 <= n_seqs && col_tile + 128 <= row_stride) {
-    // interior tile: bytes between n_cols and the pitch are junk, but those columns are never kept
+  // interior tile: bytes between n_cols and the pitch are junk, but those columns are never kept; the tile that
+  // holds the LAST row only qualifies when it lies inside n_cols (a borrowed buffer ends at that row's n_cols)
+  if (aligned16 && seq_tile + 128 <= n_seqs && col_tile + 128 <= row_stride &&
+      (col_tile + 128 <= n_cols || seq_tile + 128 < n_seqs)) {
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr) r[rr] = __ldg(reinterpret_cast<const uint4*>(raw + (seq0 + rr) * row_stride + col));
   } else {
@@ -406,20 +408,33 @@ int run_histogram(wld_ctx* c, ScopedStageTimer& tm) {
   }
   dim3 grid((unsigned)col_blocks, (unsigned)row_chunks);
   if (vec16) {
-    if (ascii)
-      hist_vec16_kernel<true><<<grid, kHistThreads, 0, c->stream>>>(c->d_raw, c->n_seqs, c->n_cols, c->row_stride,
-                                                                   (int)rows_per_block, c->hist.as<uint32_t>(),
-                                                                   c->cols_padded);
-    else
-      hist_vec16_kernel<false><<<grid, kHistThreads, 0, c->stream>>>(c->d_raw, c->n_seqs, c->n_cols, c->row_stride,
-                                                                    (int)rows_per_block, c->hist.as<uint32_t>(),
-                                                                    c->cols_padded);
+    // The vector path reads whole 16-byte groups up to cols_padded on every row.  A BORROWED buffer only has to
+    // be readable up to (n_seqs-1)*row_stride + n_cols (include/wld.h), so its last row goes through the
+    // byte-wise kernel when n_cols is not a multiple of 16; the library's own copy is padded.
+    const bool tail_row = (c->input_flags & WLD_INPUT_DEVICE) && (c->n_cols % 16 != 0);
+    const int64_t n_fast = tail_row ? c->n_seqs - 1 : c->n_seqs;
+    if (n_fast > 0) {
+      if (ascii)
+        hist_vec16_kernel<true><<<grid, kHistThreads, 0, c->stream>>>(c->d_raw, n_fast, c->n_cols, c->row_stride,
+                                                                     (int)rows_per_block, c->hist.as<uint32_t>(),
+                                                                     c->cols_padded);
+      else
+        hist_vec16_kernel<false><<<grid, kHistThreads, 0, c->stream>>>(c->d_raw, n_fast, c->n_cols, c->row_stride,
+                                                                      (int)rows_per_block, c->hist.as<uint32_t>(),
+                                                                      c->cols_padded);
+      tm.launched();
+    }
+    if (tail_row) {
+      hist_generic_kernel<<<dim3((unsigned)((c->n_cols + 255) / 256), 1), 256, 0, c->stream>>>(
+          c->d_raw, c->n_seqs - 1, c->n_seqs, c->n_cols, c->row_stride, 1, ascii, c->hist.as<uint32_t>(), c->cols_padded);
+      tm.launched();
+    }
   } else {
-    hist_generic_kernel<<<grid, 256, 0, c->stream>>>(c->d_raw, c->n_seqs, c->n_cols, c->row_stride,
+    hist_generic_kernel<<<grid, 256, 0, c->stream>>>(c->d_raw, 0, c->n_seqs, c->n_cols, c->row_stride,
                                                      (int)rows_per_block, ascii, c->hist.as<uint32_t>(),
                                                      c->cols_padded);
+    tm.launched();
   }
-  tm.launched();
   WLD_CUDA(c, cudaGetLastError());
   return WLD_OK;
 }

@@ -30,76 +30,171 @@ __device__ __forceinline__ uint16_t bf16_bits_of_small_int(uint32_t v) {
   return (uint16_t)(__float_as_uint((float)v) >> 16);
 }
 
-// One block.  flags: bit0 = invalid weight seen, bit1 = all weights equal.
-// limb_sums[l] = sum over sequences of limb l (u64) — an upper bound of every Gram entry of that limb.
-__global__ void __launch_bounds__(1024) quantize_kernel(const float* __restrict__ w, int64_t n_seqs, int64_t ldc,
-                                                        int n_limbs, int limb_bits, double* __restrict__ q,
-                                                        uint16_t* __restrict__ limbs, uint8_t* __restrict__ limbs8,
-                                                        unsigned long long* __restrict__ limb_sums,
-                                                        int* __restrict__ flags) {
-  __shared__ float s_red[32], s_min[32];
-  __shared__ unsigned long long s_sum[4][32];
-  __shared__ int s_bad;
+// -------------------------------------------------------------------------------------------------
+// Block-exponent fixed point.  With u = w/max(w) in (0, 1]:
+//     e = clamp(-exponent(u), 0, G)       (u * 2^e in (1/2, 1] unless the clamp at G bites)
+//     m = rint(u * 2^e * (2^B - 1))       B = NL * limb_bits mantissa bits, split into NL limbs
+//     q = m * 2^(G - e)                   the integer weight every kernel of the pair stage sums
+// The factor g = 2^(G - e) <= 128 ("gain") rides in the INDICATOR operand (opA holds g instead of 1), the limbs
+// of m in the limb operand, so the tensor cores still multiply u8 x u8 (or bf16 x bf16) and the Gram entry
+// sum g * limb stays an exact integer.  G extra bits of dynamic range cost no tensor work: every weight
+// down to 2^-G of the maximum keeps B relative bits (24 at NL = 3: what the reference's f32 carries,
+// lib.rs:469-479); below that the relative error grows as 2^-(B+1) / (u * 2^G).
+// The kernel also DECIDES the geometry, so that the host needs one read-back per pair stage:
+//   NL   = caller's choice, or 3, or 4 when some nonzero weight is below 2^-8 of the maximum;
+//   G    = caller's choice, or the smallest value that normalises the smallest nonzero weight (<= 7),
+//          lowered while a limb column sum (an upper bound of every Gram entry) exceeds what the
+//          accumulator holds exactly (s32: 2^31 - 1, fp32: 2^24) or the sum of all q exceeds 2^53;
+//   bits = 8, lowered for the fp32 accumulator of the bf16 kernel if the limit still does not hold at G = 0.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void quant_one(float w, double mx, double scale, int G, unsigned long long& m, int& e) {
+  const double u = __ddiv_rn((double)w, mx);
+  if (!(u > 0.0)) {
+    m = 0;
+    e = G;
+    return;
+  }
+  int ex;
+  (void)frexp(u, &ex);  // u = f * 2^ex, f in [1/2, 1)
+  e = min(G, max(0, -ex));
+  m = (unsigned long long)rint(__dmul_rn(ldexp(u, e), scale));
+}
+
+template <class T, class Op>
+__device__ __forceinline__ T block_reduce_1024(T v, T* s_buf, Op op) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_bad = 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();  // s_buf may still be read from an earlier reduction
+  if (lane == 0) s_buf[warp] = v;
   __syncthreads();
-  float mx = 0.0f, mn = INFINITY;
+  T r = s_buf[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) r = op(r, s_buf[i]);
+  return r;
+}
+
+__global__ void __launch_bounds__(1024) quantize_kernel(const float* __restrict__ w, int64_t n_seqs, int64_t ldc,
+                                                        int nl_opt, int gain_opt, int bits_opt, unsigned long long exact_limit,
+                                                        int may_narrow, double* __restrict__ q,
+                                                        uint16_t* __restrict__ limbs, uint8_t* __restrict__ limbs8,
+                                                        uint8_t* __restrict__ gain8, QuantDecision* __restrict__ out) {
+  __shared__ float s_f[32];
+  __shared__ unsigned long long s_u[32];
+  __shared__ int s_state[4];
+  float mx = 0.0f, mn = INFINITY, mnz = INFINITY;
   int bad = 0;
   for (int64_t s = threadIdx.x; s < n_seqs; s += blockDim.x) {
     const float v = w[s];
     if (!(v >= 0.0f) || isinf(v)) bad = 1;
     mx = fmaxf(mx, v);
     mn = fminf(mn, v);
+    if (v > 0.0f) mnz = fminf(mnz, v);
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-  }
-  if (lane == 0) {
-    s_red[warp] = mx;
-    s_min[warp] = mn;
-  }
-  if (bad) s_bad = 1;
-  __syncthreads();
-  mx = 0.0f;
-  mn = INFINITY;
-  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
-    mx = fmaxf(mx, s_red[i]);
-    mn = fminf(mn, s_min[i]);
-  }
-  if (s_bad || !(mx > 0.0f)) {
-    if (threadIdx.x == 0) *flags = 1;
+  mx = block_reduce_1024(mx, s_f, [](float a, float b) { return fmaxf(a, b); });
+  mn = block_reduce_1024(mn, s_f, [](float a, float b) { return fminf(a, b); });
+  mnz = block_reduce_1024(mnz, s_f, [](float a, float b) { return fminf(a, b); });
+  bad = (int)block_reduce_1024((unsigned long long)bad, s_u, [](unsigned long long a, unsigned long long b) { return a | b; });
+  if (bad || !(mx > 0.0f)) {
+    if (threadIdx.x == 0) {
+      QuantDecision d{};
+      d.flags = 1;
+      *out = d;
+    }
     return;
   }
-  if (threadIdx.x == 0) *flags = (mn == mx) ? 2 : 0;  // bit1: all weights equal
-  const int total_bits = n_limbs * limb_bits;
-  const double scale = total_bits > 0 ? (double)((1ull << total_bits) - 1ull) : 1.0;  // q <= 2^B - 1: limbs fit u8
-  const uint32_t limb_mask = (1u << limb_bits) - 1u;
-  unsigned long long sums[4] = {0, 0, 0, 0};
+  const double mxd = (double)mx;
+  int nl, bits, G, x = 0;
+  const bool all_equal = mn == mx;
+  if (all_equal) {  // e.g. --unweighted (main.rs:150-153): q == 1 for every sequence, one 0-bit limb
+    nl = 1;
+    bits = 0;
+    G = 0;
+  } else {
+    int ex;
+    (void)frexp(__ddiv_rn((double)mnz, mxd), &ex);
+    x = max(0, -ex);
+    nl = nl_opt > 0 ? nl_opt : (x > 7 ? 4 : 3);
+    bits = bits_opt > 0 ? bits_opt : 8;
+    G = gain_opt >= 0 ? min(gain_opt, 7) : min(7, x);
+  }
+  unsigned long long tot[4];
+  int unsupported = 0;
+  for (;;) {
+    const int B = nl * bits;
+    const double scale = B > 0 ? (double)((1ull << B) - 1ull) : 1.0;
+    const uint32_t mask = bits > 0 ? (1u << bits) - 1u : 1u;
+    unsigned long long sums[4] = {0, 0, 0, 0};
+    for (int64_t s = threadIdx.x; s < n_seqs; s += blockDim.x) {
+      unsigned long long m;
+      int e;
+      quant_one(w[s], mxd, scale, G, m, e);
+      const unsigned long long g = 1ull << (G - e);
+      for (int l = 0; l < nl; ++l) sums[l] += g * ((uint32_t)(m >> (bits * (nl - 1 - l))) & mask);
+    }
+    double wsum = 0.0;
+    unsigned long long worst = 0;
+    for (int l = 0; l < 4; ++l) {
+      tot[l] = block_reduce_1024(sums[l], s_u, [](unsigned long long a, unsigned long long b) { return a + b; });
+      if (l < nl) {
+        worst = max(worst, tot[l]);
+        wsum += ldexp((double)tot[l], bits * (nl - 1 - l));
+      }
+    }
+    if (threadIdx.x == 0) {
+      int st = 0;  // 0: accept
+      if (worst > exact_limit || wsum > 9007199254740992.0) {
+        if (G > 0) st = 1;                          // one gain bit less
+        else if (may_narrow && bits > 1) st = 2;    // narrower limbs (fp32 accumulator of the bf16 kernel)
+        else st = 3;                                // cannot be made exact
+      }
+      s_state[0] = st;
+    }
+    __syncthreads();
+    const int st = s_state[0];
+    __syncthreads();
+    if (st == 0) break;
+    if (st == 1) --G;
+    else if (st == 2) --bits;
+    else { unsupported = 1; break; }
+  }
+  const int B = nl * bits;
+  const double scale = B > 0 ? (double)((1ull << B) - 1ull) : 1.0;
+  const uint32_t mask = bits > 0 ? (1u << bits) - 1u : 1u;
+  double err = 0.0;
   for (int64_t s = threadIdx.x; s < ldc; s += blockDim.x) {
-    unsigned long long qi = 0;
-    if (s < n_seqs) qi = (unsigned long long)rint(__dmul_rn(__ddiv_rn((double)w[s], (double)mx), scale));
-    q[s] = (double)qi;
-    for (int l = 0; l < n_limbs; ++l) {
-      const int shift = limb_bits * (n_limbs - 1 - l);
-      uint32_t v = (uint32_t)(qi >> shift) & (limb_bits > 0 ? limb_mask : 1u);
+    unsigned long long m = 0;
+    int e = G;
+    unsigned g = 0;
+    if (s < n_seqs) {
+      quant_one(w[s], mxd, scale, G, m, e);
+      g = 1u << (G - e);
+      const double u = __ddiv_rn((double)w[s], mxd);
+      if (u > 0.0) err = fmax(err, fabs(ldexp((double)m, -e) / scale - u) / u);
+    }
+    q[s] = (double)(m * g);
+    gain8[s] = (uint8_t)g;
+    for (int l = 0; l < nl; ++l) {
+      const uint32_t v = (uint32_t)(m >> (bits * (nl - 1 - l))) & mask;
       limbs[(int64_t)l * ldc + s] = (uint16_t)v;  // raw limb value 0..255; converted at expansion
       limbs8[(int64_t)l * ldc + s] = (uint8_t)v;  // the same as bytes for the u8 operands (SWAR expansion)
-      sums[l] += v;
     }
   }
-  for (int l = 0; l < 4; ++l) {
-    unsigned long long v = sums[l];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) s_sum[l][warp] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < 4) {
-    unsigned long long v = 0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) v += s_sum[threadIdx.x][i];
-    limb_sums[threadIdx.x] = v;
+  const unsigned long long err_bits = block_reduce_1024((unsigned long long)__double_as_longlong(err), s_u,
+                                                        [](unsigned long long a, unsigned long long b) { return max(a, b); });
+  if (threadIdx.x == 0) {
+    QuantDecision d{};
+    d.flags = (all_equal ? 2 : 0) | (unsupported ? 4 : 0);
+    d.n_limbs = nl;
+    d.limb_bits = bits;
+    d.gain_bits = G;
+    d.span_log2 = x;
+    d.weight_sum = 0.0;
+    for (int l = 0; l < nl; ++l) {
+      d.limb_sums[l] = tot[l];
+      d.weight_sum += ldexp((double)tot[l], bits * (nl - 1 - l));
+    }
+    d.rel_err = __longlong_as_double((long long)err_bits);
+    *out = d;
   }
 }
 
@@ -136,19 +231,20 @@ __device__ __forceinline__ void store_select(void* dst, const uint32_t* cw, int 
         make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
   }
 }
-// Indicator rows: the element is the constant 1, so whole words can be built with SWAR compares.
+// Indicator rows: the element is the sequence's gain g = 2^(G - e) (1 when no gain bits are in use), so whole
+// words can be built with SWAR compares: (code == sym ? 0xff : 0) & gain byte.
 template <bool kI8>
-__device__ __forceinline__ void store_indicator(void* dst, const uint32_t* cw, int sym) {
+__device__ __forceinline__ void store_indicator(void* dst, const uint32_t* cw, int sym, const uint32_t* gw) {
   if (kI8) {
     const uint32_t rep = sym < 0 ? 0xffffffffu : (uint32_t)sym * 0x01010101u;  // 0xff never matches a code
     *reinterpret_cast<uint4*>(dst) =
-        make_uint4(__vcmpeq4(cw[0], rep) & 0x01010101u, __vcmpeq4(cw[1], rep) & 0x01010101u,
-                   __vcmpeq4(cw[2], rep) & 0x01010101u, __vcmpeq4(cw[3], rep) & 0x01010101u);
+        make_uint4(__vcmpeq4(cw[0], rep) & gw[0], __vcmpeq4(cw[1], rep) & gw[1],
+                   __vcmpeq4(cw[2], rep) & gw[2], __vcmpeq4(cw[3], rep) & gw[3]);
   } else {
-    uint32_t ones[8];
+    uint32_t g[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) ones[k] = elem_of<false>(1u);
-    store_select<false>(dst, cw, sym, ones);
+    for (int k = 0; k < 8; ++k) g[k] = elem_of<false>((gw[k >> 2] >> (8 * (k & 3))) & 0xffu);  // powers of two: exact in bf16
+    store_select<false>(dst, cw, sym, g);
   }
 }
 __device__ __forceinline__ void store_zero16(void* dst) { *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0); }
@@ -168,7 +264,8 @@ __device__ __forceinline__ void load_codes(const uint8_t* p, uint32_t* cw) {
 template <bool kI8>
 __global__ void __launch_bounds__(256) expand_a_kernel(const uint8_t* __restrict__ codes, int64_t ldc, int64_t n_kept,
                                                        const int8_t* __restrict__ maj, const int8_t* __restrict__ mnr,
-                                                       int64_t kp, uint8_t* __restrict__ opA) {
+                                                       const uint8_t* __restrict__ gain8, int64_t kp,
+                                                       uint8_t* __restrict__ opA) {
   constexpr int ES = kI8 ? 1 : 2;
   constexpr int kSeq = Expand<kI8>::kSeq;
   const int64_t i = blockIdx.y;
@@ -177,10 +274,11 @@ __global__ void __launch_bounds__(256) expand_a_kernel(const uint8_t* __restrict
   uint8_t* r0 = opA + ((2 * i) * kp + s0) * ES;
   uint8_t* r1 = opA + ((2 * i + 1) * kp + s0) * ES;
   if (i < n_kept) {
-    uint32_t cw[Expand<kI8>::kWords];
+    uint32_t cw[Expand<kI8>::kWords], gw[Expand<kI8>::kWords];
     load_codes<kI8>(codes + i * ldc + s0, cw);
-    store_indicator<kI8>(r0, cw, maj[i]);  // maj/min == -1 never matches a code
-    store_indicator<kI8>(r1, cw, mnr[i]);
+    load_codes<kI8>(gain8 + s0, gw);       // gains of the same kSeq sequences (0 in the K padding)
+    store_indicator<kI8>(r0, cw, maj[i], gw);  // maj/min == -1 never matches a code
+    store_indicator<kI8>(r1, cw, mnr[i], gw);
   } else {
     store_zero16(r0);
     store_zero16(r1);
@@ -255,48 +353,40 @@ __global__ void __launch_bounds__(256) expand_b_kernel(const uint8_t* __restrict
 int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm) {
   PairGeom& gm = c->geom;
   const int64_t n = c->n_seqs, L = c->n_kept;
-  gm.n_limbs = c->n_limbs_opt;
   const bool i8 = c->pair_kernel == WLD_PAIR_KERNEL_UMMA_I8;
-  // exact-accumulation limit of a Gram entry: fp32 holds integers up to 2^24, s32 up to 2^31-1
-  const unsigned long long exact_limit = i8 ? ((1ull << 31) - 1) : (1ull << 24);
+  // exact-accumulation limit of a Gram entry: fp32 holds integers up to 2^24, s32 up to 2^31-1; the FP64
+  // verification kernel only needs the sum of all q below 2^53 (checked by the quantiser for every kernel)
+  const unsigned long long exact_limit = c->pair_kernel == WLD_PAIR_KERNEL_SIMT ? (1ull << 53)
+                                         : i8                                   ? ((1ull << 31) - 1)
+                                                                                : (1ull << 24);
 
   WLD_CUDA(c, c->q.ensure(sizeof(double) * (size_t)c->ldc));
   WLD_CUDA(c, c->limbs.ensure((sizeof(uint16_t) + 1) * 4 * (size_t)c->ldc));  // u16 [4][ldc] then u8 [4][ldc]
+  WLD_CUDA(c, c->gain8.ensure((size_t)c->ldc));
+  WLD_CUDA(c, c->quant.ensure(sizeof(QuantDecision)));
   WLD_CUDA(c, c->counters.ensure(sizeof(unsigned long long) * 16));
   WLD_CUDA(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream));
+  if (!c->quant_host) WLD_CUDA(c, cudaMallocHost(&c->quant_host, sizeof(QuantDecision)));
 
-  // All-equal weights (e.g. --unweighted, main.rs:150-153) need a single 0-bit limb: q == 1.
-  // Otherwise start from 8-bit limbs and shrink only if a limb column sum could exceed 2^24.
-  unsigned long long sums[4];
-  int flag = 0;
-  int bits = 8;
-  for (;;) {
-    quantize_kernel<<<1, 1024, 0, c->stream>>>(c->w32.as<float>(), n, c->ldc, gm.n_limbs, bits,
-                                               c->q.as<double>(), c->limbs.as<uint16_t>(),
-                                               c->limbs.as<uint8_t>() + sizeof(uint16_t) * 4 * (size_t)c->ldc,
-                                               c->counters.as<unsigned long long>() + 8,
-                                               reinterpret_cast<int*>(c->counters.as<unsigned long long>() + 12));
-    tm.launched();
-    WLD_CUDA(c, cudaGetLastError());
-    WLD_CUDA(c, cudaMemcpyAsync(sums, c->counters.as<unsigned long long>() + 8, sizeof sums, cudaMemcpyDeviceToHost,
-                                c->stream));
-    WLD_CUDA(c, cudaMemcpyAsync(&flag, c->counters.as<unsigned long long>() + 12, sizeof flag,
-                                cudaMemcpyDeviceToHost, c->stream));
-    WLD_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (flag & 1) return c->fail(WLD_ERR_INVALID, "weights must be finite, >= 0 and not all zero");
-    if ((flag & 2) && !(gm.n_limbs == 1 && bits == 0)) {
-      gm.n_limbs = 1;  // q == 1 for every sequence: one limb, exact for n_seqs <= 2^24
-      bits = 0;
-      continue;
-    }
-    unsigned long long worst = 0;
-    for (int l = 0; l < gm.n_limbs; ++l) worst = std::max(worst, sums[l]);
-    if (worst <= exact_limit) break;
-    if (--bits < 1) return c->fail(WLD_ERR_UNSUPPORTED, "n_seqs too large for exact accumulation");
-  }
-  gm.limb_bits = bits;
-  c->weight_sum = 0.0;
-  for (int l = 0; l < gm.n_limbs; ++l) c->weight_sum += std::ldexp((double)sums[l], bits * (gm.n_limbs - 1 - l));
+  // One launch quantises the weights AND decides limbs / limb width / gain bits; one read-back tells the host.
+  quantize_kernel<<<1, 1024, 0, c->stream>>>(c->w32.as<float>(), n, c->ldc, c->n_limbs_opt, c->gain_opt, c->limb_bits_opt, exact_limit,
+                                             c->pair_kernel == WLD_PAIR_KERNEL_UMMA ? 1 : 0, c->q.as<double>(),
+                                             c->limbs.as<uint16_t>(),
+                                             c->limbs.as<uint8_t>() + sizeof(uint16_t) * 4 * (size_t)c->ldc,
+                                             c->gain8.as<uint8_t>(), c->quant.as<QuantDecision>());
+  tm.launched();
+  WLD_CUDA(c, cudaGetLastError());
+  WLD_CUDA(c, cudaMemcpyAsync(c->quant_host, c->quant.p, sizeof(QuantDecision), cudaMemcpyDeviceToHost, c->stream));
+  WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+  const QuantDecision qd = *c->quant_host;
+  if (qd.flags & 1) return c->fail(WLD_ERR_INVALID, "weights must be finite, >= 0 and not all zero");
+  if (qd.flags & 4) return c->fail(WLD_ERR_UNSUPPORTED, "n_seqs too large for exact accumulation");
+  gm.n_limbs = qd.n_limbs;
+  gm.limb_bits = qd.limb_bits;
+  gm.gain_bits = qd.gain_bits;
+  c->weight_sum = qd.weight_sum;
+  c->quant_span_log2 = qd.span_log2;
+  c->quant_rel_err = qd.rel_err;
   gm.rows_per_site = 2 * gm.n_limbs;
   gm.sites_per_group = 128 / gm.rows_per_site;
   gm.elem_bytes = i8 ? 1 : 2;
@@ -333,7 +423,7 @@ int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm) {
       auto kern = i8 ? expand_a_kernel<true> : expand_a_kernel<false>;
       kern<<<dim3(kblocks, ny), 256, 0, c->stream>>>(
           c->codes.as<uint8_t>() + y0 * c->ldc, c->ldc, std::max<int64_t>(L - y0, 0), c->maj.as<int8_t>() + y0,
-          c->mnr.as<int8_t>() + y0, kp, c->opA.as<uint8_t>() + (size_t)(2 * y0 * kp) * es);
+          c->mnr.as<int8_t>() + y0, c->gain8.as<uint8_t>(), kp, c->opA.as<uint8_t>() + (size_t)(2 * y0 * kp) * es);
       tm.launched();
     }
   }

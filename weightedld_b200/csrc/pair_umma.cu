@@ -84,6 +84,7 @@ struct UmmaParams {
   // to the CTA pairs on die 0, [die_split, n_tiles) to those on die 1; a pair finds its die from %smid and
   // its rank among the die's pairs from die_counter.
   const uint8_t* die_of_sm;
+  unsigned int n_sm;          // entries of die_of_sm
   unsigned int* die_counter;  // [2], zeroed before the launch
   int die_pairs[2];
   int die_split;
@@ -414,8 +415,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
   if (p.die_of_sm != nullptr && cta_rank == 0 && threadIdx.x == 96) {  // warp 3 is otherwise idle
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    const int d = p.die_of_sm[smid] ? 1 : 0;
-    const int k = (int)atomicAdd(&p.die_counter[d], 1u);
+    const bool known = smid < p.n_sm;  // %smid may exceed multiProcessorCount on partitioned devices: no map then
+    const int d = known && p.die_of_sm[smid] ? 1 : 0;
+    const int k = known ? (int)atomicAdd(&p.die_counter[d], 1u) : INT_MAX;
     int lo, hi, step;
     if (p.die_mode == 2) {
       lo = d ? p.die_pairs[0] : 0;
@@ -875,6 +877,7 @@ int run_pair_umma(wld_ctx* c, float thr) {
   // Die-aware schedule: each L2 die works on its own contiguous part of the (strip-rasterised) tile list, so
   // the panels a die's L2 holds are only the ones its own SMs reuse.  WLD_DIE=0 disables (experiments).
   prm.die_of_sm = nullptr;
+  prm.n_sm = 0;
   prm.die_counter = reinterpret_cast<unsigned int*>(c->counters.as<unsigned long long>() + 3);
   prm.die_pairs[0] = prm.die_pairs[1] = 0;
   prm.die_split = 0;
@@ -897,6 +900,7 @@ int run_pair_umma(wld_ctx* c, float thr) {
             WLD_CUDA(c, cudaStreamSynchronize(c->stream));
           }
           prm.die_of_sm = c->die_of_sm.as<uint8_t>();
+          prm.n_sm = (unsigned)dm.size();
           prm.die_pairs[0] = n0;
           prm.die_pairs[1] = n1;
           prm.die_split = (int)((n_tiles * n0 + (n0 + n1) / 2) / (n0 + n1));

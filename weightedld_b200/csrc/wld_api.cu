@@ -59,8 +59,9 @@ void wld_destroy(wld_ctx* c) {
   DevBuf* bufs[] = {&c->raw_own, &c->hist, &c->keep, &c->rank, &c->maj_raw, &c->min_raw, &c->site_map, &c->maj,
                     &c->mnr, &c->kept_count, &c->codes, &c->table, &c->partial, &c->w64, &c->w32, &c->scalars,
                     &c->q, &c->limbs, &c->opA, &c->opB, &c->tiles, &c->pairs, &c->counters, &c->py_aux, &c->die_of_sm,
-                    &c->sorted, &c->sort_keys, &c->sort_idx, &c->sort_temp};
+                    &c->sorted, &c->sort_keys, &c->sort_idx, &c->sort_temp, &c->gain8, &c->quant};
   for (DevBuf* b : bufs) b->release();
+  if (c->quant_host) cudaFreeHost(c->quant_host);
   for (auto& t : c->timers) {
     if (t.beg) cudaEventDestroy(t.beg);
     if (t.end) cudaEventDestroy(t.end);
@@ -89,8 +90,22 @@ int wld_set_partition(wld_ctx* c, int part, int nparts) {
 
 int wld_set_limbs(wld_ctx* c, int n_limbs) {
   WLD_CHECK_CTX(c);
-  if (n_limbs < 1 || n_limbs > 4) return c->fail(WLD_ERR_INVALID, "n_limbs must be 1..4");
+  if (n_limbs < 0 || n_limbs > 4) return c->fail(WLD_ERR_INVALID, "n_limbs must be 1..4, or 0 for automatic");
   c->n_limbs_opt = n_limbs;
+  return WLD_OK;
+}
+
+int wld_set_gain_bits(wld_ctx* c, int gain_bits) {
+  WLD_CHECK_CTX(c);
+  if (gain_bits < -1 || gain_bits > 7) return c->fail(WLD_ERR_INVALID, "gain_bits must be 0..7, or -1 for automatic");
+  c->gain_opt = gain_bits;
+  return WLD_OK;
+}
+
+int wld_set_limb_bits(wld_ctx* c, int limb_bits) {
+  WLD_CHECK_CTX(c);
+  if (limb_bits < 0 || limb_bits > 8) return c->fail(WLD_ERR_INVALID, "limb_bits must be 1..8, or 0 for automatic");
+  c->limb_bits_opt = limb_bits;
   return WLD_OK;
 }
 
@@ -318,9 +333,12 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
     const uint64_t total_pairs = (uint64_t)L * (uint64_t)(L - 1) / 2;
     uint64_t cap = c->pair_cap_opt ? c->pair_cap_opt : std::min<uint64_t>(total_pairs, 1ull << 24);
     cap = std::max<uint64_t>(cap, 1024);
+    // the capacity is what the buffer holds, never a cached number (a failed growth leaves an empty buffer)
+    c->pair_cap = c->pairs.p ? c->pairs.bytes / sizeof(wld_pair) : 0;
     if (c->pair_cap < cap) {
+      c->pair_cap = 0;
       WLD_CUDA(c, c->pairs.ensure(sizeof(wld_pair) * (size_t)cap));
-      c->pair_cap = cap;
+      c->pair_cap = c->pairs.bytes / sizeof(wld_pair);
     }
     if (c->compat == WLD_COMPAT_PYTHON) {
       int rc = run_pair_python_prepare(c);
@@ -372,8 +390,9 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
       }
       // overflow protocol: the count is exact, the buffer was not written past its end -> grow, rerun
       const uint64_t want = cnt[0] + cnt[0] / 16 + 1024;
+      c->pair_cap = 0;
       WLD_CUDA(c, c->pairs.ensure(sizeof(wld_pair) * (size_t)want));
-      c->pair_cap = want;
+      c->pair_cap = c->pairs.bytes / sizeof(wld_pair);
       if (attempt == 2) return c->fail(WLD_ERR_NOMEM, "survivor buffer kept overflowing");
     }
     c->info.kernel = c->pair_kernel;
@@ -382,11 +401,24 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
     c->info.limb_bits = c->geom.limb_bits;
     c->info.weight_bits = c->geom.n_limbs * c->geom.limb_bits;
     c->info.k_padded = c->geom.k_padded;
+    c->info.gain_bits = c->geom.gain_bits;
+    c->info.weight_span_log2 = c->quant_span_log2;
+    c->info.weight_rel_err = c->quant_rel_err;
   }
   if (progress) progress(c->pairs_computed, user);
   if (n_survivors) *n_survivors = c->n_survivors;
   if (pairs_computed) *pairs_computed = c->pairs_computed;
   c->stage = Stage::Paired;
+  return WLD_OK;
+}
+
+int wld_get_pair_weights(wld_ctx* c, double* out, int64_t cap) {
+  WLD_CHECK_CTX(c);
+  if (c->stage < Stage::Paired) return c->fail(WLD_ERR_STATE, "pair weights requested before wld_ld_pairs");
+  if (cap < c->n_seqs || (!out && c->n_seqs)) return c->fail(WLD_ERR_INVALID, "weight buffer too small");
+  if (c->n_kept < 2 || c->n_seqs == 0) return c->fail(WLD_ERR_STATE, "the last pair stage had nothing to compute");
+  WLD_CUDA(c, cudaMemcpyAsync(out, c->q.p, sizeof(double) * (size_t)c->n_seqs, cudaMemcpyDeviceToHost, c->stream));
+  WLD_CUDA(c, cudaStreamSynchronize(c->stream));
   return WLD_OK;
 }
 
