@@ -68,12 +68,17 @@ def peaks() -> dict:
 
 
 def int8_peak() -> dict:
-    """INT8 tensor peak measured on this pool's B200 with tools/measure_peaks.py (cuBLASLt int8 GEMM
-    8192^3 through torch._int_mm, same method as MEASURED_PEAKS.json uses for bf16)."""
-    p = ROOT / "profiles" / "r01_measured_int8_peak.json"
-    d = json.loads(p.read_text())
-    return {"sustained": d["int8_tops_sustained"], "burst": d["int8_tops"],
-            "source": "profiles/r01_measured_int8_peak.json (of measured: torch._int_mm int8 8192^3, tools/measure_peaks.py)"}
+    """INT8 tensor peak.  MEASURED_PEAKS.json holds no INT8 figure, and a library GEMM is no ceiling for
+    tcgen05 kind::i8 (round 1 beat cuBLASLt's by 40 %), so the denominator is the instruction's own issue
+    rate measured on this pool's B200 by tools/tc_peak.cu (operands resident in shared memory, back-to-back
+    cta_group::2 M256 N256 K32 MMAs on all SMs; burst and 4 s sustained under the 1000 W cap), the higher of
+    its two operand patterns.  Falls back to the nominal dense 4.5 POP/s ("of nominal") if the file is absent."""
+    p = ROOT / "profiles" / "r02_tcgen05_peak.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"sustained": d["int8_tops_sustained"], "burst": d["int8_tops"],
+                "source": "profiles/r02_tcgen05_peak.json (of measured: tcgen05.mma kind::i8 issue-rate ceiling, tools/tc_peak.cu)"}
+    return {"sustained": 4500.0, "burst": 4500.0, "source": "nominal dense INT8 4.5 POP/s (of nominal)"}
 
 
 class ClockSampler:
@@ -139,6 +144,9 @@ def cpu_reference(chars: np.ndarray, steps: int, warmup: int, target_s: float):
     from oracle import oracle as O
     O.build(native=True, force=True)  # -O3 -march=native on THIS machine's cores (README.md:88-97 of the reference)
     lib = O.lib(native=True)
+    # every core this process may run on: torchrun exports OMP_NUM_THREADS=1, which must not cap the CPU arm
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib.wldo_set_threads(ncpu)
     threads = lib.wldo_max_threads()
     ss = O.filter_sites(O.siteset_from_chars(chars), *FILTER)
     w = O.henikoff_weights(ss)
@@ -189,6 +197,33 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def check_mgpu_identity(wld, torch, dist, merge_on_device, local, rank, world):
+    """Before any multi-GPU number is believed: on a small side workload the merged N-rank output must be
+    byte-identical to one GPU computing the whole triangle (rank 0 runs that too)."""
+    from weightedld_b200.synth import make_alignment
+    chars = make_alignment(900, 6000, seed=41, block=120, clonal=True)
+    with wld.Context(local) as ctx:
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        ctx.set_partition(rank, world)
+        ctx.load_alignment(chars)
+        ctx.filter_sites(*FILTER)
+        ctx.henikoff()
+        n, _ = ctx.ld_pairs(R2_THRESHOLD)
+        merged = merge_on_device(ctx, n, rank, world)
+    ok = 1
+    if rank == 0:
+        with wld.Context(local) as ctx:
+            ctx.load_alignment(chars)
+            ctx.filter_sites(*FILTER)
+            ctx.henikoff()
+            n1, _ = ctx.ld_pairs(R2_THRESHOLD)
+            whole = ctx.fetch_pairs(n1)
+        ok = int(len(whole) > 1000 and merged.tobytes() == whole.tobytes())
+    t = torch.tensor([ok], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t.item())
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -238,31 +273,45 @@ def run_ours(args):
     state = {}
 
     loader = None
+    pageable_np = chars_np  # ordinary (pageable) host memory, as a Rust Vec<u8> caller holds it
+    from weightedld_b200.multi_gpu import merge_on_device
     if world > 1:
         from weightedld_b200.multi_gpu import ShardedLoader
         loader = ShardedLoader(n_seqs, n_cols, rank, world, torch.device("cuda", local))
 
-    def step(src, fetch: bool, record: bool):
-        if src is host_np and loader is not None:
-            src = loader.load(host)  # this rank's rows H2D + all-gather over NVLink
+    def step(src, fetch: bool, record: bool, pageable: bool = False):
+        """One pass of the hot path.  fetch: the plugin call's result as the reference delivers it — ALL survivors
+        of the job, in PairStore order with parent indices (lib.rs:623-679), in host memory; with N > 1 ranks the
+        shards travel over NVLink to rank 0, which merges, orders and copies them out (multi_gpu.merge_on_device)."""
+        if (src is host_np or src is pageable_np) and loader is not None:
+            src = loader.load(host if src is host_np else torch.from_numpy(pageable_np))  # own rows H2D + all-gather
         ctx.load_alignment(src)
         n_kept = ctx.filter_sites(*FILTER)
         ctx.henikoff()
         n_surv, done = ctx.ld_pairs(R2_THRESHOLD)
-        out = ctx.fetch_pairs(n_surv, wld.FETCH_KEPT_INDEX | wld.FETCH_UNORDERED, out=pinned_out(n_surv)) if fetch else None
+        out = None
+        if fetch:
+            if world == 1:
+                buf = np.empty(n_surv, wld.PAIR_DTYPE) if pageable else pinned_out(n_surv)
+                out = ctx.fetch_pairs(n_surv, wld.FETCH_PARENT_INDEX, out=buf)
+            else:
+                out = merge_on_device(ctx, n_surv, rank, world, out=None if pageable else pinned_out)
         state.update(n_kept=n_kept, n_surv=n_surv, done=done)
+        if fetch:
+            state["order_ms"] = state.get("order_ms", 0.0) + ctx.stage_ms(wld.STAGE_ORDER)
+            state["order_n"] = state.get("order_n", 0) + 1
         if record:
             for i, nm in enumerate(wld.STAGE_NAMES):
                 stages[nm] += ctx.stage_ms(i)
                 launches["n"] += ctx.stage_launches(i)
         return out
 
-    def timed(src, fetch, steps, record):
+    def timed(src, fetch, steps, record, pageable=False):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            step(src, fetch, record)
+            step(src, fetch, record, pageable)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
@@ -278,11 +327,16 @@ def run_ours(args):
         step(dev, False, False)
     with ClockSampler(local) as clocks:
         ms = timed(dev, False, args.steps, True)
+    mgpu_identical = None
     if args.profile:
-        ms_e2e = float('nan')
+        ms_e2e = ms_e2e_pageable = float('nan')
     else:
         step(host_np, True, False)
         ms_e2e = timed(host_np, True, args.steps, False)
+        step(pageable_np, True, False, True)
+        ms_e2e_pageable = timed(pageable_np, True, max(1, args.steps // 2), False, True)
+        if world > 1:
+            mgpu_identical = check_mgpu_identity(wld, torch, dist, merge_on_device, local, rank, world)
 
     n_kept = state["n_kept"]
     total_pairs = n_kept * (n_kept - 1) // 2
@@ -317,10 +371,12 @@ def run_ours(args):
             "tile_schedule": {0: "round-robin", 1: "per-L2-die contiguous halves of the strip-rasterised tile list",
                               2: "per-L2-die, dealt per round"}.get(info.die_schedule, "?"),
             "die_sms": list(info.die_sms)}
+    # DRAM bytes per launch of the pair kernel from an `ncu --set full` capture of THIS workload on THIS number
+    # of GPUs (profiles/pair_umma_traffic.json: {workload: {n_gpus: bytes}}); null when no such capture exists.
     prof = ROOT / "profiles" / "pair_umma_traffic.json"
     if prof.exists():
         try:
-            roof["traffic"] = json.loads(prof.read_text()).get(args.workload)
+            roof["traffic"] = json.loads(prof.read_text()).get(args.workload, {}).get(str(world))
         except Exception:
             pass
 
@@ -351,8 +407,16 @@ def run_ours(args):
             "e2e": {"value": total_pairs / (ms_e2e * 1e-3), "unit": "site-pairs/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(chars_np.nbytes),  # whole job: each rank copies 1/N of the rows
                     "d2h_bytes_per_step": int(20 * surv_all + 64 * world),
+                    "host_buffers": "pinned",
+                    "order_ms": state.get("order_ms", 0.0) / max(state.get("order_n", 1), 1),
+                    "result": "all survivors in the reference's PairStore order with parent indices (wld_fetch_pairs default flags)"
+                              + ("" if world == 1 else "; shards gathered over NVLink and merged on rank 0 inside the timed region"),
+                    "pageable": {"value": total_pairs / (ms_e2e_pageable * 1e-3), "ms_per_step": ms_e2e_pageable,
+                                 "host_buffers": "pageable input and output (what a Rust Vec<u8> / Vec<PairData> caller holds); "
+                                                 "staged through pinned chunks by host threads inside libwld"},
                     "input_distribution": "host buffer -> one GPU" if world == 1 else
                     f"rows sharded over {world} PCIe links + NCCL all-gather over NVLink"},
+            "mgpu_identical": mgpu_identical,
             "gpu_launches": launches["n"],
             "clocks": clocks.summary(),
         }

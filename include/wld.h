@@ -78,7 +78,8 @@ enum {
 enum {
   WLD_FETCH_PARENT_INDEX = 0, /* site_a/site_b are raw alignment columns (lib.rs:662-663) */
   WLD_FETCH_KEPT_INDEX = 1,   /* site_a/site_b index the filtered site set (for merging shards) */
-  WLD_FETCH_UNORDERED = 2     /* skip the sort into the reference's output order */
+  WLD_FETCH_UNORDERED = 2,    /* skip the sort into the reference's output order */
+  WLD_FETCH_DEVICE = 4        /* `out` is a device pointer on the context's GPU (e.g. to hand a shard to NCCL) */
 };
 
 /* pair-kernel selection for wld_set_pair_kernel */
@@ -97,7 +98,8 @@ enum {
   WLD_STAGE_HENIKOFF = 3,
   WLD_STAGE_PAIR_PREP = 4, /* weight quantisation + indicator / limb operand expansion */
   WLD_STAGE_PAIR = 5,      /* Gram + epilogue + compaction kernel(s) */
-  WLD_STAGE_COUNT = 6
+  WLD_STAGE_ORDER = 6,     /* survivors into the reference's output order + parent indices (first fetch after a pair stage) */
+  WLD_STAGE_COUNT = 7
 };
 
 /* Progress callback of all_weighted_ld_pairs (lib.rs:582): receives the number of site pairs
@@ -161,6 +163,12 @@ WLD_API int wld_set_pair_capacity(wld_ctx* ctx, uint64_t pairs);
 WLD_API int wld_load_alignment(wld_ctx* ctx, const uint8_t* data, int64_t n_seqs, int64_t n_cols,
                        int64_t row_stride, int flags);
 
+/* The same for sequences held one by one, as the reference's MultiSequence does (Vec<Sequence>, lib.rs:148-156)
+ * and as a FASTA file lies in memory (rows[r] may point into a mapped file, lib.rs:277-307): n_seqs host
+ * pointers to n_cols bytes each.  The rows are gathered through pinned staging buffers by several host threads
+ * while earlier chunks are already on the bus — no contiguous host copy of the alignment is ever made. */
+WLD_API int wld_load_alignment_rows(wld_ctx* ctx, const uint8_t* const* rows, int64_t n_seqs, int64_t n_cols, int flags);
+
 /* SiteSet::filter_by (lib.rs:230-251) with is_site_of_interest (lib.rs:310-338) and the
  * threshold of main.rs:139: keep a site iff acgt > ceil(f32(min_acgt)*f32(n_seqs)) and a major
  * and a minor symbol exist and min_minor <= minor/(minor+major) <= max_minor (f32).  Builds the
@@ -206,6 +214,20 @@ WLD_API int wld_ld_pairs(wld_ctx* ctx, float r2_threshold, wld_progress_fn progr
  * output order (tile rows bottom-up, columns ascending, then a, then b — lib.rs:623-679).
  * flags: WLD_FETCH_*. */
 WLD_API int wld_fetch_pairs(wld_ctx* ctx, wld_pair* out, uint64_t cap, int flags, uint64_t* n_written);
+/* The same for survivors [first, first+count) of that order: lets a writer (main.rs:82-119) stream the
+ * result in chunks, formatting one while the next is copied.  The ordering runs once per pair stage and
+ * set of flags; every call copies its slice.  Large copies into pageable memory are staged through pinned
+ * buffers by several host threads. */
+WLD_API int wld_fetch_pairs_range(wld_ctx* ctx, uint64_t first, uint64_t count, wld_pair* out, int flags,
+                                  uint64_t* n_written);
+/* Multi-GPU merge (replaces the order-preserving rayon collect of lib.rs:635-679 across devices): adds the
+ * survivors of OTHER partitions — records with KEPT indices, as WLD_FETCH_KEPT_INDEX|WLD_FETCH_UNORDERED
+ * delivers them, in host memory or (src_is_device) on this context's GPU — to this context's own, so that
+ * wld_fetch_pairs returns the union in the reference's order.  The contexts must hold the same site set. */
+WLD_API int wld_append_pairs(wld_ctx* ctx, const wld_pair* src, uint64_t n, int src_is_device);
+/* The same for a host that drives several GPUs from one process: appends the survivors of `other` (another
+ * partition of the same site set, on any GPU of the box) with one peer copy over NVLink. */
+WLD_API int wld_append_pairs_from(wld_ctx* ctx, wld_ctx* other);
 /* The integer weights q[s] the last wld_ld_pairs summed (exact in a double); the statistics of
  * lib.rs:482-518 are invariant to their common scale.  For verification against an oracle. */
 WLD_API int wld_get_pair_weights(wld_ctx* ctx, double* out, int64_t cap);

@@ -10,7 +10,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import weightedld_b200 as wld  # noqa: E402
-from weightedld_b200.multi_gpu import ShardedLoader, gather_pairs  # noqa: E402
+from weightedld_b200.multi_gpu import ShardedLoader, gather_pairs, merge_on_device  # noqa: E402
 from weightedld_b200.synth import make_alignment  # noqa: E402
 
 
@@ -33,9 +33,10 @@ def main():
         n, done = ctx.ld_pairs(0.1)
         shard = ctx.fetch_pairs(n, wld.FETCH_KEPT_INDEX | wld.FETCH_UNORDERED)
         site_map = ctx.site_map()
+        merged_dev = merge_on_device(ctx, n, rank, world)   # shards over NVLink, ordered on rank 0's GPU
     t = torch.tensor([done], device="cuda", dtype=torch.int64)
     dist.all_reduce(t)
-    merged = gather_pairs(shard, n_kept, site_map, rank, world)
+    merged = gather_pairs(shard, n_kept, site_map, rank, world)  # host merge of the same shards
     if rank == 0:
         with wld.Context(local) as ctx:            # the whole triangle on one GPU
             ctx.load_alignment(chars)
@@ -44,7 +45,8 @@ def main():
             n1, done1 = ctx.ld_pairs(0.1)
             whole = ctx.fetch_pairs(n1)
         print(json.dumps({"world": world, "pairs": int(t.item()), "expected": n_kept * (n_kept - 1) // 2, "done1": done1,
-                          "survivors": len(merged), "identical": merged.tobytes() == whole.tobytes()}))
+                          "survivors": len(merged),
+                          "identical": merged.tobytes() == whole.tobytes() and merged_dev.tobytes() == whole.tobytes()}))
     dist.destroy_process_group()
 
 

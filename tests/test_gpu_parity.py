@@ -102,6 +102,27 @@ def test_borrowed_device_buffer_exact_extent_and_stream_order(wld, oracle):
             assert np.array_equal(ctx.site_map(), ss.site_map) and np.array_equal(ctx.codes(), ss.codes)
 
 
+@pytest.mark.parametrize("n_seqs,n_cols", [(3, 5), (700, 1201), (3000, 9000)])
+def test_load_alignment_rows_by_pointer(wld, oracle, n_seqs, n_cols):
+    """wld_load_alignment_rows (the reference's Vec<Sequence>, lib.rs:148-156): rows scattered in host memory
+    (here: slices of a FASTA-like buffer with name lines of varying length in between) give the same site set as
+    the contiguous matrix; the large case goes through the multi-threaded pinned staging."""
+    chars = synth(n_seqs, n_cols, seed=n_seqs, block=64, newline_col=True)
+    blob, offs = bytearray(), []
+    for r in range(n_seqs):
+        blob += b">" + b"s" * (r % 7) + b"\n"
+        offs.append(len(blob))
+        blob += chars[r].tobytes()
+    buf = np.frombuffer(bytes(blob), np.uint8)
+    rows = [buf[o:o + chars.shape[1]] for o in offs]
+    ss = oracle.filter_sites(oracle.siteset_from_chars(chars))
+    with wld.Context(0) as ctx:
+        ctx.load_alignment_rows(rows)
+        assert ctx.filter_sites() == ss.n_sites
+        assert np.array_equal(ctx.site_map(), ss.site_map) and np.array_equal(ctx.codes(), ss.codes)
+        assert np.array_equal(ctx.histograms().astype(np.uint64), oracle.siteset_from_chars(chars).hists)
+
+
 def test_filter_edge_cases(wld, oracle):
     # all-Unknown, invariant, exact ties at the filter bounds (f32 compares, lib.rs:328-331)
     rows = ["ANAC-A", "ANAC-C", "ANCC-A", "ANCA-C"]
@@ -277,6 +298,44 @@ def test_partition_union_equals_whole(wld):
         n_kept = ctx.filter_sites()
     order = np.lexsort((merged["site_b"], merged["site_a"], W.pair_order_key(n_kept, merged["site_a"], merged["site_b"])))
     assert merged[order].tobytes() == whole[4].tobytes()
+
+
+def test_append_pairs_merges_partitions_on_the_device(wld):
+    """wld_append_pairs (multi-GPU merge on rank 0): partition 0's context takes the other partitions' unordered
+    KEPT-index shards — once from host memory, once from device memory — and one ordinary fetch returns the
+    union in the reference's order, byte-identical to the single-GPU run."""
+    import torch
+    chars = synth(500, 2300, seed=55, block=70, clonal=True)
+    whole = run_gpu_pairs(wld, chars, "i8", 0.1)[0]
+    flags = wld.FETCH_KEPT_INDEX | wld.FETCH_UNORDERED
+    for on_device in (False, True):
+        ctxs = []
+        try:
+            shards = []
+            for p in range(3):
+                ctx = wld.Context(0)
+                ctxs.append(ctx)
+                ctx.set_partition(p, 3)
+                ctx.load_alignment(chars)
+                ctx.filter_sites()
+                ctx.henikoff()
+                n, _ = ctx.ld_pairs(0.1)
+                shards.append((ctx, n))
+            root, n0 = shards[0]
+            total = n0
+            for ctx, n in shards[1:]:
+                root.append_pairs(ctx.fetch_pairs_device(n).clone() if on_device else ctx.fetch_pairs(n, flags))
+                total += n
+            merged = root.fetch_pairs(total)
+            assert len(merged) == len(whole) > 1000 and merged.tobytes() == whole.tobytes()
+            # streaming fetch: the concatenation of ranges is the whole result
+            parts = [root.fetch_pairs_range(lo, 777) for lo in range(0, total, 777)]
+            assert np.concatenate(parts).tobytes() == whole.tobytes()
+            assert len(root.fetch_pairs_range(total, 10)) == 0
+        finally:
+            for ctx in ctxs:
+                ctx.close()
+    torch.cuda.synchronize()
 
 
 def test_overflow_protocol_grows_buffer(wld):

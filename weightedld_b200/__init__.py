@@ -4,8 +4,8 @@ encode + site filter -> Henikoff weights -> all-pairs weighted LD (tcgen05 Gram 
 behind the C ABI of include/wld.h (libwld.so).  This package is the thin host-side mirror of the
 reference's Rust API; it has no CPU or PyTorch fallback and raises if libwld.so is missing.
 """
-from ._lib import (FETCH_KEPT_INDEX, FETCH_PARENT_INDEX, FETCH_UNORDERED, PAIR_DTYPE, PAIR_KERNEL_SIMT,
-                   PAIR_KERNEL_UMMA, PAIR_KERNEL_UMMA_I8, STAGE_FILTER, STAGE_HENIKOFF, STAGE_HISTOGRAM, STAGE_LOAD, STAGE_NAMES,
+from ._lib import (FETCH_DEVICE, FETCH_KEPT_INDEX, FETCH_PARENT_INDEX, FETCH_UNORDERED, PAIR_DTYPE, PAIR_KERNEL_SIMT,
+                   PAIR_KERNEL_UMMA, PAIR_KERNEL_UMMA_I8, STAGE_FILTER, STAGE_HENIKOFF, STAGE_HISTOGRAM, STAGE_LOAD, STAGE_NAMES, STAGE_ORDER,
                    STAGE_PAIR, STAGE_PAIR_PREP, WldError)
 from .api import (Context, MultiSequence, PairStore, SiteSet, all_weighted_ld_pairs, format_f3, henikoff_weights,
                   merge_shards, pair_order_key, plan_tiles, read_fasta, single_weighted_ld_pair, write_henikoff_weights, write_pair_stats)

@@ -20,11 +20,11 @@ assert PAIR_DTYPE.itemsize == 20
 
 WLD_OK = 0
 INPUT_ASCII, INPUT_CODES, INPUT_DEVICE = 0, 1, 2
-FETCH_PARENT_INDEX, FETCH_KEPT_INDEX, FETCH_UNORDERED = 0, 1, 2
+FETCH_PARENT_INDEX, FETCH_KEPT_INDEX, FETCH_UNORDERED, FETCH_DEVICE = 0, 1, 2, 4
 PAIR_KERNEL_UMMA, PAIR_KERNEL_SIMT, PAIR_KERNEL_UMMA_I8 = 0, 1, 2
 COMPAT_RUST, COMPAT_PYTHON = 0, 1
-STAGE_LOAD, STAGE_HISTOGRAM, STAGE_FILTER, STAGE_HENIKOFF, STAGE_PAIR_PREP, STAGE_PAIR = range(6)
-STAGE_NAMES = ["load", "histogram", "filter", "henikoff", "pair_prep", "pair"]
+STAGE_LOAD, STAGE_HISTOGRAM, STAGE_FILTER, STAGE_HENIKOFF, STAGE_PAIR_PREP, STAGE_PAIR, STAGE_ORDER = range(7)
+STAGE_NAMES = ["load", "histogram", "filter", "henikoff", "pair_prep", "pair", "order"]
 STATUS_NAMES = {0: "OK", 1: "INVALID", 2: "STATE", 3: "CUDA", 4: "NOMEM", 5: "UNSUPPORTED", 6: "PANIC"}
 
 PROGRESS_FN = C.CFUNCTYPE(None, C.c_uint64, C.c_void_p)
@@ -61,6 +61,7 @@ SIGNATURES = {
     "wld_set_pair_kernel": (_int, [_vp, _int]),
     "wld_set_pair_capacity": (_int, [_vp, _u64]),
     "wld_load_alignment": (_int, [_vp, _vp, _i64, _i64, _i64, _int]),
+    "wld_load_alignment_rows": (_int, [_vp, _vp, _i64, _i64, _int]),
     "wld_filter_sites": (_int, [_vp, C.c_float, C.c_float, C.c_float, C.POINTER(_i64)]),
     "wld_keep_all_sites": (_int, [_vp, C.POINTER(_i64)]),
     "wld_n_seqs": (_i64, [_vp]),
@@ -76,6 +77,9 @@ SIGNATURES = {
     "wld_get_weights_f64": (_int, [_vp, _vp, _i64]),
     "wld_ld_pairs": (_int, [_vp, C.c_float, PROGRESS_FN, _vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "wld_fetch_pairs": (_int, [_vp, _vp, _u64, _int, C.POINTER(_u64)]),
+    "wld_fetch_pairs_range": (_int, [_vp, _u64, _u64, _vp, _int, C.POINTER(_u64)]),
+    "wld_append_pairs": (_int, [_vp, _vp, _u64, _int]),
+    "wld_append_pairs_from": (_int, [_vp, _vp]),
     "wld_pair_order_key": (_u64, [_i64, C.c_uint32, C.c_uint32]),
     "wld_plan_tiles": (_int, [_i64, _int, _int, _int, _int, _int, _vp, _u64, C.POINTER(_u64), C.POINTER(_u64)]),
     "wld_set_cta_group": (_int, [_vp, _int]),

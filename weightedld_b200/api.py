@@ -40,6 +40,7 @@ class Context:
 
     def __init__(self, device: int = 0):
         self._lib = L.load()
+        self._device = device
         self._h = C.c_void_p()
         rc = self._lib.wld_create(device, C.byref(self._h))
         if rc != L.WLD_OK:
@@ -140,6 +141,17 @@ class Context:
             self._check(self._lib.wld_load_alignment(self._h, C.c_void_p(t.data_ptr()), t.shape[0], t.shape[1],
                                                      stride, flags))
 
+    def load_alignment_rows(self, rows, codes: bool = False):
+        """wld_load_alignment_rows: the sequences one by one (a list of equal-length 1-D uint8 arrays, e.g. views
+        into a mapped FASTA file) — gathered by the library, never concatenated on the host."""
+        rows = [np.ascontiguousarray(r, np.uint8) for r in rows]
+        n_cols = len(rows[0]) if rows else 0
+        if any(r.ndim != 1 or len(r) != n_cols for r in rows):
+            raise ValueError("Not all sequences have the same number of symbols")  # lib.rs:181
+        ptrs = (C.c_void_p * max(len(rows), 1))(*[r.ctypes.data for r in rows])
+        self._keepalive = rows
+        self._check(self._lib.wld_load_alignment_rows(self._h, ptrs, len(rows), n_cols, L.INPUT_CODES if codes else L.INPUT_ASCII))
+
     def filter_sites(self, min_acgt: float = 0.8, min_minor: float = 0.02, max_minor: float = 0.5) -> int:
         n = C.c_int64()
         self._check(self._lib.wld_filter_sites(self._h, min_acgt, min_minor, max_minor, C.byref(n)))
@@ -223,6 +235,38 @@ class Context:
         got = C.c_uint64()
         self._check(self._lib.wld_fetch_pairs(self._h, _ptr(out), len(out), flags, C.byref(got)))
         return out[: got.value]
+
+    def fetch_pairs_range(self, first: int, count: int, flags: int = L.FETCH_PARENT_INDEX, out: np.ndarray | None = None) -> np.ndarray:
+        """Survivors [first, first+count) of the (ordered) result: wld_fetch_pairs_range, for streaming writers."""
+        if out is None:
+            out = np.empty(count, PAIR_DTYPE)
+        got = C.c_uint64()
+        self._check(self._lib.wld_fetch_pairs_range(self._h, first, min(count, len(out)), _ptr(out), flags, C.byref(got)))
+        return out[: got.value]
+
+    def fetch_pairs_device(self, n: int, flags: int = L.FETCH_KEPT_INDEX | L.FETCH_UNORDERED):
+        """Survivors as a CUDA uint8 torch tensor of n*20 bytes on this context's GPU (WLD_FETCH_DEVICE), e.g.
+        a shard to hand to NCCL."""
+        import torch
+
+        dev = torch.device("cuda", self._lib_device())
+        t = torch.empty(max(n, 1) * PAIR_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        got = C.c_uint64()
+        self._check(self._lib.wld_fetch_pairs(self._h, C.c_void_p(t.data_ptr()), n, flags | L.FETCH_DEVICE, C.byref(got)))
+        return t[: got.value * PAIR_DTYPE.itemsize]
+
+    def append_pairs(self, shard) -> None:
+        """wld_append_pairs: adds another partition's survivors (KEPT indices) — a PAIR_DTYPE numpy array or a
+        CUDA uint8 torch tensor on this GPU — so that fetch_pairs returns the union in the reference's order."""
+        if isinstance(shard, np.ndarray):
+            shard = np.ascontiguousarray(shard, PAIR_DTYPE)
+            self._check(self._lib.wld_append_pairs(self._h, _ptr(shard), len(shard), 0))
+        else:
+            assert shard.is_cuda and shard.is_contiguous() and shard.numel() % PAIR_DTYPE.itemsize == 0
+            self._check(self._lib.wld_append_pairs(self._h, C.c_void_p(shard.data_ptr()), shard.numel() // PAIR_DTYPE.itemsize, 1))
+
+    def _lib_device(self) -> int:
+        return self._device
 
     def pair_weights(self) -> np.ndarray:
         """The integer weights q[s] the last pair stage summed (wld_get_pair_weights)."""

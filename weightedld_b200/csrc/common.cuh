@@ -138,7 +138,14 @@ struct wld_ctx {
   wld::DevBuf counters;            // u64 [4]: survivors, pairs_done, ...
   wld::DevBuf py_aux;              // uint2 [n_kept] {n5, margin}: WLD_COMPAT_PYTHON only (pair_python.cu)
   wld::DevBuf sorted, sort_keys, sort_idx, sort_temp;  // output ordering scratch (pair_order.cu)
+  int sorted_key = -1;             // what `sorted` currently holds: bit0 ordered, bit1 parent indices; -1 nothing
+  // pinned staging for large copies to / from pageable host memory (wld_api.cu, staged_copy)
+  static constexpr int kMaxStagers = 8;
+  void* stage_buf[kMaxStagers] = {};
+  cudaStream_t stage_stream[kMaxStagers] = {};
+  int n_stagers = 0;
   uint64_t pair_cap = 0;
+  uint64_t auto_cap_budget = 0;    // default survivor capacity (pairs), from the free memory at the first pair stage
   uint64_t n_survivors = 0;
   uint64_t pairs_computed = 0;
   wld_pair_info info{};

@@ -4,8 +4,10 @@
 #include <time.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <new>
+#include <thread>
 
 #include "common.cuh"
 
@@ -15,6 +17,12 @@ namespace {
 #define WLD_CHECK_CTX(c)        \
   if (!(c)) return WLD_ERR_INVALID; \
   cudaSetDevice((c)->device)
+
+bool host_is_pinned(const void* p);
+int staged_copy(wld_ctx* c, void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t row_bytes,
+                size_t rows, cudaMemcpyKind dir, const uint8_t* const* src_rows = nullptr);
+constexpr size_t kStageChunk = 8u << 20;
+constexpr size_t kStagedMin = 16u << 20;  // below this a plain copy is as fast
 
 }  // namespace
 
@@ -62,6 +70,10 @@ void wld_destroy(wld_ctx* c) {
                     &c->sorted, &c->sort_keys, &c->sort_idx, &c->sort_temp, &c->gain8, &c->quant};
   for (DevBuf* b : bufs) b->release();
   if (c->quant_host) cudaFreeHost(c->quant_host);
+  for (int i = 0; i < wld_ctx::kMaxStagers; ++i) {
+    if (c->stage_buf[i]) cudaFreeHost(c->stage_buf[i]);
+    if (c->stage_stream[i]) cudaStreamDestroy(c->stage_stream[i]);
+  }
   for (auto& t : c->timers) {
     if (t.beg) cudaEventDestroy(t.beg);
     if (t.end) cudaEventDestroy(t.end);
@@ -137,11 +149,8 @@ int wld_set_pair_capacity(wld_ctx* c, uint64_t pairs) {
 }
 
 // ---- stage 1 -----------------------------------------------------------------------------------
-int wld_load_alignment(wld_ctx* c, const uint8_t* data, int64_t n_seqs, int64_t n_cols, int64_t row_stride, int flags) {
-  WLD_CHECK_CTX(c);
-  if (n_seqs < 0 || n_cols < 0 || row_stride < n_cols || (!data && n_seqs * n_cols > 0))
-    return c->fail(WLD_ERR_INVALID, "bad alignment shape %lld x %lld (stride %lld)", (long long)n_seqs, (long long)n_cols,
-                   (long long)row_stride);
+static int load_common(wld_ctx* c, const uint8_t* data, const uint8_t* const* rows, int64_t n_seqs, int64_t n_cols,
+                       int64_t row_stride, int flags) {
   if (n_seqs >= (1ll << 31) || n_cols >= (1ll << 31) - 64)
     return c->fail(WLD_ERR_UNSUPPORTED, "alignment dimensions must be below 2^31");
   c->stage = Stage::Created;
@@ -159,7 +168,16 @@ int wld_load_alignment(wld_ctx* c, const uint8_t* data, int64_t n_seqs, int64_t 
       const size_t bytes = (size_t)pitch * (size_t)std::max<int64_t>(n_seqs, 1);
       WLD_CUDA(c, c->raw_own.ensure(bytes));
       if (pitch != n_cols) WLD_CUDA(c, cudaMemsetAsync(c->raw_own.p, 0, bytes, c->stream));
-      if (n_seqs > 0 && n_cols > 0) {
+      const bool big = (size_t)n_seqs * (size_t)n_cols >= kStagedMin && (size_t)n_cols <= kStageChunk;
+      if (n_seqs > 0 && n_cols > 0 && (rows || (big && !host_is_pinned(data)))) {
+        // rows by pointer, or a large pageable source (a Rust Vec<u8>, a numpy array, a mapped file): several host
+        // threads stage it through pinned buffers, each chunk's H2D copy overlapping the others' memcpy
+        if ((size_t)n_cols > kStageChunk) return c->fail(WLD_ERR_UNSUPPORTED, "rows longer than %zu bytes must be passed contiguously", kStageChunk);
+        WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+        const int rc = staged_copy(c, c->raw_own.p, (size_t)pitch, data, (size_t)row_stride, (size_t)n_cols, (size_t)n_seqs,
+                                   cudaMemcpyHostToDevice, rows);
+        if (rc != WLD_OK) return rc;
+      } else if (n_seqs > 0 && n_cols > 0) {
         if (row_stride == pitch)  // same pitch on both sides: one linear copy (a pageable 2-D copy goes row by row)
           WLD_CUDA(c, cudaMemcpyAsync(c->raw_own.p, data, (size_t)(n_seqs - 1) * (size_t)pitch + (size_t)n_cols,
                                       cudaMemcpyHostToDevice, c->stream));
@@ -180,6 +198,23 @@ int wld_load_alignment(wld_ctx* c, const uint8_t* data, int64_t n_seqs, int64_t 
   WLD_CUDA(c, cudaStreamSynchronize(c->stream));
   c->stage = Stage::Loaded;
   return WLD_OK;
+}
+
+int wld_load_alignment(wld_ctx* c, const uint8_t* data, int64_t n_seqs, int64_t n_cols, int64_t row_stride, int flags) {
+  WLD_CHECK_CTX(c);
+  if (n_seqs < 0 || n_cols < 0 || row_stride < n_cols || (!data && n_seqs * n_cols > 0))
+    return c->fail(WLD_ERR_INVALID, "bad alignment shape %lld x %lld (stride %lld)", (long long)n_seqs, (long long)n_cols,
+                   (long long)row_stride);
+  return load_common(c, data, nullptr, n_seqs, n_cols, row_stride, flags);
+}
+
+int wld_load_alignment_rows(wld_ctx* c, const uint8_t* const* rows, int64_t n_seqs, int64_t n_cols, int flags) {
+  WLD_CHECK_CTX(c);
+  if (n_seqs < 0 || n_cols < 0 || (!rows && n_seqs > 0) || (flags & WLD_INPUT_DEVICE))
+    return c->fail(WLD_ERR_INVALID, "bad alignment rows (%lld x %lld); rows must be host pointers", (long long)n_seqs, (long long)n_cols);
+  for (int64_t r = 0; r < n_seqs && n_cols > 0; ++r)
+    if (!rows[r]) return c->fail(WLD_ERR_INVALID, "row %lld is null", (long long)r);
+  return load_common(c, nullptr, rows, n_seqs, n_cols, n_cols, flags);
 }
 
 static int filter_common(wld_ctx* c, int mode, float min_acgt, float min_minor, float max_minor, double py_min_acgt,
@@ -321,6 +356,9 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
   if (progress) progress(0, user);  // lib.rs:584
   c->n_survivors = 0;
   c->pairs_computed = 0;
+  c->sorted_key = -1;
+  c->timers[WLD_STAGE_ORDER].valid = false;
+  c->timers[WLD_STAGE_ORDER].launches = 0;
   c->last_thr = r2_threshold;
   c->info = wld_pair_info{};
   const int64_t L = c->n_kept;
@@ -331,7 +369,18 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
       if (rc != WLD_OK) return rc;
     }
     const uint64_t total_pairs = (uint64_t)L * (uint64_t)(L - 1) / 2;
-    uint64_t cap = c->pair_cap_opt ? c->pair_cap_opt : std::min<uint64_t>(total_pairs, 1ull << 24);
+    uint64_t cap = c->pair_cap_opt;
+    if (!cap) {
+      // Room for EVERY pair when that is cheap (an eighth of the free memory, at most 8 GB = 4.3e8 survivors), so
+      // that high-LD inputs never take the overflow path below (which re-runs the pair kernel); 2^24 otherwise.
+      // (cudaMemGetInfo takes milliseconds on this driver: asked once per context.)
+      if (!c->auto_cap_budget) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
+        c->auto_cap_budget = std::max<uint64_t>(1ull << 24, std::min<uint64_t>(free_b / 8, 8ull << 30) / sizeof(wld_pair));
+      }
+      cap = std::min<uint64_t>(total_pairs, c->auto_cap_budget);
+    }
     cap = std::max<uint64_t>(cap, 1024);
     // the capacity is what the buffer holds, never a cached number (a failed growth leaves an empty buffer)
     c->pair_cap = c->pairs.p ? c->pairs.bytes / sizeof(wld_pair) : 0;
@@ -447,37 +496,180 @@ int wld_plan_tiles(int64_t n_kept, int n_limbs, int cta_group, int part, int npa
   return WLD_OK;
 }
 
-int wld_fetch_pairs(wld_ctx* c, wld_pair* out, uint64_t cap, int flags, uint64_t* n_written) {
+// ---- host <-> device copies of large pageable buffers ------------------------------------------------
+// A cudaMemcpy between device memory and PAGEABLE host memory (a Rust Vec<u8> / Vec<PairData>, a numpy array)
+// is staged by the driver through a small pinned buffer at a fraction of the PCIe rate.  Large copies are
+// therefore cut into chunks and moved by a few host threads, each with its own pinned staging buffer and stream:
+// while one thread's chunk is on the bus, the others memcpy theirs between the staging buffer and the caller's
+// memory.  Buffers that are already pinned (cudaHostAlloc / cudaHostRegister) take one plain async copy.
+}  // extern "C"
+namespace {
+
+bool host_is_pinned(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+int ensure_stagers(wld_ctx* c) {
+  if (c->n_stagers) return WLD_OK;
+  const unsigned hw = std::thread::hardware_concurrency();
+  const int want = (int)std::min<unsigned>(wld_ctx::kMaxStagers, std::max(2u, hw / 4));
+  for (int i = 0; i < want; ++i) {
+    if (cudaMallocHost(&c->stage_buf[i], kStageChunk) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->stage_stream[i], cudaStreamNonBlocking) != cudaSuccess) {
+      cudaGetLastError();
+      if (c->stage_buf[i]) cudaFreeHost(c->stage_buf[i]);
+      c->stage_buf[i] = nullptr;
+      break;
+    }
+    ++c->n_stagers;
+  }
+  return c->n_stagers >= 1 ? WLD_OK : c->fail(WLD_ERR_NOMEM, "cannot allocate pinned staging buffers");
+}
+
+// dir: cudaMemcpyDeviceToHost or cudaMemcpyHostToDevice.  Row form: `rows` rows of `row_bytes`, pitches in bytes
+// (a linear copy is one row).  The context's stream must be idle with respect to the device buffer.
+// src_rows (host -> device only): the source rows by pointer instead of base + pitch.
+int staged_copy(wld_ctx* c, void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t row_bytes,
+                size_t rows, cudaMemcpyKind dir, const uint8_t* const* src_rows) {
+  int rc = ensure_stagers(c);
+  if (rc != WLD_OK) return rc;
+  const bool linear = !src_rows && (rows == 1 || (dst_pitch == row_bytes && src_pitch == row_bytes));
+  // unit of work: a run of whole rows (or a byte range of the single row) of at most kStageChunk bytes
+  const size_t total = linear ? row_bytes * rows : rows;
+  const size_t unit = linear ? kStageChunk : std::max<size_t>(1, kStageChunk / std::max<size_t>(row_bytes, 1));
+  if (!linear && row_bytes > kStageChunk) return c->fail(WLD_ERR_UNSUPPORTED, "row longer than the staging chunk");
+  std::atomic<size_t> next{0};
+  std::atomic<int> failed{0};
+  const int device = c->device;
+  auto worker = [&](int t) {
+    cudaSetDevice(device);
+    uint8_t* stage = static_cast<uint8_t*>(c->stage_buf[t]);
+    cudaStream_t st = c->stage_stream[t];
+    for (;;) {
+      const size_t lo = next.fetch_add(unit);
+      if (lo >= total || failed.load()) break;
+      const size_t cnt = std::min(unit, total - lo);
+      cudaError_t e = cudaSuccess;
+      if (linear) {
+        uint8_t* d = static_cast<uint8_t*>(dst) + lo;
+        const uint8_t* s_ = static_cast<const uint8_t*>(src) + lo;
+        if (dir == cudaMemcpyDeviceToHost) {
+          e = cudaMemcpyAsync(stage, s_, cnt, dir, st);
+          if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+          if (e == cudaSuccess) std::memcpy(d, stage, cnt);
+        } else {
+          std::memcpy(stage, s_, cnt);
+          e = cudaMemcpyAsync(d, stage, cnt, dir, st);
+          if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+      } else {
+        uint8_t* d = static_cast<uint8_t*>(dst) + lo * dst_pitch;
+        const uint8_t* s_ = static_cast<const uint8_t*>(src) + lo * src_pitch;
+        if (dir == cudaMemcpyDeviceToHost) {
+          e = cudaMemcpy2DAsync(stage, row_bytes, s_, src_pitch, row_bytes, cnt, dir, st);
+          if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+          if (e == cudaSuccess)
+            for (size_t r = 0; r < cnt; ++r) std::memcpy(d + r * dst_pitch, stage + r * row_bytes, row_bytes);
+        } else {
+          if (src_rows)
+            for (size_t r = 0; r < cnt; ++r) std::memcpy(stage + r * row_bytes, src_rows[lo + r], row_bytes);
+          else
+            for (size_t r = 0; r < cnt; ++r) std::memcpy(stage + r * row_bytes, s_ + r * src_pitch, row_bytes);
+          e = cudaMemcpy2DAsync(d, dst_pitch, stage, row_bytes, row_bytes, cnt, dir, st);
+          if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+      }
+      if (e != cudaSuccess) failed.store((int)e);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < c->n_stagers; ++t) pool.emplace_back(worker, t);
+  worker(0);
+  for (auto& th : pool) th.join();
+  if (failed.load())
+    return c->fail(WLD_ERR_CUDA, "staged copy failed: %s", cudaGetErrorString((cudaError_t)failed.load()));
+  return WLD_OK;
+}
+
+// device -> caller copy of `bytes` (after the stream's pending work), pageable-aware
+int copy_out(wld_ctx* c, void* out, const void* dev, size_t bytes, bool out_is_device) {
+  if (out_is_device) {
+    WLD_CUDA(c, cudaMemcpyAsync(out, dev, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+    return WLD_OK;
+  }
+  if (bytes < kStagedMin || host_is_pinned(out)) {
+    WLD_CUDA(c, cudaMemcpyAsync(out, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+    WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+    return WLD_OK;
+  }
+  WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+  return staged_copy(c, out, bytes, dev, bytes, bytes, 1, cudaMemcpyDeviceToHost);
+}
+
+// Orders / maps the survivors as `flags` asks (cached until the next pair stage or append) and returns the
+// device buffer that holds them.  *host_fallback is set when the scratch did not fit (caller merges on the host).
+int order_for_fetch(wld_ctx* c, int flags, const wld_pair** dev, bool* host_fallback) {
+  const bool ordered = !(flags & WLD_FETCH_UNORDERED), parent = !(flags & WLD_FETCH_KEPT_INDEX);
+  *host_fallback = false;
+  if (!ordered && !parent) {
+    *dev = c->pairs.as<wld_pair>();
+    return WLD_OK;
+  }
+  const int key = (ordered ? 1 : 0) | (parent ? 2 : 0);
+  if (c->sorted_key != key) {
+    c->sorted_key = -1;
+    const int rc = run_pair_order(c, ordered, parent);
+    if (rc == WLD_ERR_NOMEM) {
+      *host_fallback = true;
+      return WLD_OK;
+    }
+    if (rc != WLD_OK) return rc;
+    c->sorted_key = key;
+  }
+  *dev = c->sorted.as<wld_pair>();
+  return WLD_OK;
+}
+
+}  // namespace
+extern "C" {
+
+int wld_fetch_pairs_range(wld_ctx* c, uint64_t first, uint64_t count, wld_pair* out, int flags, uint64_t* n_written) {
   WLD_CHECK_CTX(c);
   if (c->stage < Stage::Paired) return c->fail(WLD_ERR_STATE, "wld_fetch_pairs before wld_ld_pairs");
   const uint64_t n = c->n_survivors;
   if (n_written) *n_written = 0;
-  if (cap < n) return c->fail(WLD_ERR_INVALID, "pair buffer holds %llu, need %llu", (unsigned long long)cap, (unsigned long long)n);
-  if (n == 0) return WLD_OK;
+  if (first > n) return c->fail(WLD_ERR_INVALID, "range starts at %llu, there are %llu pairs", (unsigned long long)first, (unsigned long long)n);
+  count = std::min<uint64_t>(count, n - first);
+  if (count == 0) return WLD_OK;
+  if (!out) return c->fail(WLD_ERR_INVALID, "null output buffer");
   const bool ordered = !(flags & WLD_FETCH_UNORDERED), parent = !(flags & WLD_FETCH_KEPT_INDEX);
-  if (!ordered && !parent) {  // raw shard: straight device -> caller copy
-    WLD_CUDA(c, cudaMemcpyAsync(out, c->pairs.p, sizeof(wld_pair) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
-    WLD_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (n_written) *n_written = n;
-    return WLD_OK;
+  const bool to_device = (flags & WLD_FETCH_DEVICE) != 0;
+  const wld_pair* dev = nullptr;
+  bool host_fallback = false;
+  int rc = order_for_fetch(c, flags, &dev, &host_fallback);
+  if (rc != WLD_OK) return rc;
+  if (!host_fallback) {
+    rc = copy_out(c, out, dev + first, sizeof(wld_pair) * (size_t)count, to_device);
+    if (rc == WLD_OK && n_written) *n_written = count;
+    return rc;
   }
-  // Order (and map to raw columns) on the device, then one copy straight into the caller's buffer.
-  int rc = run_pair_order(c, ordered, parent);
-  if (rc == WLD_OK) {
-    WLD_CUDA(c, cudaMemcpyAsync(out, c->sorted.p, sizeof(wld_pair) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
-    WLD_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (n_written) *n_written = n;
-    return WLD_OK;
-  }
-  if (rc != WLD_ERR_NOMEM) return rc;
-  // Not enough device memory for the sort scratch: merge on the host (same order, slower).
-  WLD_CUDA(c, cudaMemcpyAsync(out, c->pairs.p, sizeof(wld_pair) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  // Not enough device memory for the ordering scratch: merge on the host (same order, slower; whole set only).
+  if (to_device || first != 0 || count != n)
+    return c->fail(WLD_ERR_NOMEM, "no device memory to order %llu pairs (fetch them whole into host memory)", (unsigned long long)n);
+  rc = copy_out(c, out, c->pairs.p, sizeof(wld_pair) * (size_t)n, false);
+  if (rc != WLD_OK) return rc;
   std::vector<int32_t> smap;
   if (parent) {
     smap.resize((size_t)c->n_kept);
     WLD_CUDA(c, cudaMemcpyAsync(smap.data(), c->site_map.p, sizeof(int32_t) * smap.size(), cudaMemcpyDeviceToHost, c->stream));
+    WLD_CUDA(c, cudaStreamSynchronize(c->stream));
   }
-  WLD_CUDA(c, cudaStreamSynchronize(c->stream));
   if (ordered) {
     const int64_t nk = c->n_kept;
     std::sort(out, out + n, [nk](const wld_pair& x, const wld_pair& y) {
@@ -493,6 +685,82 @@ int wld_fetch_pairs(wld_ctx* c, wld_pair* out, uint64_t cap, int flags, uint64_t
       out[i].site_b = (uint32_t)smap[out[i].site_b];
     }
   if (n_written) *n_written = n;
+  return WLD_OK;
+}
+
+int wld_fetch_pairs(wld_ctx* c, wld_pair* out, uint64_t cap, int flags, uint64_t* n_written) {
+  WLD_CHECK_CTX(c);
+  if (c->stage < Stage::Paired) return c->fail(WLD_ERR_STATE, "wld_fetch_pairs before wld_ld_pairs");
+  if (n_written) *n_written = 0;
+  if (cap < c->n_survivors)
+    return c->fail(WLD_ERR_INVALID, "pair buffer holds %llu, need %llu", (unsigned long long)cap, (unsigned long long)c->n_survivors);
+  return wld_fetch_pairs_range(c, 0, c->n_survivors, out, flags, n_written);
+}
+
+int wld_append_pairs(wld_ctx* c, const wld_pair* src, uint64_t n, int src_is_device) {
+  WLD_CHECK_CTX(c);
+  if (c->stage < Stage::Paired) return c->fail(WLD_ERR_STATE, "wld_append_pairs before wld_ld_pairs");
+  if (n == 0) return WLD_OK;
+  if (!src) return c->fail(WLD_ERR_INVALID, "null shard");
+  const uint64_t have = c->n_survivors, want = have + n;
+  const uint64_t cap = c->pairs.p ? c->pairs.bytes / sizeof(wld_pair) : 0;
+  if (cap < want) {  // grow, keeping this context's own survivors
+    DevBuf bigger;
+    WLD_CUDA(c, bigger.ensure(sizeof(wld_pair) * (size_t)(want + want / 8)));
+    if (have) WLD_CUDA(c, cudaMemcpyAsync(bigger.p, c->pairs.p, sizeof(wld_pair) * (size_t)have, cudaMemcpyDeviceToDevice, c->stream));
+    WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->pairs.release();
+    c->pairs = bigger;
+    c->pair_cap = c->pairs.bytes / sizeof(wld_pair);
+  }
+  wld_pair* dst = c->pairs.as<wld_pair>() + have;
+  if (src_is_device) {
+    WLD_CUDA(c, cudaMemcpyAsync(dst, src, sizeof(wld_pair) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+    WLD_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller may release or reuse `src` on return
+  } else if (sizeof(wld_pair) * n < kStagedMin || host_is_pinned(src)) {
+    WLD_CUDA(c, cudaMemcpyAsync(dst, src, sizeof(wld_pair) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+  } else {
+    WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+    const int rc = staged_copy(c, dst, sizeof(wld_pair) * (size_t)n, src, sizeof(wld_pair) * (size_t)n,
+                               sizeof(wld_pair) * (size_t)n, 1, cudaMemcpyHostToDevice);
+    if (rc != WLD_OK) return rc;
+  }
+  c->n_survivors = want;
+  c->sorted_key = -1;
+  return WLD_OK;
+}
+
+int wld_append_pairs_from(wld_ctx* c, wld_ctx* other) {
+  WLD_CHECK_CTX(c);
+  if (!other || other == c) return c->fail(WLD_ERR_INVALID, "wld_append_pairs_from needs another context");
+  if (c->stage < Stage::Paired || other->stage < Stage::Paired)
+    return c->fail(WLD_ERR_STATE, "wld_append_pairs_from before wld_ld_pairs on both contexts");
+  if (c->n_kept != other->n_kept || c->n_seqs != other->n_seqs)
+    return c->fail(WLD_ERR_INVALID, "the contexts hold different site sets");
+  const uint64_t n = other->n_survivors;
+  if (n == 0) return WLD_OK;
+  cudaSetDevice(other->device);
+  cudaError_t e = cudaStreamSynchronize(other->stream);  // its survivors are complete
+  cudaSetDevice(c->device);
+  if (e != cudaSuccess) return c->fail(WLD_ERR_CUDA, "peer context failed: %s", cudaGetErrorString(e));
+  const uint64_t have = c->n_survivors, want = have + n;
+  const uint64_t cap = c->pairs.p ? c->pairs.bytes / sizeof(wld_pair) : 0;
+  if (cap < want) {
+    DevBuf bigger;
+    WLD_CUDA(c, bigger.ensure(sizeof(wld_pair) * (size_t)(want + want / 8)));
+    if (have) WLD_CUDA(c, cudaMemcpyAsync(bigger.p, c->pairs.p, sizeof(wld_pair) * (size_t)have, cudaMemcpyDeviceToDevice, c->stream));
+    WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->pairs.release();
+    c->pairs = bigger;
+    c->pair_cap = c->pairs.bytes / sizeof(wld_pair);
+  }
+  // NVLink / PCIe peer copy (the runtime stages through the host when peer access is not available)
+  WLD_CUDA(c, cudaMemcpyPeerAsync(c->pairs.as<wld_pair>() + have, c->device, other->pairs.p, other->device,
+                                  sizeof(wld_pair) * (size_t)n, c->stream));
+  WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->n_survivors = want;
+  c->sorted_key = -1;
   return WLD_OK;
 }
 

@@ -170,8 +170,10 @@ int main(int argc, char** argv) {
                                 : opt.python_compat ? read_fasta_python(opt.fasta_input) : read_fasta(opt.fasta_input);
       if (ms.ragged) throw Panic("Not all sequences have the same number of symbols");
       uint64_t h = 1469598103934665603ull;
-      for (int64_t r = 0; r < ms.n_seqs; ++r)
-        for (int64_t c = 0; c < ms.n_cols; ++c) h = (h ^ ms.chars[(size_t)(r * ms.row_stride + c)]) * 1099511628211ull;
+      for (int64_t r = 0; r < ms.n_seqs; ++r) {
+        const uint8_t* row = ms.row(r);
+        for (int64_t c = 0; c < ms.n_cols; ++c) h = (h ^ row[c]) * 1099511628211ull;
+      }
       uint64_t hl = 1469598103934665603ull;
       for (int64_t v : ms.site_labels)
         for (int b = 0; b < 8; ++b) hl = (hl ^ (uint8_t)((uint64_t)v >> (8 * b))) * 1099511628211ull;
@@ -181,6 +183,13 @@ int main(int argc, char** argv) {
     }
     std::vector<int> devices;
     for (int g = 0; g < std::max(1, opt.gpus); ++g) devices.push_back(g);
+    // The CUDA driver initialises every GPU it can see (about 0.2 s each on an 8-GPU box): show it only the ones
+    // this run uses, unless the caller already chose.
+    if (!std::getenv("CUDA_VISIBLE_DEVICES")) {
+      std::string vis;
+      for (int g : devices) vis += (vis.empty() ? "" : ",") + std::to_string(g);
+      setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 0);
+    }
 
     auto sw = Clock::now();
     // CUDA initialisation takes seconds and is independent of the input: do it while the file is read

@@ -36,65 +36,6 @@ void parallel_for(size_t n, size_t min_chunk, F&& f) {
 }
 }  // namespace
 
-// ---------------------------------------------------------------------------------------------
-// read_fasta, lib.rs:277-307.  Line-oriented: '>' lines are names; EVERY other line is one whole
-// sequence INCLUDING its '\n' (lib.rs:297), so an alignment of L bases has L+1 columns, the last
-// being Unknown.  A final line without '\n' is one column short -> ragged -> panic in from_multiseq.
-// The file is mmap'ed and the rows are copied by all host threads into a 16-byte-pitched buffer.
-// ---------------------------------------------------------------------------------------------
-MultiSequence read_fasta(const std::string& path) {
-  MultiSequence ms;
-  ms.source = path;
-  int fd = ::open(path.c_str(), O_RDONLY);
-  if (fd < 0) throw std::ios_base::failure(std::string(std::strerror(errno)) + " (os error " + std::to_string(errno) + ")");
-  struct stat st;
-  if (fstat(fd, &st) != 0) { ::close(fd); throw std::ios_base::failure("fstat failed"); }
-  const size_t size = (size_t)st.st_size;
-  if (size == 0) { ::close(fd); return ms; }
-  const char* data = (const char*)mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
-  ::close(fd);
-  if (data == MAP_FAILED) throw std::ios_base::failure("mmap failed");
-  madvise((void*)data, size, MADV_SEQUENTIAL);
-
-  std::vector<std::pair<size_t, size_t>> rows;  // (offset, length incl. newline)
-  std::string pending;
-  bool have_name = false;
-  size_t pos = 0;
-  while (pos < size) {
-    const char* nl = (const char*)memchr(data + pos, '\n', size - pos);
-    const size_t end = nl ? (size_t)(nl - data) + 1 : size;
-    if (data[pos] == '>') {
-      pending.assign(data + pos + 1, end - pos - 1);  // lib.rs:294-295 keeps the newline in the name
-      have_name = true;
-    } else {
-      rows.emplace_back(pos, end - pos);
-      ms.names.push_back(have_name ? pending : std::string());
-      have_name = false;
-    }
-    pos = end;
-  }
-  ms.n_seqs = (int64_t)rows.size();
-  if (!rows.empty()) {
-    ms.n_cols = (int64_t)rows[0].second;
-    for (auto& r : rows)
-      if ((int64_t)r.second != ms.n_cols) ms.ragged = true;
-    if (!ms.ragged) {
-      ms.row_stride = (ms.n_cols + 15) / 16 * 16;
-      ms.chars.resize((size_t)ms.row_stride * rows.size());
-      parallel_for(rows.size(), 256, [&](size_t a, size_t b) {
-        for (size_t i = a; i < b; ++i) {
-          uint8_t* dst = ms.chars.data() + i * (size_t)ms.row_stride;
-          memcpy(dst, data + rows[i].first, (size_t)ms.n_cols);
-          memset(dst + ms.n_cols, 0, (size_t)(ms.row_stride - ms.n_cols));
-        }
-      });
-    }
-  }
-  munmap((void*)data, size);
-  return ms;
-}
-
-namespace {
 struct MappedFile {
   const char* data = nullptr;
   size_t size = 0;
@@ -108,12 +49,81 @@ struct MappedFile {
       void* p = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
       if (p == MAP_FAILED) { ::close(fd); throw std::ios_base::failure("mmap failed"); }
       data = (const char*)p;
+      madvise(p, size, MADV_WILLNEED);
     }
     ::close(fd);
   }
+  MappedFile(const MappedFile&) = delete;
   ~MappedFile() { if (data) munmap((void*)data, size); }
 };
-}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// read_fasta, lib.rs:277-307.  Line-oriented: '>' lines are names; EVERY other line is one whole
+// sequence INCLUDING its '\n' (lib.rs:297), so an alignment of L bases has L+1 columns, the last
+// being Unknown.  A final line without '\n' is one column short -> ragged -> panic in from_multiseq.
+// The file is mapped, all host threads look for the line ends of their share of it, and the sequences
+// are NOT copied: MultiSequence::rows points into the mapping, from where the library's staging threads
+// gather them on their way to the GPU (wld_load_alignment_rows).
+// ---------------------------------------------------------------------------------------------
+MultiSequence read_fasta(const std::string& path) {
+  MultiSequence ms;
+  ms.source = path;
+  auto map = std::make_shared<MappedFile>(path);
+  const char* data = map->data;
+  const size_t size = map->size;
+  if (size == 0) return ms;
+
+  // line ends, found in parallel: thread t scans [size*t/T, size*(t+1)/T)
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const size_t nthr = std::max<size_t>(1, std::min<size_t>(hw, size / (4u << 20)));
+  std::vector<std::vector<size_t>> found(nthr);
+  {
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nthr; ++t)
+      th.emplace_back([&, t] {
+        size_t pos = size * t / nthr;
+        const size_t end = size * (t + 1) / nthr;
+        auto& v = found[t];
+        while (pos < end) {
+          const char* nl = (const char*)memchr(data + pos, '\n', end - pos);
+          if (!nl) break;
+          v.push_back((size_t)(nl - data));
+          pos = (size_t)(nl - data) + 1;
+        }
+      });
+    for (auto& x : th) x.join();
+  }
+  size_t n_nl = 0;
+  for (auto& v : found) n_nl += v.size();
+  std::vector<size_t> starts;  // start offset of every line; starts[k+1] - starts[k] = its length incl. '\n'
+  starts.reserve(n_nl + 2);
+  starts.push_back(0);
+  for (auto& v : found)
+    for (size_t e : v) starts.push_back(e + 1);
+  if (starts.back() != size) starts.push_back(size);  // last line has no terminator
+  const size_t n_lines = starts.size() - 1;
+
+  ms.rows.reserve(n_lines / 2 + 1);
+  const char* pending = nullptr;
+  size_t pending_len = 0;
+  for (size_t k = 0; k < n_lines; ++k) {
+    const size_t pos = starts[k], len = starts[k + 1] - pos;
+    if (data[pos] == '>') {
+      pending = data + pos + 1;  // lib.rs:294-295 keeps the newline in the name
+      pending_len = len - 1;
+    } else {
+      if (ms.rows.empty()) ms.n_cols = (int64_t)len;
+      else if ((int64_t)len != ms.n_cols) ms.ragged = true;
+      ms.rows.push_back((const uint8_t*)data + pos);
+      ms.names.emplace_back(pending ? std::string(pending, pending_len) : std::string());
+      pending = nullptr;
+    }
+  }
+  ms.n_seqs = (int64_t)ms.rows.size();
+  ms.row_stride = ms.n_cols;
+  ms.mapping = std::move(map);
+  return ms;
+}
 
 // ---------------------------------------------------------------------------------------------
 // read_fasta_python, WeightedLD.py:21-41 through Bio.AlignIO.read(.., "fasta"): a record is a '>'
@@ -321,8 +331,10 @@ SiteSet SiteSet::from_multiseq(const MultiSequence& ms, std::shared_ptr<Impl> op
       wld_ctx* c = s.impl->ctx[(size_t)g];
       int rc = wld_set_partition(c, g, n);
       if (rc == WLD_OK)
-        rc = wld_load_alignment(c, ms.chars.data(), ms.n_seqs, ms.n_cols, ms.row_stride,
-                                ms.codes ? WLD_INPUT_CODES : WLD_INPUT_ASCII);
+        rc = !ms.rows.empty()
+                 ? wld_load_alignment_rows(c, ms.rows.data(), ms.n_seqs, ms.n_cols, ms.codes ? WLD_INPUT_CODES : WLD_INPUT_ASCII)
+                 : wld_load_alignment(c, ms.chars.data(), ms.n_seqs, ms.n_cols, ms.row_stride,
+                                      ms.codes ? WLD_INPUT_CODES : WLD_INPUT_ASCII);
       if (rc != WLD_OK) errs[(size_t)g] = wld_last_error(c);
     });
   for (auto& t : th) t.join();
@@ -408,8 +420,7 @@ PairStore all_weighted_ld_pairs(const SiteSet& site_set, const std::vector<float
     for (auto d : u->sh->done) total += d;
     if (total > 0 && *u->sh->cb) (*u->sh->cb)((size_t)total);
   };
-  std::vector<PairVec> parts((size_t)n);
-  std::vector<uint64_t> computed((size_t)n, 0);
+  std::vector<uint64_t> computed((size_t)n, 0), survivors((size_t)n, 0);
   std::vector<std::string> errs((size_t)n);
   std::vector<User> users;
   for (int g = 0; g < n; ++g) users.push_back(User{&shared, g});
@@ -417,43 +428,72 @@ PairStore all_weighted_ld_pairs(const SiteSet& site_set, const std::vector<float
   for (int g = 0; g < n; ++g)
     th.emplace_back([&, g] {
       wld_ctx* c = ctxs[(size_t)g];
-      uint64_t ns = 0, nc = 0, got = 0;
+      uint64_t ns = 0, nc = 0;
       int rc = wld_set_weights(c, weights.data(), (int64_t)weights.size());
       if (rc == WLD_OK) rc = wld_ld_pairs(c, thr, +tramp, &users[(size_t)g], &ns, &nc);
-      if (rc == WLD_OK) {
-        parts[(size_t)g].resize((size_t)ns);
-        rc = wld_fetch_pairs(c, parts[(size_t)g].data(), ns, n > 1 ? WLD_FETCH_KEPT_INDEX : WLD_FETCH_PARENT_INDEX, &got);
-      }
       if (rc != WLD_OK) errs[(size_t)g] = wld_last_error(c);
       computed[(size_t)g] = nc;
+      survivors[(size_t)g] = ns;
     });
   for (auto& t : th) t.join();
   for (auto& e : errs)
     if (!e.empty()) throw WldError(WLD_ERR_CUDA, e);
   PairStore store;
   for (auto v : computed) store.pairs_computed += v;
-  if (n == 1) {
-    store.pairs.swap(parts[0]);
-    return store;
+  // Merge (the order-preserving rayon collect of lib.rs:635-679, across devices): the other GPUs' survivors
+  // travel to GPU 0 by peer copy and are ordered there together with its own when the store is read.
+  store.n_ = survivors[0];
+  for (int g = 1; g < n; ++g) {
+    check(ctxs[0], wld_append_pairs_from(ctxs[0], ctxs[(size_t)g]));
+    store.n_ += survivors[(size_t)g];
   }
-  // host merge of the per-GPU shards (each already in reference order) by (tile key, a, b)
-  const int64_t n_kept = wld_n_kept(ctxs[0]);
-  const std::vector<int64_t> smap = site_set.site_map();
-  size_t total = 0;
-  for (auto& p : parts) total += p.size();
-  store.pairs.reserve(total);
-  for (auto& p : parts) store.pairs.insert(store.pairs.end(), p.begin(), p.end());
-  std::sort(store.pairs.begin(), store.pairs.end(), [&](const wld_pair& x, const wld_pair& y) {
-    const uint64_t kx = wld_pair_order_key(n_kept, x.site_a, x.site_b), ky = wld_pair_order_key(n_kept, y.site_a, y.site_b);
-    if (kx != ky) return kx < ky;
-    if (x.site_a != y.site_a) return x.site_a < y.site_a;
-    return x.site_b < y.site_b;
-  });
-  for (auto& p : store.pairs) {
-    p.site_a = (uint32_t)smap[p.site_a];
-    p.site_b = (uint32_t)smap[p.site_b];
-  }
+  store.root_ = ctxs[0];
+  store.keep_ = site_set.impl;
   return store;
+}
+
+const PairVec& PairStore::pairs() const {
+  if (!cached_) {
+    cache_.resize((size_t)n_);
+    uint64_t got = 0;
+    if (n_) check(root_, wld_fetch_pairs(root_, cache_.data(), n_, WLD_FETCH_PARENT_INDEX, &got));
+    cached_ = true;
+  }
+  return cache_;
+}
+
+void PairStore::for_each_chunk(size_t chunk_pairs, const std::function<void(const wld_pair*, size_t, size_t)>& fn) const {
+  if (cached_ || n_ <= chunk_pairs) {  // small: one fetch
+    const PairVec& all = pairs();
+    if (!all.empty()) fn(all.data(), 0, all.size());
+    return;
+  }
+  PairVec buf[2];
+  buf[0].resize(chunk_pairs);
+  buf[1].resize(chunk_pairs);
+  auto fetch = [&](int which, size_t first) -> size_t {
+    uint64_t got = 0;
+    check(root_, wld_fetch_pairs_range(root_, first, chunk_pairs, buf[which].data(), WLD_FETCH_PARENT_INDEX, &got));
+    return (size_t)got;
+  };
+  size_t first = 0, have = fetch(0, 0);
+  int cur = 0;
+  while (have) {
+    const size_t next_first = first + have;
+    size_t next_have = 0;
+    std::exception_ptr err;
+    std::thread prefetch;
+    if (next_first < n_)
+      prefetch = std::thread([&] {
+        try { next_have = fetch(cur ^ 1, next_first); } catch (...) { err = std::current_exception(); }
+      });
+    fn(buf[cur].data(), first, have);
+    if (prefetch.joinable()) prefetch.join();
+    if (err) std::rethrow_exception(err);
+    first = next_first;
+    have = next_have;
+    cur ^= 1;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -542,79 +582,121 @@ std::string format_py4(double v) {
   return out;
 }
 
+namespace {
+// Formats `n` records with `fmt_line` on all host threads and writes the pieces IN ORDER at `*file_pos`:
+// every thread formats a contiguous run into its own buffer, the run lengths give each buffer its file
+// offset, and the threads pwrite() their buffers concurrently (page-cache copies scale with threads).
+template <class LineFn>
+void write_records_parallel(int fd, off_t* file_pos, const wld_pair* recs, size_t n, LineFn&& fmt_line) {
+  if (n == 0) return;
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const size_t nthr = std::max<size_t>(1, std::min<size_t>(hw, n / 4096));
+  std::vector<std::string> out(nthr);
+  auto format = [&](size_t t) {
+    const size_t lo = n * t / nthr, hi = n * (t + 1) / nthr;
+    std::string& s = out[t];
+    s.reserve((hi - lo) * 44);
+    char line[192];
+    for (size_t i = lo; i < hi; ++i) s.append(line, (size_t)fmt_line(recs[i], line));
+  };
+  auto run = [&](auto&& f) {
+    if (nthr == 1) { f(0); return; }
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nthr; ++t) th.emplace_back([&, t] { f(t); });
+    for (auto& x : th) x.join();
+  };
+  run(format);
+  std::vector<off_t> at(nthr);
+  off_t pos = *file_pos;
+  for (size_t t = 0; t < nthr; ++t) {
+    at[t] = pos;
+    pos += (off_t)out[t].size();
+  }
+  std::vector<int> errs(nthr, 0);
+  run([&](size_t t) {
+    const char* p = out[t].data();
+    size_t left = out[t].size();
+    off_t o = at[t];
+    while (left) {
+      const ssize_t w = ::pwrite(fd, p, left, o);
+      if (w < 0) { if (errno == EINTR) continue; errs[t] = errno; return; }
+      p += w; left -= (size_t)w; o += w;
+    }
+  });
+  for (int e : errs)
+    if (e) throw std::ios_base::failure(std::string(std::strerror(e)) + " (os error " + std::to_string(e) + ")");
+  *file_pos = pos;
+}
+
+int open_out(const std::string& path) {
+  const int fd = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+  if (fd < 0) throw std::ios_base::failure(std::string(std::strerror(errno)) + " (os error " + std::to_string(errno) + ")");
+  return fd;
+}
+void write_header(int fd, off_t* pos, const char* text) {
+  const size_t n = std::strlen(text);
+  if (::pwrite(fd, text, n, *pos) != (ssize_t)n) { const int e = errno; ::close(fd); throw std::ios_base::failure(std::string(std::strerror(e))); }
+  *pos += (off_t)n;
+}
+}  // namespace
+
 void write_pair_stats_python(const std::string& path, const PairStore& store, const std::vector<int64_t>& labels) {
-  FILE* f = path == "-" ? stdout : std::fopen(path.c_str(), "w");
-  if (!f) throw std::ios_base::failure(std::string(std::strerror(errno)) + " (os error " + std::to_string(errno) + ")");
-  std::fputs("posa\tposb\tD\tD'\tR2\n", f);
   // WeightedLD.py:177-179 prints in plain row-major order of the upper triangle
-  PairVec sorted = store.pairs;
+  PairVec sorted = store.pairs();
   std::sort(sorted.begin(), sorted.end(), [](const wld_pair& x, const wld_pair& y) {
     return x.site_a != y.site_a ? x.site_a < y.site_a : x.site_b < y.site_b;
   });
-  const size_t n = sorted.size(), chunk = 1 << 14;
-  for (size_t base = 0; base < n; base += chunk * 64) {
-    const size_t hi = std::min(n, base + chunk * 64);
-    const size_t nchunks = (hi - base + chunk - 1) / chunk;
-    std::vector<std::string> out(nchunks);
-    parallel_for(nchunks, 1, [&](size_t a, size_t b) {
-      for (size_t ci = a; ci < b; ++ci) {
-        std::string& s = out[ci];
-        const size_t lo = base + ci * chunk, up = std::min(hi, lo + chunk);
-        for (size_t i = lo; i < up; ++i) {
-          const wld_pair& p = sorted[i];
-          const long long la = labels.empty() ? (long long)p.site_a : (long long)labels[p.site_a];
-          const long long lb = labels.empty() ? (long long)p.site_b : (long long)labels[p.site_b];
-          s += std::to_string(la) + "\t" + std::to_string(lb) + "\t" + format_py4((double)p.d) + "\t" +
-               format_py4((double)p.d_prime) + "\t" + format_py4((double)p.r2) + "\n";
-        }
-      }
-    });
-    for (auto& s : out) std::fwrite(s.data(), 1, s.size(), f);
+  auto line = [&](const wld_pair& p, char* buf) {
+    const long long la = labels.empty() ? (long long)p.site_a : (long long)labels[p.site_a];
+    const long long lb = labels.empty() ? (long long)p.site_b : (long long)labels[p.site_b];
+    return std::snprintf(buf, 192, "%lld\t%lld\t%s\t%s\t%s\n", la, lb, format_py4((double)p.d).c_str(),
+                         format_py4((double)p.d_prime).c_str(), format_py4((double)p.r2).c_str());
+  };
+  if (path == "-") {
+    std::fputs("posa\tposb\tD\tD'\tR2\n", stdout);
+    char buf[192];
+    for (const wld_pair& p : sorted) std::fwrite(buf, 1, (size_t)line(p, buf), stdout);
+    std::fflush(stdout);
+    return;
   }
-  if (f != stdout) std::fclose(f);
-  else std::fflush(f);
+  const int fd = open_out(path);
+  off_t pos = 0;
+  write_header(fd, &pos, "posa\tposb\tD\tD'\tR2\n");
+  try {
+    write_records_parallel(fd, &pos, sorted.data(), sorted.size(), line);
+  } catch (...) { ::close(fd); throw; }
+  ::close(fd);
 }
 
 void write_pair_stats(const std::string& path, const PairStore& store, const std::vector<int64_t>& labels) {
-  FILE* f = std::fopen(path.c_str(), "w");
-  if (!f) throw std::ios_base::failure(std::string(std::strerror(errno)) + " (os error " + std::to_string(errno) + ")");
-  std::fputs("site_a\tsite_b\td\td'\tr2\n", f);
-  // format in parallel chunks, write in order
-  const size_t n = store.pairs.size(), chunk = 1 << 16;
-  for (size_t base = 0; base < n; base += chunk * 64) {
-    const size_t hi = std::min(n, base + chunk * 64);
-    const size_t nchunks = (hi - base + chunk - 1) / chunk;
-    std::vector<std::string> out(nchunks);
-    parallel_for(nchunks, 1, [&](size_t a, size_t b) {
-      char line[160];
-      for (size_t ci = a; ci < b; ++ci) {
-        std::string& s = out[ci];
-        const size_t lo = base + ci * chunk, up = std::min(hi, lo + chunk);
-        s.reserve((up - lo) * 40);
-        for (size_t i = lo; i < up; ++i) {
-          const wld_pair& p = store.pairs[i];
-          int k = 0;
-          if (labels.empty()) {
-            k += fmt_u64(p.site_a, line + k);
-            line[k++] = '\t';
-            k += fmt_u64(p.site_b, line + k);
-            line[k++] = '\t';
-          } else {
-            k = std::sprintf(line, "%lld\t%lld\t", (long long)labels[p.site_a], (long long)labels[p.site_b]);
-          }
-          k += fmt_f3(p.d, line + k);
-          line[k++] = '\t';
-          k += fmt_f3(p.d_prime, line + k);
-          line[k++] = '\t';
-          k += fmt_f3(p.r2, line + k);
-          line[k++] = '\n';
-          s.append(line, (size_t)k);
-        }
-      }
+  const int fd = open_out(path);
+  off_t pos = 0;
+  write_header(fd, &pos, "site_a\tsite_b\td\td'\tr2\n");
+  auto line = [&](const wld_pair& p, char* buf) {
+    int k = 0;
+    if (labels.empty()) {
+      k += fmt_u64(p.site_a, buf + k);
+      buf[k++] = '\t';
+      k += fmt_u64(p.site_b, buf + k);
+      buf[k++] = '\t';
+    } else {
+      k = std::sprintf(buf, "%lld\t%lld\t", (long long)labels[p.site_a], (long long)labels[p.site_b]);
+    }
+    k += fmt_f3(p.d, buf + k);
+    buf[k++] = '\t';
+    k += fmt_f3(p.d_prime, buf + k);
+    buf[k++] = '\t';
+    k += fmt_f3(p.r2, buf + k);
+    buf[k++] = '\n';
+    return k;
+  };
+  try {
+    // streamed: the next chunk is fetched from the device while this one is formatted and written
+    store.for_each_chunk((size_t)4 << 20, [&](const wld_pair* recs, size_t, size_t count) {
+      write_records_parallel(fd, &pos, recs, count, line);
     });
-    for (auto& s : out) std::fwrite(s.data(), 1, s.size(), f);
-  }
-  std::fclose(f);
+  } catch (...) { ::close(fd); throw; }
+  ::close(fd);
 }
 
 }  // namespace weighted_ld

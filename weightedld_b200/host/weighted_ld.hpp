@@ -34,10 +34,19 @@ struct Panic : std::runtime_error {  // the reference's panic!() sites
   using std::runtime_error::runtime_error;
 };
 
+struct MappedFile;                     // read-only mmap of the input (weighted_ld.cpp)
+
 struct MultiSequence {                 // lib.rs:153-156
   std::string source;
   int64_t n_seqs = 0, n_cols = 0, row_stride = 0;
-  std::vector<uint8_t> chars;          // n_seqs rows, pitch row_stride (16-byte multiple), newline column kept
+  // The sequences, one of two ways.  read_fasta leaves them WHERE THEY ARE — rows[r] points at the r-th
+  // sequence line inside the mapped file (the reference's Vec<Sequence>, lib.rs:148-156, without the copy) and the
+  // library gathers them straight into its pinned staging buffers (wld_load_alignment_rows).  The VCF and
+  // Python-dialect readers build a matrix: n_seqs rows, pitch row_stride (16-byte multiple).
+  std::vector<const uint8_t*> rows;
+  std::shared_ptr<MappedFile> mapping; // keeps rows[] valid
+  std::vector<uint8_t> chars;
+  const uint8_t* row(int64_t r) const { return rows.empty() ? chars.data() + (size_t)(r * row_stride) : rows[(size_t)r]; }
   std::vector<std::string> names;      // lib.rs:143-146 (empty = None)
   bool ragged = false;                 // rows of unequal length: from_multiseq panics (lib.rs:180-182)
   bool codes = false;                  // chars already hold 0..5 codes (VCF allele indices, Python FASTA reader)
@@ -64,11 +73,25 @@ struct default_init_allocator : std::allocator<T> {
 };
 using PairVec = std::vector<wld_pair, default_init_allocator<wld_pair>>;
 
-class PairStore {                                   // lib.rs:529-576
+// lib.rs:529-576.  The survivors stay ON THE DEVICE, already merged over all GPUs, until they are asked for:
+// pairs() copies all of them (reference order, parent indices); for_each_chunk streams them, fetching the next
+// chunk while the caller works on the current one (the TSV writers use it, so a result larger than host
+// memory could still be written).
+class SiteSet;
+class PairStore {
  public:
-  PairVec pairs;                                    // reference order, parent indices
   uint64_t pairs_computed = 0;
-  size_t len() const { return pairs.size(); }
+  size_t len() const { return (size_t)n_; }
+  const PairVec& pairs() const;
+  void for_each_chunk(size_t chunk_pairs, const std::function<void(const wld_pair*, size_t first, size_t count)>& fn) const;
+
+ private:
+  friend PairStore all_weighted_ld_pairs(const SiteSet&, const std::vector<float>&, float, const std::function<void(size_t)>&);
+  std::shared_ptr<void> keep_;                      // the contexts
+  wld_ctx* root_ = nullptr;                         // holds the merged survivors
+  uint64_t n_ = 0;
+  mutable PairVec cache_;
+  mutable bool cached_ = false;
 };
 
 class SiteSet {                                     // lib.rs:158-275

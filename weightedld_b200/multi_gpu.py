@@ -50,8 +50,9 @@ class ShardedLoader:
 
 
 def gather_pairs(shard: np.ndarray, n_kept: int, site_map: np.ndarray | None, rank: int, world: int, group=None):
-    """Gathers KEPT-index survivor shards on rank 0 and merges them into the reference's output order;
-    returns the merged array on rank 0 and None elsewhere."""
+    """Gathers KEPT-index survivor shards (host arrays) on rank 0 and merges them on the host into the
+    reference's output order; returns the merged array on rank 0 and None elsewhere.  (Host-only variant, used
+    by the gloo tests; merge_on_device below is what the GPU path uses.)"""
     import torch.distributed as dist
 
     from .api import merge_shards
@@ -61,3 +62,40 @@ def gather_pairs(shard: np.ndarray, n_kept: int, site_map: np.ndarray | None, ra
     parts = [None] * world if rank == 0 else None
     dist.gather_object(shard, parts, dst=0, group=group)
     return merge_shards(n_kept, parts, site_map) if rank == 0 else None
+
+
+def merge_on_device(ctx, n_survivors: int, rank: int, world: int, out: np.ndarray | None = None, group=None):
+    """The host merge of the north star, done on rank 0's GPU: every rank hands its unordered KEPT-index shard
+    to NCCL straight from device memory (no host round trip), rank 0 appends the foreign shards to its own
+    survivors (wld_append_pairs) and one wld_fetch_pairs orders the union (lib.rs:623-679), maps it to raw
+    columns (lib.rs:662-663) and copies it out.  Returns the merged PAIR_DTYPE array on rank 0, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    from ._lib import FETCH_PARENT_INDEX, PAIR_DTYPE
+
+    def buffer(n):  # `out`: None, a PAIR_DTYPE array, or a callable n -> array (e.g. a pinned-buffer pool)
+        return out(n) if callable(out) else out
+
+    if world == 1:
+        return ctx.fetch_pairs(n_survivors, FETCH_PARENT_INDEX, out=buffer(n_survivors))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    mine = torch.tensor([n_survivors], dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, mine, group=group)
+    counts = counts.tolist()
+    item = PAIR_DTYPE.itemsize
+    shard = ctx.fetch_pairs_device(n_survivors) if rank != 0 else None
+    if rank == 0:
+        bufs = [torch.empty(max(c, 1) * item, dtype=torch.uint8, device=dev) for c in counts]
+        reqs = [dist.irecv(bufs[r][: counts[r] * item], src=r, group=group) for r in range(1, world) if counts[r]]
+        for q in reqs:
+            q.wait()
+        torch.cuda.current_stream().synchronize()
+        for r in range(1, world):
+            if counts[r]:
+                ctx.append_pairs(bufs[r][: counts[r] * item])
+        return ctx.fetch_pairs(sum(counts), FETCH_PARENT_INDEX, out=buffer(sum(counts)))
+    if n_survivors:
+        dist.send(shard, dst=0, group=group)
+    return None
