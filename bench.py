@@ -205,9 +205,8 @@ def check_mgpu_identity(wld, torch, dist, merge_on_device, local, rank, world):
     with wld.Context(local) as ctx:
         ctx.set_stream(torch.cuda.current_stream().cuda_stream)
         ctx.set_partition(rank, world)
-        ctx.load_alignment(chars)
-        ctx.filter_sites(*FILTER)
-        ctx.henikoff()
+        from weightedld_b200.multi_gpu import sharded_stages
+        sharded_stages(ctx, torch.from_numpy(chars).cuda(), FILTER, rank, world)
         n, _ = ctx.ld_pairs(R2_THRESHOLD)
         merged = merge_on_device(ctx, n, rank, world)
     ok = 1
@@ -274,7 +273,7 @@ def run_ours(args):
 
     loader = None
     pageable_np = chars_np  # ordinary (pageable) host memory, as a Rust Vec<u8> caller holds it
-    from weightedld_b200.multi_gpu import merge_on_device
+    from weightedld_b200.multi_gpu import merge_on_device, sharded_stages
     if world > 1:
         from weightedld_b200.multi_gpu import ShardedLoader
         loader = ShardedLoader(n_seqs, n_cols, rank, world, torch.device("cuda", local))
@@ -285,9 +284,8 @@ def run_ours(args):
         shards travel over NVLink to rank 0, which merges, orders and copies them out (multi_gpu.merge_on_device)."""
         if (src is host_np or src is pageable_np) and loader is not None:
             src = loader.load(host if src is host_np else torch.from_numpy(pageable_np))  # own rows H2D + all-gather
-        ctx.load_alignment(src)
-        n_kept = ctx.filter_sites(*FILTER)
-        ctx.henikoff()
+        # stages 1-2: split over the ranks with two small exact exchanges (multi_gpu.sharded_stages); one rank: plain
+        n_kept = sharded_stages(ctx, src, FILTER, rank, world)
         n_surv, done = ctx.ld_pairs(R2_THRESHOLD)
         out = None
         if fetch:

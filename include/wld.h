@@ -194,6 +194,31 @@ WLD_API int wld_get_major_minor(wld_ctx* ctx, int8_t* major, int8_t* minor, int6
 /* Kept code matrix, site-major: out[k*n_seqs + seq] (SiteSet::site_symbols, lib.rs:267). */
 WLD_API int wld_get_codes(wld_ctx* ctx, uint8_t* out, int64_t cap_bytes);
 
+/* ---- stages 1-2 on several GPUs ---------------------------------------------------
+ * Without these calls every GPU of a multi-GPU run repeats stages 1-2 on the whole alignment.  With them
+ * rank r counts only its rows and sums only its sequences; two small exchanges make every rank whole:
+ *   wld_set_row_shard(r's rows) -> wld_load_alignment -> SUM of the histograms over ranks (u32, exact)
+ *   -> wld_filter_sites -> wld_set_seq_shard(r's sequences) -> wld_henikoff -> ALL-GATHER of the weight sums
+ *   -> wld_henikoff_finish.
+ * Every sequence is summed whole by exactly one GPU in the single-GPU order, so all results stay
+ * bit-identical for any number of GPUs.  The exchange runs outside the library: over NCCL on the buffers
+ * wld_exchange_buffer names (one process per GPU), or by wld_sum_histograms / wld_share_weight_sums (one
+ * process driving several GPUs; peer copies).  This replaces nothing in the reference (it is single-node
+ * rayon, lib.rs:98-104,340-358); it shards the same arithmetic. */
+WLD_API int wld_set_row_shard(wld_ctx* ctx, int64_t row_lo, int64_t row_hi); /* row_hi < 0: all rows */
+WLD_API int wld_set_seq_shard(wld_ctx* ctx, int64_t seq_lo, int64_t seq_hi); /* seq_hi < 0: all sequences */
+enum {
+  WLD_EXCHANGE_HISTOGRAM = 0,   /* u32 [5][n_cols rounded up to 16]: sum over ranks, in place, after loading */
+  WLD_EXCHANGE_WEIGHT_SUMS = 1  /* f64 [n_seqs]: rank r owns [seq_lo, seq_hi), the rest is zero: all-gather in place, or
+                                   sum over ranks (x + 0 is exact), after wld_henikoff */
+};
+/* Device address and size of an exchange buffer (the ONE exception to "no device pointers leave the library":
+ * a collective has to run on it).  Valid until the next stage call on the context. */
+WLD_API int wld_exchange_buffer(wld_ctx* ctx, int which, void** device_ptr, uint64_t* bytes);
+WLD_API int wld_henikoff_finish(wld_ctx* ctx);  /* max + normalisation (lib.rs:355) after the all-gather */
+WLD_API int wld_sum_histograms(wld_ctx* const* ctxs, int n);
+WLD_API int wld_share_weight_sums(wld_ctx* const* ctxs, int n);
+
 /* ---- stage 2: sequence weights ------------------------------------------------------------- */
 /* henikoff_weights (lib.rs:340-358) + henikoff_site_contributions (lib.rs:360-380) over the
  * kept sites; f64 accumulation on the GPU, results held as f64 and as f32 (the reference type). */
@@ -210,6 +235,12 @@ WLD_API int wld_get_weights_f64(wld_ctx* ctx, double* out, int64_t cap);
  * n_survivors receives their count; pairs_computed (may be NULL) the number of pairs evaluated. */
 WLD_API int wld_ld_pairs(wld_ctx* ctx, float r2_threshold, wld_progress_fn progress, void* user,
                  uint64_t* n_survivors, uint64_t* pairs_computed);
+/* main.rs:129-190 in one call: load -> filter -> Henikoff weights (weights == NULL) or the caller's ->
+ * all pairs.  Same results as the four stage calls; the host waits for the device three times in total
+ * (kept-site count, weight quantisation decision, survivor count) plus once for a host input buffer. */
+WLD_API int wld_run(wld_ctx* ctx, const uint8_t* data, int64_t n_seqs, int64_t n_cols, int64_t row_stride, int flags,
+                    float min_acgt, float min_minor, float max_minor, const float* weights, float r2_threshold,
+                    int64_t* n_kept, uint64_t* n_survivors, uint64_t* pairs_computed);
 /* PairStore::iter (lib.rs:533-575): copies the survivors into out[0..cap) in the reference's
  * output order (tile rows bottom-up, columns ascending, then a, then b — lib.rs:623-679).
  * flags: WLD_FETCH_*. */

@@ -10,7 +10,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import weightedld_b200 as wld  # noqa: E402
-from weightedld_b200.multi_gpu import ShardedLoader, gather_pairs, merge_on_device  # noqa: E402
+from weightedld_b200.multi_gpu import ShardedLoader, gather_pairs, merge_on_device, sharded_stages  # noqa: E402
 from weightedld_b200.synth import make_alignment  # noqa: E402
 
 
@@ -27,9 +27,8 @@ def main():
     with wld.Context(local) as ctx:
         ctx.set_stream(torch.cuda.current_stream().cuda_stream)
         ctx.set_partition(rank, world)
-        ctx.load_alignment(full)
-        n_kept = ctx.filter_sites()
-        ctx.henikoff()
+        n_kept = sharded_stages(ctx, full, (0.8, 0.02, 0.5), rank, world)  # row / sequence shards + two exchanges
+        w_sharded = ctx.weights_f64()
         n, done = ctx.ld_pairs(0.1)
         shard = ctx.fetch_pairs(n, wld.FETCH_KEPT_INDEX | wld.FETCH_UNORDERED)
         site_map = ctx.site_map()
@@ -42,11 +41,13 @@ def main():
             ctx.load_alignment(chars)
             assert ctx.filter_sites() == n_kept
             ctx.henikoff()
+            w_whole = ctx.weights_f64()
             n1, done1 = ctx.ld_pairs(0.1)
             whole = ctx.fetch_pairs(n1)
         print(json.dumps({"world": world, "pairs": int(t.item()), "expected": n_kept * (n_kept - 1) // 2, "done1": done1,
                           "survivors": len(merged),
-                          "identical": merged.tobytes() == whole.tobytes() and merged_dev.tobytes() == whole.tobytes()}))
+                          "identical": merged.tobytes() == whole.tobytes() and merged_dev.tobytes() == whole.tobytes()
+                          and w_sharded.tobytes() == w_whole.tobytes()}))
     dist.destroy_process_group()
 
 

@@ -338,6 +338,45 @@ def test_append_pairs_merges_partitions_on_the_device(wld):
     torch.cuda.synchronize()
 
 
+def test_sharded_stages_are_bit_identical(wld, oracle):
+    """Stages 1-2 split over "ranks" (include/wld.h): three contexts on this GPU each count a third of the rows and
+    sum a third of the sequences; after the two exchanges (here wld_sum_histograms / wld_share_weight_sums, the
+    one-process form) every context holds the same histograms, site set and — bit for bit — the same weights as a
+    single context doing everything."""
+    import ctypes as C
+    chars = synth(1000, 1800, seed=66, block=60, clonal=True)
+    lib = wld._lib.load() if hasattr(wld, "_lib") else None
+    from weightedld_b200 import _lib as L
+    lib = L.load()
+    with wld.Context(0) as ref:
+        ref.load_alignment(chars)
+        k_ref = ref.filter_sites()
+        ref.henikoff()
+        h_ref, w_ref, sm_ref = ref.histograms(), ref.weights_f64(), ref.site_map()
+    ctxs = [wld.Context(0) for _ in range(3)]
+    try:
+        bounds = [(0, 334), (334, 668), (668, 1000)]
+        for ctx, (lo, hi) in zip(ctxs, bounds):
+            ctx.set_row_shard(lo, hi)
+            ctx.set_seq_shard(lo, hi)
+            ctx.load_alignment(chars)
+        arr = (C.c_void_p * 3)(*[c._h for c in ctxs])
+        assert lib.wld_sum_histograms(arr, 3) == 0
+        for ctx in ctxs:
+            assert ctx.filter_sites() == k_ref
+            assert np.array_equal(ctx.histograms(), h_ref) and np.array_equal(ctx.site_map(), sm_ref)
+            ctx.henikoff()
+            with pytest.raises(wld.WldError):
+                ctx.weights()                      # not whole yet
+        assert lib.wld_share_weight_sums(arr, 3) == 0
+        for ctx in ctxs:
+            ctx.henikoff_finish()
+            assert ctx.weights_f64().tobytes() == w_ref.tobytes()
+    finally:
+        for ctx in ctxs:
+            ctx.close()
+
+
 def test_overflow_protocol_grows_buffer(wld):
     chars = synth(200, 900, seed=8, block=90)
     small = run_gpu_pairs(wld, chars, "umma", -1.0, cap=1024)

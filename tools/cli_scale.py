@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--dir", default="/dev/shm")
     ap.add_argument("--repeat", type=int, default=2)
+    ap.add_argument("--quiet", action="store_true", help="RUST_LOG=info: no progress lines")
     args = ap.parse_args()
     import bench
 
@@ -44,14 +45,15 @@ def main():
     rec.tofile(fasta)
     del rec
     gen_s = time.perf_counter() - t0
-    out = {"workload": args.workload, "n_seqs": n, "n_cols": l, "fasta_bytes": fasta.stat().st_size, "generate_s": gen_s, "runs": []}
+    out = {"host_threads": os.cpu_count(), "workload": args.workload, "n_seqs": n, "n_cols": l, "fasta_bytes": fasta.stat().st_size, "generate_s": gen_s, "runs": []}
     for r in range(args.repeat):
         t0 = time.perf_counter()
         p = subprocess.run([str(ROOT / "weightedld_b200" / "weighted_ld"), "--fasta-input", str(fasta), "--pair-output",
-                            str(d / "pairs.tsv"), "--weights-output", str(d / "w.tsv"), "--gpus", str(args.gpus)], env=dict(os.environ, RUST_LOG="debug"),
+                            str(d / "pairs.tsv"), "--weights-output", str(d / "w.tsv"), "--gpus", str(args.gpus)],
+                           env=dict(os.environ, RUST_LOG="info" if args.quiet else "debug", WLD_DEBUG="1", WLD_CLI_TIMING="1"),
                            capture_output=True, text=True)
         wall = time.perf_counter() - t0
-        lines = [ln.split("] ", 1)[-1] for ln in p.stderr.splitlines()]
+        lines = [ln.split("] ", 1)[-1] for ln in p.stderr.splitlines() if "progress " not in ln]
         out["runs"].append({"rc": p.returncode, "wall_s": wall, "log": lines,
                             "pairs_tsv_bytes": (d / "pairs.tsv").stat().st_size if (d / "pairs.tsv").exists() else 0})
     print(json.dumps(out, indent=1))

@@ -23,6 +23,7 @@ INPUT_ASCII, INPUT_CODES, INPUT_DEVICE = 0, 1, 2
 FETCH_PARENT_INDEX, FETCH_KEPT_INDEX, FETCH_UNORDERED, FETCH_DEVICE = 0, 1, 2, 4
 PAIR_KERNEL_UMMA, PAIR_KERNEL_SIMT, PAIR_KERNEL_UMMA_I8 = 0, 1, 2
 COMPAT_RUST, COMPAT_PYTHON = 0, 1
+EXCHANGE_HISTOGRAM, EXCHANGE_WEIGHT_SUMS = 0, 1
 STAGE_LOAD, STAGE_HISTOGRAM, STAGE_FILTER, STAGE_HENIKOFF, STAGE_PAIR_PREP, STAGE_PAIR, STAGE_ORDER = range(7)
 STAGE_NAMES = ["load", "histogram", "filter", "henikoff", "pair_prep", "pair", "order"]
 STATUS_NAMES = {0: "OK", 1: "INVALID", 2: "STATE", 3: "CUDA", 4: "NOMEM", 5: "UNSUPPORTED", 6: "PANIC"}
@@ -72,10 +73,18 @@ SIGNATURES = {
     "wld_get_major_minor": (_int, [_vp, _vp, _vp, _i64]),
     "wld_get_codes": (_int, [_vp, _vp, _i64]),
     "wld_henikoff": (_int, [_vp]),
+    "wld_henikoff_finish": (_int, [_vp]),
+    "wld_set_row_shard": (_int, [_vp, _i64, _i64]),
+    "wld_set_seq_shard": (_int, [_vp, _i64, _i64]),
+    "wld_exchange_buffer": (_int, [_vp, _int, C.POINTER(_vp), C.POINTER(_u64)]),
+    "wld_sum_histograms": (_int, [C.POINTER(_vp), _int]),
+    "wld_share_weight_sums": (_int, [C.POINTER(_vp), _int]),
     "wld_set_weights": (_int, [_vp, _vp, _i64]),
     "wld_get_weights": (_int, [_vp, _vp, _i64]),
     "wld_get_weights_f64": (_int, [_vp, _vp, _i64]),
     "wld_ld_pairs": (_int, [_vp, C.c_float, PROGRESS_FN, _vp, C.POINTER(_u64), C.POINTER(_u64)]),
+    "wld_run": (_int, [_vp, _vp, _i64, _i64, _i64, _int, C.c_float, C.c_float, C.c_float, _vp, C.c_float, C.POINTER(_i64),
+                       C.POINTER(_u64), C.POINTER(_u64)]),
     "wld_fetch_pairs": (_int, [_vp, _vp, _u64, _int, C.POINTER(_u64)]),
     "wld_fetch_pairs_range": (_int, [_vp, _u64, _u64, _vp, _int, C.POINTER(_u64)]),
     "wld_append_pairs": (_int, [_vp, _vp, _u64, _int]),

@@ -201,6 +201,34 @@ class Context:
         self._check(self._lib.wld_get_codes(self._h, _ptr(out), out.size))
         return out
 
+    # ---- stages 1-2 on several GPUs
+    def set_row_shard(self, lo: int, hi: int = -1):
+        self._check(self._lib.wld_set_row_shard(self._h, lo, hi))
+
+    def set_seq_shard(self, lo: int, hi: int = -1):
+        self._check(self._lib.wld_set_seq_shard(self._h, lo, hi))
+
+    def exchange_tensor(self, which: int):
+        """The exchange buffer `which` (L.EXCHANGE_*) as a CUDA torch tensor aliasing the library's memory, for a
+        torch.distributed collective on it (wld_exchange_buffer).  Histogram: int32 view of the u32 counts (sums
+        stay far below 2^31); weight sums: float64."""
+        import torch
+
+        ptr, nbytes = C.c_void_p(), C.c_uint64()
+        self._check(self._lib.wld_exchange_buffer(self._h, which, C.byref(ptr), C.byref(nbytes)))
+        typestr, item, dtype = ("<i4", 4, torch.int32) if which == L.EXCHANGE_HISTOGRAM else ("<f8", 8, torch.float64)
+        n = nbytes.value // item
+        if n == 0:
+            return torch.empty(0, dtype=dtype, device=f"cuda:{self._device}")
+
+        class _Dev:  # zero-copy: torch reads the CUDA array interface
+            __cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr.value, False), "version": 2}
+
+        return torch.as_tensor(_Dev(), device=f"cuda:{self._device}")
+
+    def henikoff_finish(self):
+        self._check(self._lib.wld_henikoff_finish(self._h))
+
     # ---- stage 2
     def henikoff(self):
         self._check(self._lib.wld_henikoff(self._h))
@@ -225,6 +253,27 @@ class Context:
         cb = L.PROGRESS_FN(lambda v, _u: progress(int(v))) if progress else C.cast(None, L.PROGRESS_FN)
         self._check(self._lib.wld_ld_pairs(self._h, r2_threshold, cb, None, C.byref(n), C.byref(done)))
         return n.value, done.value
+
+    def run(self, chars, min_acgt=0.8, min_minor=0.02, max_minor=0.5, weights=None, r2_threshold=0.1, codes=False):
+        """wld_run: main.rs:129-190 in one call -> (n_kept, n_survivors, pairs_computed)."""
+        flags = L.INPUT_CODES if codes else L.INPUT_ASCII
+        if isinstance(chars, np.ndarray):
+            chars = np.ascontiguousarray(chars, np.uint8)
+            ptr, stride = _ptr(chars), chars.shape[1]
+        else:
+            import torch
+
+            if chars.is_cuda:
+                flags |= L.INPUT_DEVICE
+                if not self._stream_set:
+                    self._check(self._lib.wld_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(chars.device).cuda_stream)))
+            ptr, stride = C.c_void_p(chars.data_ptr()), (chars.stride(0) if chars.shape[0] > 1 else max(chars.shape[1], 1))
+        self._keepalive = chars
+        w = None if weights is None else np.ascontiguousarray(weights, np.float32)
+        k, n, done = C.c_int64(), C.c_uint64(), C.c_uint64()
+        self._check(self._lib.wld_run(self._h, ptr, chars.shape[0], chars.shape[1], stride, flags, min_acgt, min_minor, max_minor,
+                                      _ptr(w), r2_threshold, C.byref(k), C.byref(n), C.byref(done)))
+        return k.value, n.value, done.value
 
     def fetch_pairs(self, n: int, flags: int = L.FETCH_PARENT_INDEX, out: np.ndarray | None = None) -> np.ndarray:
         """Survivors as a structured array.  `out` may be a preallocated (e.g. pinned) PAIR_DTYPE array."""

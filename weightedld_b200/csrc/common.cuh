@@ -115,6 +115,11 @@ struct wld_ctx {
   int64_t ldc = 0;                 // code row pitch: n_seqs rounded up to 128
   wld::DevBuf codes;               // u8 [n_kept][ldc], site-major, pad = 5
 
+  // multi-GPU shards of stages 1-2 (wld_set_row_shard / wld_set_seq_shard); hi < 0 = everything
+  int64_t row_lo = 0, row_hi = -1;
+  int64_t seq_lo = 0, seq_hi = -1;
+  bool weights_partial = false;    // wld_henikoff ran on a shard: exchange + wld_henikoff_finish still to come
+
   // stage 2
   wld::DevBuf table;               // f64 [n_kept][8]  per-site contribution per code (6 used)
   wld::DevBuf partial;             // f64 [site_chunks][n_seqs]
@@ -207,7 +212,8 @@ int run_histogram(wld_ctx* c, ScopedStageTimer& tm);                       // en
 // (WeightedLD.py:44-98) with the f64 thresholds py_min_acgt / py_min_variability
 int run_filter(wld_ctx* c, int mode, float min_acgt, float min_minor, float max_minor, double py_min_acgt,
                double py_min_variability, ScopedStageTimer& tm);           // encode_filter.cu
-int run_henikoff(wld_ctx* c, ScopedStageTimer& tm);                        // henikoff.cu
+int run_henikoff(wld_ctx* c, ScopedStageTimer& tm, bool finish);           // henikoff.cu
+int run_henikoff_finish(wld_ctx* c, ScopedStageTimer& tm);                 // henikoff.cu: max + normalise
 int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm);                       // pair_prep.cu
 // The pair launchers bracket ONLY the kernel launch with the WLD_STAGE_PAIR timer (host-side
 // planning and the tile-list upload happen before the start event).

@@ -389,48 +389,53 @@ int run_histogram(wld_ctx* c, ScopedStageTimer& tm) {
   c->cols_padded = round_up(c->n_cols, 16);
   WLD_CUDA(c, c->hist.ensure(sizeof(uint32_t) * 6 * (size_t)c->cols_padded));
   WLD_CUDA(c, cudaMemsetAsync(c->hist.p, 0, sizeof(uint32_t) * 6 * (size_t)c->cols_padded, c->stream));
-  if (c->n_seqs == 0 || c->n_cols == 0) return WLD_OK;
+  // rows this context counts: all of them, or its shard of a multi-GPU run (wld_set_row_shard; the per-GPU
+  // histograms are then summed before the filter — integer counts, so the sum is exact)
+  const int64_t r_lo = std::min(c->row_lo, c->n_seqs), r_hi = c->row_hi < 0 ? c->n_seqs : std::min(c->row_hi, c->n_seqs);
+  const int64_t n_rows = r_hi - r_lo;
+  if (n_rows <= 0 || c->n_cols == 0) return WLD_OK;
+  const uint8_t* raw = c->d_raw + r_lo * c->row_stride;
 
-  const bool vec16 = (reinterpret_cast<uintptr_t>(c->d_raw) % 16 == 0) && (c->row_stride % 16 == 0) &&
+  const bool vec16 = (reinterpret_cast<uintptr_t>(raw) % 16 == 0) && (c->row_stride % 16 == 0) &&
                      (c->cols_padded <= c->row_stride);
   // Row chunk per block: enough blocks for several waves, at most 2040 rows (8 warps x 255).
   const int64_t col_blocks = vec16 ? (c->cols_padded + kHistColsPerBlock - 1) / kHistColsPerBlock
                                    : (c->n_cols + 255) / 256;
   int64_t want_blocks = (int64_t)c->sm_count * 16;
   int64_t row_chunks = (want_blocks + col_blocks - 1) / col_blocks;
-  int64_t rows_per_block = (c->n_seqs + row_chunks - 1) / row_chunks;
+  int64_t rows_per_block = (n_rows + row_chunks - 1) / row_chunks;
   rows_per_block = std::max<int64_t>(64, std::min<int64_t>(rows_per_block, 2040));
   rows_per_block = round_up(rows_per_block, 8);
-  row_chunks = (c->n_seqs + rows_per_block - 1) / rows_per_block;
+  row_chunks = (n_rows + rows_per_block - 1) / rows_per_block;
   if (row_chunks > 65535) {
-    rows_per_block = round_up((c->n_seqs + 65534) / 65535, 8);
-    row_chunks = (c->n_seqs + rows_per_block - 1) / rows_per_block;
+    rows_per_block = round_up((n_rows + 65534) / 65535, 8);
+    row_chunks = (n_rows + rows_per_block - 1) / rows_per_block;
   }
   dim3 grid((unsigned)col_blocks, (unsigned)row_chunks);
   if (vec16) {
     // The vector path reads whole 16-byte groups up to cols_padded on every row.  A BORROWED buffer only has to
     // be readable up to (n_seqs-1)*row_stride + n_cols (include/wld.h), so its last row goes through the
     // byte-wise kernel when n_cols is not a multiple of 16; the library's own copy is padded.
-    const bool tail_row = (c->input_flags & WLD_INPUT_DEVICE) && (c->n_cols % 16 != 0);
-    const int64_t n_fast = tail_row ? c->n_seqs - 1 : c->n_seqs;
+    const bool tail_row = (c->input_flags & WLD_INPUT_DEVICE) && (c->n_cols % 16 != 0) && r_hi == c->n_seqs;
+    const int64_t n_fast = tail_row ? n_rows - 1 : n_rows;
     if (n_fast > 0) {
       if (ascii)
-        hist_vec16_kernel<true><<<grid, kHistThreads, 0, c->stream>>>(c->d_raw, n_fast, c->n_cols, c->row_stride,
+        hist_vec16_kernel<true><<<grid, kHistThreads, 0, c->stream>>>(raw, n_fast, c->n_cols, c->row_stride,
                                                                      (int)rows_per_block, c->hist.as<uint32_t>(),
                                                                      c->cols_padded);
       else
-        hist_vec16_kernel<false><<<grid, kHistThreads, 0, c->stream>>>(c->d_raw, n_fast, c->n_cols, c->row_stride,
+        hist_vec16_kernel<false><<<grid, kHistThreads, 0, c->stream>>>(raw, n_fast, c->n_cols, c->row_stride,
                                                                       (int)rows_per_block, c->hist.as<uint32_t>(),
                                                                       c->cols_padded);
       tm.launched();
     }
     if (tail_row) {
       hist_generic_kernel<<<dim3((unsigned)((c->n_cols + 255) / 256), 1), 256, 0, c->stream>>>(
-          c->d_raw, c->n_seqs - 1, c->n_seqs, c->n_cols, c->row_stride, 1, ascii, c->hist.as<uint32_t>(), c->cols_padded);
+          raw, n_rows - 1, n_rows, c->n_cols, c->row_stride, 1, ascii, c->hist.as<uint32_t>(), c->cols_padded);
       tm.launched();
     }
   } else {
-    hist_generic_kernel<<<grid, 256, 0, c->stream>>>(c->d_raw, 0, c->n_seqs, c->n_cols, c->row_stride,
+    hist_generic_kernel<<<grid, 256, 0, c->stream>>>(raw, 0, n_rows, c->n_cols, c->row_stride,
                                                      (int)rows_per_block, ascii, c->hist.as<uint32_t>(),
                                                      c->cols_padded);
     tm.launched();

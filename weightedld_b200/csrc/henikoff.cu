@@ -61,8 +61,8 @@ __global__ void table_kernel(const uint32_t* __restrict__ hist, int64_t cols_pad
 // time: s_tab2[pair][6*code_a + code_b] = table[a][code_a] + table[b][code_b] — one lookup and one f64 add per
 // TWO cells.  (Summation order per sequence: pairs of sites in ascending order; deterministic.)
 __global__ void __launch_bounds__(kAccThreads) accumulate_kernel(const uint8_t* __restrict__ codes, int64_t ldc,
-                                                                 int64_t n_kept, int64_t n_seqs,
-                                                                 const double* __restrict__ table,
+                                                                 int64_t n_kept, int64_t n_seqs, int64_t seq_lo,
+                                                                 int64_t seq_hi, const double* __restrict__ table,
                                                                  double* __restrict__ partial) {
   __shared__ double s_tab2[kSiteChunk / 2][36];
   const int64_t k0 = (int64_t)blockIdx.y * kSiteChunk;
@@ -75,8 +75,9 @@ __global__ void __launch_bounds__(kAccThreads) accumulate_kernel(const uint8_t* 
     (&s_tab2[0][0])[i] = __dadd_rn(ta, tb);
   }
   __syncthreads();
-  const int64_t s0 = ((int64_t)blockIdx.x * kAccThreads + threadIdx.x) * 4;
-  if (s0 >= ldc) return;
+  // this launch covers the sequences [seq_lo, seq_hi) (a multi-GPU shard, or all of them), four per thread
+  const int64_t s0 = (seq_lo / 4 + (int64_t)blockIdx.x * kAccThreads + threadIdx.x) * 4;
+  if (s0 >= ldc || s0 >= seq_hi) return;
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   const uint8_t* p = codes + k0 * ldc + s0;
   auto add_pair = [&](int pr, uint32_t wa, uint32_t wb) {
@@ -102,20 +103,24 @@ __global__ void __launch_bounds__(kAccThreads) accumulate_kernel(const uint8_t* 
   }
 #pragma unroll
   for (int b = 0; b < 4; ++b)
-    if (s0 + b < n_seqs) partial[(int64_t)blockIdx.y * n_seqs + s0 + b] = acc[b];
+    if (s0 + b >= seq_lo && s0 + b < seq_hi) partial[(int64_t)blockIdx.y * n_seqs + s0 + b] = acc[b];
 }
 
-// Sum chunk partials in ascending chunk order; track the maximum (NaN ignored like f32::max).
-__global__ void reduce_kernel(const double* __restrict__ partial, int64_t n_chunks, int64_t n_seqs,
-                              double* __restrict__ w64, unsigned long long* __restrict__ max_bits) {
-  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// Sum chunk partials in ascending chunk order for the sequences [seq_lo, seq_hi).
+__global__ void reduce_kernel(const double* __restrict__ partial, int64_t n_chunks, int64_t n_seqs, int64_t seq_lo,
+                              int64_t seq_hi, double* __restrict__ w64) {
+  const int64_t s = seq_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= seq_hi) return;
   double v = 0.0;
-  if (s < n_seqs) {
-    for (int64_t ch = 0; ch < n_chunks; ++ch) v = __dadd_rn(v, partial[ch * n_seqs + s]);
-    w64[s] = v;
-  }
-  // lib.rs:355 fold(0.0, max): sums are >= 0 or NaN; for non-negative doubles the bit pattern is
-  // monotone, so an integer atomicMax implements it.
+  for (int64_t ch = 0; ch < n_chunks; ++ch) v = __dadd_rn(v, partial[ch * n_seqs + s]);
+  w64[s] = v;
+}
+
+// lib.rs:355 fold(0.0, max) over ALL sequences (NaN ignored like f32::max): sums are >= 0 or NaN; for
+// non-negative doubles the bit pattern is monotone, so an integer atomicMax implements it.
+__global__ void max_kernel(const double* __restrict__ w64, int64_t n_seqs, unsigned long long* __restrict__ max_bits) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const double v = s < n_seqs ? w64[s] : 0.0;
   unsigned long long bits = (s < n_seqs && v == v && v > 0.0) ? (unsigned long long)__double_as_longlong(v) : 0ull;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, o));
@@ -134,34 +139,50 @@ __global__ void normalize_kernel(double* __restrict__ w64, float* __restrict__ w
 
 }  // namespace
 
-int run_henikoff(wld_ctx* c, ScopedStageTimer& tm) {
+// Per-sequence sums for the context's sequence shard (all sequences unless wld_set_seq_shard narrowed it): every
+// sequence is summed whole, over all kept sites in the same order, by exactly one GPU — so the weights are
+// bit-identical for any number of GPUs.  `finish` adds the maximum and the normalisation (lib.rs:355).
+int run_henikoff(wld_ctx* c, ScopedStageTimer& tm, bool finish) {
   const int64_t n = c->n_seqs, L = c->n_kept;
+  const int64_t lo = std::min(c->seq_lo, n), hi = c->seq_hi < 0 ? n : std::min(c->seq_hi, n);
   WLD_CUDA(c, c->w64.ensure(sizeof(double) * (size_t)std::max<int64_t>(n, 1)));
   WLD_CUDA(c, c->w32.ensure(sizeof(float) * (size_t)std::max<int64_t>(n, 1)));
   WLD_CUDA(c, c->scalars.ensure(sizeof(double) * 8));
-  WLD_CUDA(c, cudaMemsetAsync(c->scalars.p, 0, sizeof(double) * 8, c->stream));
   if (n == 0) return WLD_OK;
   const int64_t n_chunks = (L + kSiteChunk - 1) / kSiteChunk;
   WLD_CUDA(c, c->table.ensure(sizeof(double) * 8 * (size_t)std::max<int64_t>(L, 1)));
   WLD_CUDA(c, c->partial.ensure(sizeof(double) * (size_t)std::max<int64_t>(n_chunks, 1) * (size_t)n));
-  if (L > 0) {
-    table_kernel<<<(unsigned)((L + 255) / 256), 256, 0, c->stream>>>(c->hist.as<uint32_t>(), c->cols_padded,
-                                                                    c->site_map.as<int32_t>(), L,
-                                                                    c->compat == WLD_COMPAT_PYTHON, c->table.as<double>());
-    tm.launched();
-    dim3 grid((unsigned)((c->ldc / 4 + kAccThreads - 1) / kAccThreads), (unsigned)n_chunks);
-    if (grid.y > 65535) return c->fail(WLD_ERR_UNSUPPORTED, "too many kept sites for the Henikoff grid");
-    accumulate_kernel<<<grid, kAccThreads, 0, c->stream>>>(c->codes.as<uint8_t>(), c->ldc, L, n,
-                                                           c->table.as<double>(), c->partial.as<double>());
+  // a shard leaves the other sequences' sums at zero, so that the exchange may also be a SUM over ranks
+  if (!finish) WLD_CUDA(c, cudaMemsetAsync(c->w64.p, 0, sizeof(double) * (size_t)n, c->stream));
+  if (hi > lo) {
+    if (L > 0) {
+      table_kernel<<<(unsigned)((L + 255) / 256), 256, 0, c->stream>>>(c->hist.as<uint32_t>(), c->cols_padded,
+                                                                      c->site_map.as<int32_t>(), L,
+                                                                      c->compat == WLD_COMPAT_PYTHON, c->table.as<double>());
+      tm.launched();
+      const int64_t span = std::min(round_up(hi, 4), c->ldc) - lo / 4 * 4;  // whole groups of four sequences
+      dim3 grid((unsigned)((span / 4 + kAccThreads - 1) / kAccThreads), (unsigned)n_chunks);
+      if (grid.y > 65535) return c->fail(WLD_ERR_UNSUPPORTED, "too many kept sites for the Henikoff grid");
+      accumulate_kernel<<<grid, kAccThreads, 0, c->stream>>>(c->codes.as<uint8_t>(), c->ldc, L, n, lo, hi,
+                                                             c->table.as<double>(), c->partial.as<double>());
+      tm.launched();
+    }
+    reduce_kernel<<<(unsigned)((hi - lo + 255) / 256), 256, 0, c->stream>>>(c->partial.as<double>(), n_chunks, n, lo, hi,
+                                                                           c->w64.as<double>());
     tm.launched();
   }
-  reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->partial.as<double>(), n_chunks, n,
-                                                                   c->w64.as<double>(),
-                                                                   c->scalars.as<unsigned long long>());
-  tm.launched();
+  WLD_CUDA(c, cudaGetLastError());
+  return finish ? run_henikoff_finish(c, tm) : WLD_OK;
+}
+
+int run_henikoff_finish(wld_ctx* c, ScopedStageTimer& tm) {
+  const int64_t n = c->n_seqs;
+  if (n == 0) return WLD_OK;
+  WLD_CUDA(c, cudaMemsetAsync(c->scalars.p, 0, sizeof(double) * 8, c->stream));
+  max_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->w64.as<double>(), n, c->scalars.as<unsigned long long>());
   normalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->w64.as<double>(), c->w32.as<float>(), n,
                                                                       c->scalars.as<unsigned long long>());
-  tm.launched();
+  tm.launched(2);
   WLD_CUDA(c, cudaGetLastError());
   return WLD_OK;
 }

@@ -5,7 +5,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <new>
 #include <thread>
 
@@ -19,6 +21,7 @@ namespace {
   cudaSetDevice((c)->device)
 
 bool host_is_pinned(const void* p);
+int ensure_stagers(wld_ctx* c);
 int staged_copy(wld_ctx* c, void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t row_bytes,
                 size_t rows, cudaMemcpyKind dir, const uint8_t* const* src_rows = nullptr);
 constexpr size_t kStageChunk = 8u << 20;
@@ -174,9 +177,19 @@ static int load_common(wld_ctx* c, const uint8_t* data, const uint8_t* const* ro
         // threads stage it through pinned buffers, each chunk's H2D copy overlapping the others' memcpy
         if ((size_t)n_cols > kStageChunk) return c->fail(WLD_ERR_UNSUPPORTED, "rows longer than %zu bytes must be passed contiguously", kStageChunk);
         WLD_CUDA(c, cudaStreamSynchronize(c->stream));
-        const int rc = staged_copy(c, c->raw_own.p, (size_t)pitch, data, (size_t)row_stride, (size_t)n_cols, (size_t)n_seqs,
-                                   cudaMemcpyHostToDevice, rows);
+        const auto t0 = std::chrono::steady_clock::now();
+        int rc = ensure_stagers(c);
+        const auto t1 = std::chrono::steady_clock::now();
+        if (rc == WLD_OK)
+          rc = staged_copy(c, c->raw_own.p, (size_t)pitch, data, (size_t)row_stride, (size_t)n_cols, (size_t)n_seqs,
+                           cudaMemcpyHostToDevice, rows);
         if (rc != WLD_OK) return rc;
+        if (std::getenv("WLD_DEBUG")) {
+          const double ms0 = std::chrono::duration<double, std::milli>(t1 - t0).count();
+          const double ms1 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+          std::fprintf(stderr, "[libwld] staged load: %d threads, pinned buffers %.1f ms, copy of %.1f MB %.1f ms (%.1f GB/s)\n",
+                       c->n_stagers, ms0, (double)n_seqs * n_cols / 1e6, ms1, (double)n_seqs * n_cols / 1e6 / ms1);
+        }
       } else if (n_seqs > 0 && n_cols > 0) {
         if (row_stride == pitch)  // same pitch on both sides: one linear copy (a pageable 2-D copy goes row by row)
           WLD_CUDA(c, cudaMemcpyAsync(c->raw_own.p, data, (size_t)(n_seqs - 1) * (size_t)pitch + (size_t)n_cols,
@@ -194,8 +207,9 @@ static int load_common(wld_ctx* c, const uint8_t* data, const uint8_t* const* ro
     int rc = run_histogram(c, tm);
     if (rc != WLD_OK) return rc;
   }
-  // The host buffer may be reused by the caller as soon as we return.
-  WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+  // The host buffer may be reused by the caller as soon as we return.  (A borrowed device buffer stays the
+  // caller's promise until the next load, so its kernels are left running: one pipeline drain less per step.)
+  if (!(flags & WLD_INPUT_DEVICE)) WLD_CUDA(c, cudaStreamSynchronize(c->stream));
   c->stage = Stage::Loaded;
   return WLD_OK;
 }
@@ -225,7 +239,7 @@ static int filter_common(wld_ctx* c, int mode, float min_acgt, float min_minor, 
     int rc = run_filter(c, mode, min_acgt, min_minor, max_minor, py_min_acgt, py_min_variability, tm);
     if (rc != WLD_OK) return rc;
   }
-  WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+  // (run_filter waited for the kept count; the gather that follows it keeps running)
   if (n_kept) *n_kept = c->n_kept;
   c->stage = Stage::Filtered;
   return WLD_OK;
@@ -305,11 +319,123 @@ int wld_henikoff(wld_ctx* c) {
   if (c->stage < Stage::Filtered) return c->fail(WLD_ERR_STATE, "wld_henikoff before wld_filter_sites");
   {
     ScopedStageTimer tm(c, WLD_STAGE_HENIKOFF);
-    int rc = run_henikoff(c, tm);
+    const bool whole = c->seq_lo <= 0 && (c->seq_hi < 0 || c->seq_hi >= c->n_seqs);
+    int rc = run_henikoff(c, tm, whole);
+    if (rc != WLD_OK) return rc;
+    c->weights_partial = !whole;
+  }
+  // a shard: the sums of the other sequences arrive by exchange, then wld_henikoff_finish normalises
+  if (!c->weights_partial) c->stage = Stage::Weighted;  // no wait: the weights are read on the same stream
+  return WLD_OK;
+}
+
+int wld_henikoff_finish(wld_ctx* c) {
+  WLD_CHECK_CTX(c);
+  if (c->stage < Stage::Filtered || !c->weights_partial)
+    return c->fail(WLD_ERR_STATE, "wld_henikoff_finish without a sharded wld_henikoff before it");
+  {
+    ScopedStageTimer tm(c, WLD_STAGE_HENIKOFF);  // (the timer then shows the finishing kernels only)
+    int rc = run_henikoff_finish(c, tm);
     if (rc != WLD_OK) return rc;
   }
-  WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->weights_partial = false;
   c->stage = Stage::Weighted;
+  return WLD_OK;
+}
+
+int wld_set_row_shard(wld_ctx* c, int64_t row_lo, int64_t row_hi) {
+  WLD_CHECK_CTX(c);
+  if (row_lo < 0 || (row_hi >= 0 && row_hi < row_lo)) return c->fail(WLD_ERR_INVALID, "bad row shard");
+  c->row_lo = row_lo;
+  c->row_hi = row_hi;
+  return WLD_OK;
+}
+
+int wld_set_seq_shard(wld_ctx* c, int64_t seq_lo, int64_t seq_hi) {
+  WLD_CHECK_CTX(c);
+  if (seq_lo < 0 || (seq_hi >= 0 && seq_hi < seq_lo)) return c->fail(WLD_ERR_INVALID, "bad sequence shard");
+  c->seq_lo = seq_lo;
+  c->seq_hi = seq_hi;
+  return WLD_OK;
+}
+
+int wld_exchange_buffer(wld_ctx* c, int which, void** device_ptr, uint64_t* bytes) {
+  WLD_CHECK_CTX(c);
+  if (!device_ptr || !bytes) return c->fail(WLD_ERR_INVALID, "null output");
+  *device_ptr = nullptr;
+  *bytes = 0;
+  if (which == WLD_EXCHANGE_HISTOGRAM) {
+    if (c->stage < Stage::Loaded) return c->fail(WLD_ERR_STATE, "histogram buffer before wld_load_alignment");
+    *device_ptr = c->hist.p;
+    *bytes = sizeof(uint32_t) * 5 * (uint64_t)c->cols_padded;  // bins A C G T -; Unknown is derived from n_seqs
+  } else if (which == WLD_EXCHANGE_WEIGHT_SUMS) {
+    if (c->stage < Stage::Filtered || !c->w64.p) return c->fail(WLD_ERR_STATE, "weight sums before wld_henikoff");
+    *device_ptr = c->w64.p;
+    *bytes = sizeof(double) * (uint64_t)c->n_seqs;
+  } else {
+    return c->fail(WLD_ERR_INVALID, "unknown exchange buffer %d", which);
+  }
+  return WLD_OK;
+}
+
+// One process driving several GPUs: the exchanges by peer copies (sizes are below a megabyte).
+namespace {
+__global__ void add_u32_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+}  // namespace
+
+int wld_sum_histograms(wld_ctx* const* ctxs, int n) {
+  if (!ctxs || n < 1 || !ctxs[0]) return WLD_ERR_INVALID;
+  wld_ctx* root = ctxs[0];
+  if (n == 1) return WLD_OK;
+  cudaSetDevice(root->device);
+  const size_t words = 5 * (size_t)root->cols_padded;
+  for (int g = 0; g < n; ++g)
+    if (!ctxs[g] || ctxs[g]->stage < Stage::Loaded || ctxs[g]->cols_padded != root->cols_padded)
+      return root->fail(WLD_ERR_STATE, "wld_sum_histograms: every context must hold the same loaded alignment");
+  DevBuf tmp;
+  WLD_CUDA(root, tmp.ensure(sizeof(uint32_t) * std::max<size_t>(words, 1)));
+  int rc = WLD_OK;
+  for (int g = 1; g < n && rc == WLD_OK; ++g) {
+    cudaSetDevice(ctxs[g]->device);
+    cudaError_t e = cudaStreamSynchronize(ctxs[g]->stream);
+    cudaSetDevice(root->device);
+    if (e == cudaSuccess) e = cudaMemcpyPeerAsync(tmp.p, root->device, ctxs[g]->hist.p, ctxs[g]->device, sizeof(uint32_t) * words, root->stream);
+    if (e != cudaSuccess) { rc = root->fail(WLD_ERR_CUDA, "histogram exchange failed: %s", cudaGetErrorString(e)); break; }
+    if (words) add_u32_kernel<<<(unsigned)((words + 255) / 256), 256, 0, root->stream>>>(root->hist.as<uint32_t>(), tmp.as<uint32_t>(), words);
+  }
+  if (rc == WLD_OK && cudaStreamSynchronize(root->stream) != cudaSuccess) rc = root->fail(WLD_ERR_CUDA, "histogram exchange failed");
+  for (int g = 1; g < n && rc == WLD_OK; ++g) {
+    if (cudaMemcpyPeer(ctxs[g]->hist.p, ctxs[g]->device, root->hist.p, root->device, sizeof(uint32_t) * words) != cudaSuccess)
+      rc = root->fail(WLD_ERR_CUDA, "histogram broadcast failed");
+  }
+  tmp.release();
+  return rc;
+}
+
+int wld_share_weight_sums(wld_ctx* const* ctxs, int n) {
+  if (!ctxs || n < 1 || !ctxs[0]) return WLD_ERR_INVALID;
+  wld_ctx* root = ctxs[0];
+  for (int g = 0; g < n; ++g)
+    if (!ctxs[g] || !ctxs[g]->weights_partial || ctxs[g]->n_seqs != root->n_seqs)
+      return root->fail(WLD_ERR_STATE, "wld_share_weight_sums: every context needs a sharded wld_henikoff first");
+  for (int g = 0; g < n; ++g) {  // every source's stream is done with its slice
+    cudaSetDevice(ctxs[g]->device);
+    if (cudaStreamSynchronize(ctxs[g]->stream) != cudaSuccess) return root->fail(WLD_ERR_CUDA, "weight exchange failed");
+  }
+  for (int src = 0; src < n; ++src) {
+    const wld_ctx* s_ = ctxs[src];
+    const int64_t lo = std::min(s_->seq_lo, s_->n_seqs), hi = s_->seq_hi < 0 ? s_->n_seqs : std::min(s_->seq_hi, s_->n_seqs);
+    if (hi <= lo) continue;
+    for (int dst = 0; dst < n; ++dst) {
+      if (dst == src) continue;
+      if (cudaMemcpyPeer(ctxs[dst]->w64.as<double>() + lo, ctxs[dst]->device, s_->w64.as<double>() + lo, s_->device,
+                         sizeof(double) * (size_t)(hi - lo)) != cudaSuccess)
+        return root->fail(WLD_ERR_CUDA, "weight exchange failed");
+    }
+  }
   return WLD_OK;
 }
 
@@ -469,6 +595,16 @@ int wld_get_pair_weights(wld_ctx* c, double* out, int64_t cap) {
   WLD_CUDA(c, cudaMemcpyAsync(out, c->q.p, sizeof(double) * (size_t)c->n_seqs, cudaMemcpyDeviceToHost, c->stream));
   WLD_CUDA(c, cudaStreamSynchronize(c->stream));
   return WLD_OK;
+}
+
+int wld_run(wld_ctx* c, const uint8_t* data, int64_t n_seqs, int64_t n_cols, int64_t row_stride, int flags, float min_acgt,
+            float min_minor, float max_minor, const float* weights, float r2_threshold, int64_t* n_kept,
+            uint64_t* n_survivors, uint64_t* pairs_computed) {
+  int rc = wld_load_alignment(c, data, n_seqs, n_cols, row_stride, flags);
+  if (rc == WLD_OK) rc = wld_filter_sites(c, min_acgt, min_minor, max_minor, n_kept);
+  if (rc == WLD_OK) rc = weights ? wld_set_weights(c, weights, n_seqs) : wld_henikoff(c);
+  if (rc == WLD_OK) rc = wld_ld_pairs(c, r2_threshold, nullptr, nullptr, n_survivors, pairs_computed);
+  return rc;
 }
 
 uint64_t wld_pair_order_key(int64_t n_kept, uint32_t kept_a, uint32_t kept_b) {

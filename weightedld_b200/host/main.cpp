@@ -246,7 +246,10 @@ int main(int argc, char** argv) {
     if (opt.python_compat) write_pair_stats_python(opt.pair_output, store, multiseq.site_labels);  // WeightedLD.py:176,283
     else write_pair_stats(opt.pair_output, store, multiseq.site_labels);  // main.rs:209
     INFO("Finshed writing output in " + fmt_duration(Clock::now() - sw)); // main.rs:210 (sic)
-    return 0;
+    // Everything is written and closed.  Releasing tens of GB of device memory buffer by buffer and tearing the
+    // CUDA context down in order takes longer than the whole computation; the process is about to end anyway.
+    std::fflush(nullptr);
+    std::_Exit(0);
   } catch (const Panic& p) {
     std::fprintf(stderr, "thread 'main' panicked at '%s'\n", p.what());
     return 101;  // Rust's panic exit code

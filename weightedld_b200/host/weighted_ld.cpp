@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <charconv>
+#include <chrono>
 #include <cctype>
 #include <cmath>
 #include <cstdio>
@@ -330,6 +331,10 @@ SiteSet SiteSet::from_multiseq(const MultiSequence& ms, std::shared_ptr<Impl> op
     th.emplace_back([&, g] {
       wld_ctx* c = s.impl->ctx[(size_t)g];
       int rc = wld_set_partition(c, g, n);
+      // stages 1-2 are split over the GPUs: GPU g counts the rows [g*R, (g+1)*R) and later sums those sequences
+      const int64_t per = (ms.n_seqs + n - 1) / n, lo = std::min<int64_t>(g * per, ms.n_seqs), hi = std::min<int64_t>(lo + per, ms.n_seqs);
+      if (rc == WLD_OK) rc = wld_set_row_shard(c, lo, n > 1 ? hi : -1);
+      if (rc == WLD_OK) rc = wld_set_seq_shard(c, lo, n > 1 ? hi : -1);
       if (rc == WLD_OK)
         rc = !ms.rows.empty()
                  ? wld_load_alignment_rows(c, ms.rows.data(), ms.n_seqs, ms.n_cols, ms.codes ? WLD_INPUT_CODES : WLD_INPUT_ASCII)
@@ -340,6 +345,7 @@ SiteSet SiteSet::from_multiseq(const MultiSequence& ms, std::shared_ptr<Impl> op
   for (auto& t : th) t.join();
   for (auto& e : errs)
     if (!e.empty()) throw WldError(WLD_ERR_CUDA, e);
+  if (n > 1) check(s.impl->ctx[0], wld_sum_histograms(s.impl->ctx.data(), n));  // exact integer sum over the GPUs
   return s;
 }
 
@@ -391,7 +397,12 @@ int64_t SiteSet::parent_site_index(int64_t idx) const { return filtered ? site_m
 
 std::vector<float> henikoff_weights(const SiteSet& data) {
   std::vector<float> w((size_t)data.n_seqs());
-  for (auto* c : data.impl->ctx) check(c, wld_henikoff(c));
+  auto& ctxs = data.impl->ctx;
+  for (auto* c : ctxs) check(c, wld_henikoff(c));  // asynchronous: the GPUs sum their sequence shards concurrently
+  if (ctxs.size() > 1) {
+    check(ctxs[0], wld_share_weight_sums(ctxs.data(), (int)ctxs.size()));
+    for (auto* c : ctxs) check(c, wld_henikoff_finish(c));
+  }
   check(data.impl->ctx[0], wld_get_weights(data.impl->ctx[0], w.data(), (int64_t)w.size()));
   return w;
 }
@@ -518,8 +529,8 @@ static int fmt_f3(float v, char* buf) {
   if (std::isinf(v)) return std::sprintf(buf, v < 0 ? "-inf" : "inf");
   const double x = (double)v;
   if (std::fabs(x) >= 1e15) return std::sprintf(buf, "%.3f", x);
-  const double r = std::nearbyint(std::fabs(x) * 1000.0);
-  const unsigned long long m = (unsigned long long)r;
+  // llrint: one cvtsd2si in the default rounding mode (to nearest, ties to even) instead of a libm call
+  const unsigned long long m = (unsigned long long)std::llrint(std::fabs(x) * 1000.0);
   int k = 0;
   if (std::signbit(v)) buf[k++] = '-';
   k += fmt_u64(m / 1000, buf + k);
@@ -586,18 +597,27 @@ namespace {
 // Formats `n` records with `fmt_line` on all host threads and writes the pieces IN ORDER at `*file_pos`:
 // every thread formats a contiguous run into its own buffer, the run lengths give each buffer its file
 // offset, and the threads pwrite() their buffers concurrently (page-cache copies scale with threads).
+struct WriteTiming { double format_s = 0, write_s = 0; };
+WriteTiming g_write_timing;
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 template <class LineFn>
 void write_records_parallel(int fd, off_t* file_pos, const wld_pair* recs, size_t n, LineFn&& fmt_line) {
   if (n == 0) return;
+  const double t_begin = now_s();
   const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
   const size_t nthr = std::max<size_t>(1, std::min<size_t>(hw, n / 4096));
   std::vector<std::string> out(nthr);
   auto format = [&](size_t t) {
     const size_t lo = n * t / nthr, hi = n * (t + 1) / nthr;
-    std::string& s = out[t];
-    s.reserve((hi - lo) * 44);
-    char line[192];
-    for (size_t i = lo; i < hi; ++i) s.append(line, (size_t)fmt_line(recs[i], line));
+    std::string& s = out[t];  // lines are formatted in place: no per-line append
+    s.resize((hi - lo) * 40 + 256);
+    size_t used = 0;
+    for (size_t i = lo; i < hi; ++i) {
+      if (s.size() - used < 192) s.resize(s.size() + s.size() / 4 + 4096);
+      used += (size_t)fmt_line(recs[i], &s[used]);
+    }
+    s.resize(used);
   };
   auto run = [&](auto&& f) {
     if (nthr == 1) { f(0); return; }
@@ -606,6 +626,7 @@ void write_records_parallel(int fd, off_t* file_pos, const wld_pair* recs, size_
     for (auto& x : th) x.join();
   };
   run(format);
+  const double t_fmt = now_s();
   std::vector<off_t> at(nthr);
   off_t pos = *file_pos;
   for (size_t t = 0; t < nthr; ++t) {
@@ -626,6 +647,8 @@ void write_records_parallel(int fd, off_t* file_pos, const wld_pair* recs, size_
   for (int e : errs)
     if (e) throw std::ios_base::failure(std::string(std::strerror(e)) + " (os error " + std::to_string(e) + ")");
   *file_pos = pos;
+  g_write_timing.format_s += t_fmt - t_begin;
+  g_write_timing.write_s += now_s() - t_fmt;
 }
 
 int open_out(const std::string& path) {
@@ -690,6 +713,8 @@ void write_pair_stats(const std::string& path, const PairStore& store, const std
     buf[k++] = '\n';
     return k;
   };
+  g_write_timing = WriteTiming{};
+  const double t0 = now_s();
   try {
     // streamed: the next chunk is fetched from the device while this one is formatted and written
     store.for_each_chunk((size_t)4 << 20, [&](const wld_pair* recs, size_t, size_t count) {
@@ -697,6 +722,9 @@ void write_pair_stats(const std::string& path, const PairStore& store, const std
     });
   } catch (...) { ::close(fd); throw; }
   ::close(fd);
+  if (std::getenv("WLD_CLI_TIMING"))
+    std::fprintf(stderr, "[weighted_ld] pair writer: %.1f ms total, %.1f ms formatting, %.1f ms pwrite, rest = waiting for the device copy; %u host threads\n",
+                 (now_s() - t0) * 1e3, g_write_timing.format_s * 1e3, g_write_timing.write_s * 1e3, std::thread::hardware_concurrency());
 }
 
 }  // namespace weighted_ld

@@ -49,6 +49,34 @@ class ShardedLoader:
         return self.full[: self.n_seqs, : self.n_cols]
 
 
+def sharded_stages(ctx, src, filt, rank: int, world: int, group=None, weights=None) -> int:
+    """Stages 1-2 with the work split over the ranks (include/wld.h, "stages 1-2 on several GPUs"): rank r
+    histograms its rows and sums the Henikoff contributions of its sequences; one all-reduce of the integer
+    histogram (<= 720 KB at config 4) and one of the weight sums (f64, every entry has exactly one non-zero
+    contributor, so the sum is exact) make every rank whole.  Returns n_kept.  Results are bit-identical to
+    the replicated path for any world size."""
+    import torch.distributed as dist
+
+    from ._lib import EXCHANGE_HISTOGRAM, EXCHANGE_WEIGHT_SUMS
+
+    n_seqs = src.shape[0]
+    lo, hi, _ = shard_rows(n_seqs, rank, world)
+    ctx.set_row_shard(lo, hi)
+    ctx.load_alignment(src)
+    if world > 1:
+        dist.all_reduce(ctx.exchange_tensor(EXCHANGE_HISTOGRAM), group=group)
+    n_kept = ctx.filter_sites(*filt)
+    if weights is not None:
+        ctx.set_weights(weights)
+        return n_kept
+    ctx.set_seq_shard(lo, hi)
+    ctx.henikoff()
+    if world > 1:
+        dist.all_reduce(ctx.exchange_tensor(EXCHANGE_WEIGHT_SUMS), group=group)
+        ctx.henikoff_finish()
+    return n_kept
+
+
 def gather_pairs(shard: np.ndarray, n_kept: int, site_map: np.ndarray | None, rank: int, world: int, group=None):
     """Gathers KEPT-index survivor shards (host arrays) on rank 0 and merges them on the host into the
     reference's output order; returns the merged array on rank 0 and None elsewhere.  (Host-only variant, used
