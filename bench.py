@@ -233,6 +233,11 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    # stdout carries exactly ONE JSON line: everything else that writes to file descriptor 1 while the job runs
+    # (NCCL prints its version banner there from C) is sent to stderr, and the line goes to the saved descriptor.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
@@ -423,7 +428,8 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": v, "unit": "site-pairs/s", "cores": ci["cores"], "kind": ci["kind"], "sample": ci["sample"]}
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -114,7 +114,9 @@ WLD_API void wld_destroy(wld_ctx* ctx);
 WLD_API const char* wld_last_error(const wld_ctx* ctx);
 WLD_API int wld_abi_version(void);
 
-/* Run all work on this CUDA stream (a cudaStream_t passed as void*); NULL = the context's own. */
+/* Run all work on this CUDA stream (a cudaStream_t passed as void*); NULL = the context's own (a private
+ * non-blocking stream).  To run on the legacy default stream — whose handle is also 0 — pass the explicit
+ * handle cudaStreamLegacy ((cudaStream_t)0x1). */
 WLD_API int wld_set_stream(wld_ctx* ctx, void* cuda_stream);
 
 /* Shard the pair stage: this context computes part `part` of `nparts` of the upper-triangular

@@ -75,8 +75,21 @@ class Context:
 
     # ---- options
     def set_stream(self, cuda_stream_ptr: int | None):
-        self._stream_set = True
-        self._check(self._lib.wld_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+        """Run on this CUDA stream.  None = the context's own stream; 0 (what torch reports for its default stream)
+        = the legacy default stream, passed to the library as the explicit handle cudaStreamLegacy (0x1), because
+        a NULL argument of wld_set_stream means "your own stream"."""
+        self._stream_set = cuda_stream_ptr is not None
+        handle = 0 if cuda_stream_ptr is None else (1 if cuda_stream_ptr == 0 else cuda_stream_ptr)
+        self._check(self._lib.wld_set_stream(self._h, C.c_void_p(handle)))
+
+    def adopt_torch_stream(self, device=None):
+        """Run on torch's current stream (so that torch / NCCL work on tensors this context reads or writes is
+        ordered with its kernels) unless the caller chose a stream explicitly."""
+        if not self._stream_set:
+            import torch
+
+            s = torch.cuda.current_stream(device if device is not None else self._device).cuda_stream
+            self._check(self._lib.wld_set_stream(self._h, C.c_void_p(1 if s == 0 else s)))
 
     def set_partition(self, part: int, nparts: int):
         self._check(self._lib.wld_set_partition(self._h, part, nparts))
@@ -131,11 +144,10 @@ class Context:
                 raise ValueError("alignment tensor must be 2-D uint8 with unit inner stride")
             if t.is_cuda:
                 flags |= L.INPUT_DEVICE
-                if not self._stream_set:
-                    # A borrowed device buffer is read on the context's stream (include/wld.h, WLD_INPUT_DEVICE): run on
-                    # the torch stream that produced the tensor unless the caller chose a stream, so that the kernels are
-                    # ordered after the copy / collective that filled it.
-                    self._check(self._lib.wld_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)))
+                # A borrowed device buffer is read on the context's stream (include/wld.h, WLD_INPUT_DEVICE): run on
+                # the torch stream that produced the tensor unless the caller chose a stream, so that the kernels are
+                # ordered after the copy / collective that filled it.
+                self.adopt_torch_stream(t.device)
             self._keepalive = t
             stride = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
             self._check(self._lib.wld_load_alignment(self._h, C.c_void_p(t.data_ptr()), t.shape[0], t.shape[1],
@@ -214,6 +226,7 @@ class Context:
         stay far below 2^31); weight sums: float64."""
         import torch
 
+        self.adopt_torch_stream()  # the collective must be ordered with this context's kernels
         ptr, nbytes = C.c_void_p(), C.c_uint64()
         self._check(self._lib.wld_exchange_buffer(self._h, which, C.byref(ptr), C.byref(nbytes)))
         typestr, item, dtype = ("<i4", 4, torch.int32) if which == L.EXCHANGE_HISTOGRAM else ("<f8", 8, torch.float64)
@@ -265,8 +278,7 @@ class Context:
 
             if chars.is_cuda:
                 flags |= L.INPUT_DEVICE
-                if not self._stream_set:
-                    self._check(self._lib.wld_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(chars.device).cuda_stream)))
+                self.adopt_torch_stream(chars.device)
             ptr, stride = C.c_void_p(chars.data_ptr()), (chars.stride(0) if chars.shape[0] > 1 else max(chars.shape[1], 1))
         self._keepalive = chars
         w = None if weights is None else np.ascontiguousarray(weights, np.float32)
