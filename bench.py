@@ -198,26 +198,31 @@ def run_reference(args):
 # our arm
 # ------------------------------------------------------------------------------------------------
 def check_mgpu_identity(wld, torch, dist, merge_on_device, local, rank, world):
-    """Before any multi-GPU number is believed: on a small side workload the merged N-rank output must be
-    byte-identical to one GPU computing the whole triangle (rank 0 runs that too)."""
+    """Before any multi-GPU number is believed: on two small side workloads the merged N-rank output must be
+    byte-identical to one GPU computing the whole triangle with the exact n-limb kernel (rank 0 runs that too).
+    The first (clonal, high LD) goes through the exact kernel on every rank, the second through the one-limb
+    screen + refinement on the even ranks and the exact kernel on the odd ones."""
+    from weightedld_b200.multi_gpu import sharded_stages
     from weightedld_b200.synth import make_alignment
-    chars = make_alignment(900, 6000, seed=41, block=120, clonal=True)
-    with wld.Context(local) as ctx:
-        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-        ctx.set_partition(rank, world)
-        from weightedld_b200.multi_gpu import sharded_stages
-        sharded_stages(ctx, torch.from_numpy(chars).cuda(), FILTER, rank, world)
-        n, _ = ctx.ld_pairs(R2_THRESHOLD)
-        merged = merge_on_device(ctx, n, rank, world)
     ok = 1
-    if rank == 0:
+    for chars, modes in ((make_alignment(900, 6000, seed=41, block=120, clonal=True), ("auto", "auto")),
+                         (make_alignment(900, 6000, seed=42, block=120), ("always", "never"))):
         with wld.Context(local) as ctx:
-            ctx.load_alignment(chars)
-            ctx.filter_sites(*FILTER)
-            ctx.henikoff()
-            n1, _ = ctx.ld_pairs(R2_THRESHOLD)
-            whole = ctx.fetch_pairs(n1)
-        ok = int(len(whole) > 1000 and merged.tobytes() == whole.tobytes())
+            ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+            ctx.set_partition(rank, world)
+            ctx.set_screen(modes[rank % 2])
+            sharded_stages(ctx, torch.from_numpy(chars).cuda(), FILTER, rank, world)
+            n, _ = ctx.ld_pairs(R2_THRESHOLD)
+            merged = merge_on_device(ctx, n, rank, world)
+        if rank == 0:
+            with wld.Context(local) as ctx:
+                ctx.set_screen("never")
+                ctx.load_alignment(chars)
+                ctx.filter_sites(*FILTER)
+                ctx.henikoff()
+                n1, _ = ctx.ld_pairs(R2_THRESHOLD)
+                whole = ctx.fetch_pairs(n1)
+            ok &= int(len(whole) > 1000 and merged.tobytes() == whole.tobytes())
     t = torch.tensor([ok], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     return bool(t.item())
@@ -264,6 +269,8 @@ def run_ours(args):
         ctx.set_pair_kernel(args.kernel)
     if args.ctas:
         ctx.set_cta_group(args.ctas)
+    if args.screen:
+        ctx.set_screen(args.screen)
 
     out_buf = {"t": None}
 
@@ -354,12 +361,16 @@ def run_ours(args):
     info = ctx.pair_info()
     pk = peaks()
     pair_ms = stages["pair"] / args.steps
-    algo_flop = 8.0 * n_seqs * info.n_limbs * state["done"]      # 8*N flop per pair per limb pass
+    # The dominant kernel: the exact n-limb Gram, or — screen + refine — the ONE-limb Gram that every pair goes through
+    # (its candidates, a few in 10^5 here, are recomputed exactly by pair_refine_kernel: stages_ms.pair_refine).
+    k_limbs = 1 if info.screen else info.n_limbs
+    algo_flop = 8.0 * n_seqs * k_limbs * state["done"]           # 8*N flop per pair per limb pass
     useful_flop = 8.0 * n_seqs * state["done"]
     achieved = algo_flop / (pair_ms * 1e-3) / 1e12
     if info.kernel == 2:
         ip = int8_peak()
-        peak, peak_src, kname = ip["sustained"], ip["source"] + ", sustained int8 figure (kernel timed inside a long step)", "pair_umma_kernel<NL, i8>"
+        peak, peak_src = ip["sustained"], ip["source"] + ", sustained int8 figure (kernel timed inside a long step)"
+        kname = "pair_umma_kernel<1, i8, screen>" if info.screen else "pair_umma_kernel<NL, i8>"
     else:
         peak, peak_src = pk["bf16_sustained"], pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)"
         kname = "pair_umma_kernel<NL, bf16>" if info.kernel == 0 else "pair_simt_kernel"
@@ -368,7 +379,8 @@ def run_ours(args):
             "peak_source": peak_src,
             "achieved_useful": useful_flop / (pair_ms * 1e-3) / 1e12,
             "executed": info.executed_flop / (pair_ms * 1e-3) / 1e12,
-            "algorithmic_flop_per_pair": 8 * n_seqs * info.n_limbs, "n_limbs": info.n_limbs, "limb_bits": info.limb_bits,
+            "algorithmic_flop_per_pair": 8 * n_seqs * k_limbs, "n_limbs": info.n_limbs, "kernel_limbs": k_limbs,
+            "limb_bits": info.limb_bits,
             "frac_of_nominal_dense_int8": (achieved / 4500.0) if info.kernel == 2 else None,  # 4.5 POP/s data-sheet figure
             "kernel_ms": pair_ms, "traffic": None,
             "tile_schedule": {0: "round-robin", 1: "per-L2-die contiguous halves of the strip-rasterised tile list",
@@ -379,7 +391,7 @@ def run_ours(args):
     prof = ROOT / "profiles" / "pair_umma_traffic.json"
     if prof.exists():
         try:
-            roof["traffic"] = json.loads(prof.read_text()).get(args.workload, {}).get(str(world))
+            roof["traffic"] = json.loads(prof.read_text()).get(args.workload + ("_screen" if info.screen else ""), {}).get(str(world))
         except Exception:
             pass
 
@@ -388,7 +400,7 @@ def run_ours(args):
     es = 1 if info.kernel == 2 else 2
     cells_raw, cells_kept = float(n_seqs) * n_cols, float(n_seqs) * n_kept
     hbm_bytes = {"histogram": cells_raw, "filter": cells_raw + cells_kept, "henikoff": cells_kept,
-                 "pair_prep": 2 * cells_kept + cells_kept * es * (2 + 2 * info.n_limbs) / max(world, 1)}
+                 "pair_prep": 2 * cells_kept + cells_kept * es * (2 + 2 * k_limbs) / max(world, 1)}
     hbm = {k: {"bytes": b, "ms": stages[k] / args.steps, "gbs": b / (stages[k] / args.steps * 1e-3) / 1e9,
                "frac_of_measured_hbm": b / (stages[k] / args.steps * 1e-3) / 1e9 / pk["hbm"]}
            for k, b in hbm_bytes.items() if stages[k] > 0}
@@ -406,6 +418,11 @@ def run_ours(args):
                        "parallelism": f"triangle-partition x{world}", "l2": "inputs larger than L2 (no flush needed)"},
             "stages_ms": {k: v / args.steps for k, v in stages.items()},
             "roofline": roof,
+            "screen": {"used": bool(info.screen), "candidates": int(info.screen_candidates), "top_min": int(info.screen_top_min),
+                       "sample_pairs": int(info.sample_pairs), "sample_candidates": int(info.sample_candidates),
+                       "reruns": int(info.screen_reruns),
+                       "note": "one-limb Gram + rigorous r2 bound, candidates recomputed exactly (wld_set_screen); rank 0's figures; "
+                               "survivors bit-identical to the exact n-limb kernel (tests/test_screen_refine.py)"},
             "hbm_stages": hbm,
             "e2e": {"value": total_pairs / (ms_e2e * 1e-3), "unit": "site-pairs/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(chars_np.nbytes),  # whole job: each rank copies 1/N of the rows
@@ -445,6 +462,7 @@ def main():
     ap.add_argument("--limbs", type=int, default=0)
     ap.add_argument("--kernel", default="", choices=["", "umma", "bf16", "i8", "simt"])
     ap.add_argument("--ctas", type=int, default=0, choices=[0, 1, 2], help="tcgen05 cta_group (0 = library default)")
+    ap.add_argument("--screen", default="", choices=["", "auto", "never", "always"], help="wld_set_screen (default: library default = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--profile", action="store_true", help="profiling run: honour --warmup < 3, skip the e2e leg (numbers are not bench values)")
     args = ap.parse_args()

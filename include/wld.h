@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define WLD_ABI_VERSION 2
+#define WLD_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define WLD_API __attribute__((visibility("default")))
@@ -99,7 +99,9 @@ enum {
   WLD_STAGE_PAIR_PREP = 4, /* weight quantisation + indicator / limb operand expansion */
   WLD_STAGE_PAIR = 5,      /* Gram + epilogue + compaction kernel(s) */
   WLD_STAGE_ORDER = 6,     /* survivors into the reference's output order + parent indices (first fetch after a pair stage) */
-  WLD_STAGE_COUNT = 7
+  WLD_STAGE_PAIR_SAMPLE = 7, /* the one-limb screen over a sample of the tiles (decides screen + refine vs. the exact kernel) */
+  WLD_STAGE_PAIR_REFINE = 8, /* exact sums + statistics of the screen's candidates */
+  WLD_STAGE_COUNT = 9
 };
 
 /* Progress callback of all_weighted_ld_pairs (lib.rs:582): receives the number of site pairs
@@ -156,6 +158,18 @@ WLD_API int wld_set_compat(wld_ctx* ctx, int mode);
 WLD_API int wld_set_cta_group(wld_ctx* ctx, int ctas);
 /* Initial capacity (in pairs) of the device survivor buffer; it grows automatically. */
 WLD_API int wld_set_pair_capacity(wld_ctx* ctx, uint64_t pairs);
+/* Screen + refine.  With an r2 threshold most site pairs of a real alignment are far below it, and whether a
+ * pair can reach it is decided by far fewer weight bits than its statistics need.  The library can therefore run
+ * the Gram with ONE limb (the top 8 bits of every fixed-point weight; a third / a quarter of the tensor work),
+ * bound r2 from above rigorously from those sums (the truncated part of every weight is below 1/top_min of what
+ * was summed), and recompute only the pairs that bound does not rule out — exactly, from the code matrix and the
+ * full integer weights, through the same f64 statistics of lib.rs:482-518.  The survivors are the same records,
+ * bit for bit, as the exact n-limb kernel's (all_weighted_ld_pairs, lib.rs:578-684).
+ *   mode 0: never; 1 (default): when it pays — the candidate rate is measured on a sample of the tiles first,
+ *   and high-LD inputs (more than 1 pair in 256 a candidate) go straight to the exact kernel; 2: whenever the
+ *   bound is valid (tests).  The screen needs the u8 kernel, the Rust dialect, a positive threshold, at least
+ *   two limbs and top_min >= 32; otherwise the exact kernel runs.  wld_pair_info.screen tells which ran. */
+WLD_API int wld_set_screen(wld_ctx* ctx, int mode);
 
 /* ---- stage 1: encode + histogram + filter -------------------------------------------------- */
 /* SiteSet::from_multiseq (lib.rs:176-206) for an alignment given as n_seqs rows of n_cols bytes,
@@ -269,11 +283,15 @@ WLD_API int wld_get_pair_weights(wld_ctx* ctx, double* out, int64_t cap);
 WLD_API uint64_t wld_pair_order_key(int64_t n_kept, uint32_t kept_a, uint32_t kept_b);
 /* The pair-stage schedule, host only (no GPU needed): the upper-triangular tile list of partition
  * `part` of `nparts` exactly as wld_ld_pairs runs it (replaces rayon's fan-out over triu_index,
- * lib.rs:623-637).  A tile covers kept sites [tm*64, tm*64+64) x [tn*TN, tn*TN+TN), TN =
- * 2*floor(128/(2*n_limbs)); only pairs a < b inside it are evaluated.  Writes 2 uint32 (tm, tn) per
- * tile into tiles_mn (may be NULL to count), n_tiles = number of tiles, n_pairs = site pairs they
- * cover.  sm_count sizes the round-robin blocks (148 on B200). */
-WLD_API int wld_plan_tiles(int64_t n_kept, int n_limbs, int cta_group, int part, int nparts, int sm_count, uint32_t* tiles_mn,
+ * lib.rs:623-637).  Partitions are contiguous, equally long ranges of a canonical list of 128 x 128-site
+ * cells (strips of 8 cell columns), so the site pairs a partition owns do not depend on the kernel variant.
+ * A tile of a variant covers kept sites [tm*TM, tm*TM+TM) x [j_lo, j_hi), TM = 64*cta_group, with
+ * [j_lo, j_hi) the part of [tn*TN, tn*TN+TN), TN = 2*floor(128/(2*n_limbs)), that belongs to the partition;
+ * only pairs a < b inside it are evaluated (a tile that straddles a partition boundary appears in both
+ * partitions with disjoint windows).  n_limbs = 1 is the schedule of the one-limb screen.  Writes 4 uint32
+ * (tm, tn, j_lo, j_hi) per tile into tiles (may be NULL to count), n_tiles = number of tiles, n_pairs =
+ * site pairs they cover.  sm_count is unused (kept for ABI stability). */
+WLD_API int wld_plan_tiles(int64_t n_kept, int n_limbs, int cta_group, int part, int nparts, int sm_count, uint32_t* tiles,
                            uint64_t cap_tiles, uint64_t* n_tiles, uint64_t* n_pairs);
 
 /* ---- introspection ------------------------------------------------------------------------- */
@@ -297,10 +315,17 @@ typedef struct wld_pair_info {
   int32_t die_sms[2];      /* SMs found on each L2 die (0, 0 when the map could not be established) */
   int32_t gain_bits;       /* G, see wld_set_gain_bits */
   int32_t weight_span_log2;/* x: the smallest nonzero weight lies in [2^-(x+1), 2^-x) of the largest */
-  int32_t reserved;
+  int32_t screen;          /* 0: every pair went through the exact n-limb kernel; 1: one-limb screen + exact
+                              refinement of its candidates (same survivors, bit for bit; see wld_set_screen) */
   double weight_rel_err;   /* realised max over nonzero weights of |q/scale - w/max| / (w/max).  A priori:
                               <= 2^-B when x <= G, else <= 2^(x-G-B).  Every weighted sum of lib.rs:469-479
                               (all terms >= 0) carries at most this relative error before the f64 epilogue. */
+  /* screen + refine bookkeeping (all 0 when the screen was not considered) */
+  int64_t screen_candidates;   /* site pairs the screen could not rule out (each recomputed exactly) */
+  int64_t sample_pairs;        /* site pairs of the sampling launch that chose the path */
+  int64_t sample_candidates;   /* ... and how many of them were candidates */
+  int32_t screen_top_min;      /* smallest top limb of a nonzero weight: the screen's bound is x <= y <= x (1 + 1/top_min) */
+  int32_t screen_reruns;       /* times the screen was repeated because the candidate buffer was too small */
 } wld_pair_info;
 WLD_API int wld_get_pair_info(wld_ctx* ctx, wld_pair_info* out);
 

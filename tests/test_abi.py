@@ -27,7 +27,7 @@ def test_header_symbols_exported(lib):
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.wld_abi_version() == 2
+    assert lib.wld_abi_version() == 3
 
 
 def test_struct_layout():

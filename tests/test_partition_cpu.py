@@ -12,47 +12,77 @@ import pytest
 
 
 def tile_owner_mask(wld, n_kept, a, b, tiles, tile_m, tile_n):
-    own = np.zeros((n_kept // tile_m + 1, n_kept // tile_n + 1), bool)
-    own[tiles[:, 0], tiles[:, 1]] = True
-    return own[a // tile_m, b // tile_n]
+    """Which pairs (a < b, kept indices) fall into this partition's tiles: inside a tile's rows AND its window."""
+    own = np.zeros(len(a), bool)
+    for tm, tn, j_lo, j_hi in tiles.astype(np.int64):
+        own |= (a // tile_m == tm) & (b // tile_n == tn) & (b >= j_lo) & (b < j_hi)
+    return own
+
+
+def pair_cover(tiles, n_kept, tile_m, tile_n):
+    """(n_kept, n_kept) count of how many tiles evaluate pair (a, b), a < b."""
+    seen = np.zeros((n_kept, n_kept), np.int32)
+    for tm, tn, j_lo, j_hi in tiles.astype(np.int64):
+        assert tn * tile_n <= j_lo < j_hi <= min(n_kept, (tn + 1) * tile_n)
+        i0, i1 = tm * tile_m, min(n_kept, (tm + 1) * tile_m)
+        seen[i0:i1, j_lo:j_hi] += 1
+    return np.triu(seen, 1)
 
 
 @pytest.mark.parametrize("ctas", [1, 2])
 @pytest.mark.parametrize("n_limbs,tile_n", [(1, 128), (2, 64), (3, 42), (4, 32)])
-@pytest.mark.parametrize("n_kept", [1, 2, 63, 64, 65, 700, 5000])
+@pytest.mark.parametrize("n_kept", [1, 2, 63, 64, 65, 129, 700, 1500])
 def test_plan_covers_each_pair_once(n_kept, n_limbs, tile_n, ctas):
     import weightedld_b200 as wld
     tile_m = 64 * ctas
+    want = np.triu(np.ones((n_kept, n_kept), np.int32), 1)
     for nparts in (1, 2, 3, 8):
-        seen = np.zeros((n_kept // tile_m + 1, n_kept // tile_n + 1), np.int32)
+        seen = np.zeros((n_kept, n_kept), np.int32)
         total = 0
         for part in range(nparts):
             tiles, pairs = wld.plan_tiles(n_kept, n_limbs, part, nparts, sm_count=4, cta_group=ctas)
+            cover = pair_cover(tiles, n_kept, tile_m, tile_n)
+            assert cover.sum() == pairs          # the pair count the kernel must report
+            assert len(tiles) == 0 or all(cover[tm * tile_m:(tm + 1) * tile_m, lo:hi].any() for tm, _, lo, hi in tiles.astype(np.int64))
+            seen += cover
             total += pairs
-            if len(tiles):
-                np.add.at(seen, (tiles[:, 0], tiles[:, 1]), 1)
         assert total == n_kept * (n_kept - 1) // 2
-        assert seen.max() <= 1
-        # every tile that contains a pair a < b is present
-        for tm in range(seen.shape[0]):
-            for tn in range(seen.shape[1]):
-                j_last = min(n_kept, (tn + 1) * tile_n) - 1
-                needed = tm * tile_m < j_last and tm * tile_m < n_kept and tn * tile_n < n_kept
-                assert bool(seen[tm, tn]) == needed, (tm, tn)
+        assert np.array_equal(seen, want)        # every pair a < b exactly once over the partitions
+
+
+@pytest.mark.parametrize("n_kept,nparts", [(700, 2), (1500, 3), (5000, 8)])
+def test_partitions_own_the_same_pairs_for_every_kernel_variant(n_kept, nparts):
+    """A GPU may run the one-limb screen (128-site tiles) or the exact kernel (42- or 32-site tiles) on its own:
+    the site pairs of partition p must not depend on that choice."""
+    import weightedld_b200 as wld
+    rng = np.random.default_rng(n_kept)
+    a = rng.integers(0, n_kept - 1, 20000)
+    b = rng.integers(0, n_kept, 20000)
+    a, b = np.minimum(a, b), np.maximum(a, b)
+    a, b = a[a < b], b[a < b]
+    for part in range(nparts):
+        masks = []
+        for n_limbs, tile_n in ((1, 128), (2, 64), (3, 42), (4, 32)):
+            for ctas in (1, 2):
+                tiles, _ = wld.plan_tiles(n_kept, n_limbs, part, nparts, cta_group=ctas)
+                masks.append(tile_owner_mask(wld, n_kept, a, b, tiles, 64 * ctas, tile_n))
+        assert all(np.array_equal(masks[0], m) for m in masks[1:])
 
 
 def test_plan_is_balanced_at_config5():
     import weightedld_b200 as wld
     for ctas in (1, 2):
         for nparts in (2, 4, 8):
-            plans = [wld.plan_tiles(48601, 3, p, nparts, cta_group=ctas) for p in range(nparts)]
-            pairs = [p[1] for p in plans]
-            tiles = [len(p[0]) for p in plans]
-            assert max(tiles) - min(tiles) <= 1                   # MMA work: contiguous ranges of equal tile count
-            assert max(pairs) / min(pairs) < 1.02                 # site pairs (diagonal tiles hold fewer)
-            ranges = [(int(tl[:, 1].min()), int(tl[:, 1].max())) for tl, _ in plans]
-            for (lo0, hi0), (lo1, hi1) in zip(ranges, ranges[1:]):  # contiguous runs: neighbours share at most one strip
-                assert lo0 <= lo1 and hi0 <= hi1 and lo1 >= hi0 - 7
+            for n_limbs in (1, 3):
+                plans = [wld.plan_tiles(48601, n_limbs, p, nparts, cta_group=ctas) for p in range(nparts)]
+                pairs = [p[1] for p in plans]
+                tiles = [len(p[0]) for p in plans]
+                # equal ranges of the 128 x 128-site cell list: tensor work within one cell row of tiles, pairs within 2 %
+                assert max(tiles) / min(tiles) < (1.001 if n_limbs == 1 else 1.02)  # exact-kernel tiles straddling a partition edge run in both
+                assert max(pairs) / min(pairs) < 1.02                 # site pairs (diagonal tiles hold fewer)
+                ranges = [(int(tl[:, 2].min()), int(tl[:, 3].max())) for tl, _ in plans]
+                for (lo0, hi0), (lo1, hi1) in zip(ranges, ranges[1:]):  # contiguous runs: neighbours share at most one strip of 1024 sites
+                    assert lo0 <= lo1 and hi0 <= hi1 and lo1 >= hi0 - 1024
 
 
 def _worker(rank, world, port, n_kept, q):

@@ -24,8 +24,9 @@ FETCH_PARENT_INDEX, FETCH_KEPT_INDEX, FETCH_UNORDERED, FETCH_DEVICE = 0, 1, 2, 4
 PAIR_KERNEL_UMMA, PAIR_KERNEL_SIMT, PAIR_KERNEL_UMMA_I8 = 0, 1, 2
 COMPAT_RUST, COMPAT_PYTHON = 0, 1
 EXCHANGE_HISTOGRAM, EXCHANGE_WEIGHT_SUMS = 0, 1
-STAGE_LOAD, STAGE_HISTOGRAM, STAGE_FILTER, STAGE_HENIKOFF, STAGE_PAIR_PREP, STAGE_PAIR, STAGE_ORDER = range(7)
-STAGE_NAMES = ["load", "histogram", "filter", "henikoff", "pair_prep", "pair", "order"]
+(STAGE_LOAD, STAGE_HISTOGRAM, STAGE_FILTER, STAGE_HENIKOFF, STAGE_PAIR_PREP, STAGE_PAIR, STAGE_ORDER, STAGE_PAIR_SAMPLE,
+ STAGE_PAIR_REFINE) = range(9)
+STAGE_NAMES = ["load", "histogram", "filter", "henikoff", "pair_prep", "pair", "order", "pair_sample", "pair_refine"]
 STATUS_NAMES = {0: "OK", 1: "INVALID", 2: "STATE", 3: "CUDA", 4: "NOMEM", 5: "UNSUPPORTED", 6: "PANIC"}
 
 PROGRESS_FN = C.CFUNCTYPE(None, C.c_uint64, C.c_void_p)
@@ -36,7 +37,9 @@ class PairInfo(C.Structure):
         ("kernel", C.c_int32), ("n_limbs", C.c_int32), ("limb_bits", C.c_int32), ("weight_bits", C.c_int32),
         ("k_padded", C.c_int64), ("tiles", C.c_int64), ("tile_sites_m", C.c_int64), ("tile_sites_n", C.c_int64),
         ("executed_flop", C.c_double), ("die_schedule", C.c_int32), ("die_sms", C.c_int32 * 2), ("gain_bits", C.c_int32),
-        ("weight_span_log2", C.c_int32), ("reserved", C.c_int32), ("weight_rel_err", C.c_double),
+        ("weight_span_log2", C.c_int32), ("screen", C.c_int32), ("weight_rel_err", C.c_double),
+        ("screen_candidates", C.c_int64), ("sample_pairs", C.c_int64), ("sample_candidates", C.c_int64),
+        ("screen_top_min", C.c_int32), ("screen_reruns", C.c_int32),
     ]
 
 
@@ -61,6 +64,7 @@ SIGNATURES = {
     "wld_get_pair_weights": (_int, [_vp, _vp, _i64]),
     "wld_set_pair_kernel": (_int, [_vp, _int]),
     "wld_set_pair_capacity": (_int, [_vp, _u64]),
+    "wld_set_screen": (_int, [_vp, _int]),
     "wld_load_alignment": (_int, [_vp, _vp, _i64, _i64, _i64, _int]),
     "wld_load_alignment_rows": (_int, [_vp, _vp, _i64, _i64, _int]),
     "wld_filter_sites": (_int, [_vp, C.c_float, C.c_float, C.c_float, C.POINTER(_i64)]),

@@ -120,6 +120,14 @@ class Context:
     def set_pair_capacity(self, pairs: int):
         self._check(self._lib.wld_set_pair_capacity(self._h, pairs))
 
+    def set_screen(self, mode: int | str):
+        """One-limb screen + exact refinement of its candidates (wld_set_screen): 'never' / 0, 'auto' / 1
+        (default: chosen from the candidate rate of a sample of the tiles), 'always' / 2.  Same survivors, bit for
+        bit, as the exact n-limb kernel."""
+        if isinstance(mode, str):
+            mode = {"never": 0, "off": 0, "auto": 1, "always": 2}[mode]
+        self._check(self._lib.wld_set_screen(self._h, mode))
+
     # ---- stage 1
     def load_alignment(self, chars, codes: bool = False):
         """chars: (n_seqs, n_cols) uint8 — numpy array (host, copied) or a CUDA torch tensor
@@ -362,14 +370,15 @@ def pair_order_key(n_kept: int, kept_a, kept_b) -> np.ndarray:
 
 def plan_tiles(n_kept: int, n_limbs: int = 3, part: int = 0, nparts: int = 1, sm_count: int = 148,
                cta_group: int = 2):
-    """Host-only pair-stage schedule (wld_plan_tiles): ((n_tiles, 2) uint32 tile coordinates,
-    site pairs covered).  Needs no GPU."""
+    """Host-only pair-stage schedule (wld_plan_tiles): ((n_tiles, 4) uint32 {M tile, N tile, first site j,
+    end site j} — the window of site columns of the tile that belongs to this partition —, site pairs covered).
+    n_limbs = 1 is the schedule of the one-limb screen.  Needs no GPU."""
     lib = L.load()
     n, pairs = C.c_uint64(), C.c_uint64()
     rc = lib.wld_plan_tiles(n_kept, n_limbs, cta_group, part, nparts, sm_count, None, 0, C.byref(n), C.byref(pairs))
     if rc != L.WLD_OK:
         raise WldError(rc, "bad tile plan arguments")
-    tiles = np.empty((n.value, 2), np.uint32)
+    tiles = np.empty((n.value, 4), np.uint32)
     rc = lib.wld_plan_tiles(n_kept, n_limbs, cta_group, part, nparts, sm_count, _ptr(tiles), n.value, C.byref(n), C.byref(pairs))
     if rc != L.WLD_OK:
         raise WldError(rc, "bad tile plan arguments")

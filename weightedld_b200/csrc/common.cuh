@@ -68,10 +68,22 @@ struct QuantDecision {
   int32_t flags;       // bit0: invalid weights (negative, NaN, inf, all zero); bit1: all equal; bit2: cannot be made exact
   int32_t n_limbs, limb_bits, gain_bits;
   int32_t span_log2;   // x: the smallest nonzero weight lies in [2^-(x+1), 2^-x) of the maximum
-  int32_t pad;
+  int32_t top_min;     // smallest TOP limb among the nonzero fixed-point weights (0: some weight has an empty top limb)
   double weight_sum;   // sum of q
   double rel_err;      // max over nonzero weights of |q / (2^G (2^B - 1)) - u| / u  (realised)
   unsigned long long limb_sums[4];
+  float kappa;         // (1 + 1/top_min)^2 - 1 + 1e-5, rounded up: the screen's widening of |P - Q| (ld_screen_f32)
+  float pad2;
+};
+
+// A tile schedule of the tcgen05 pair kernel kept on the device (pair_umma.cu, ensure_tile_plan).
+struct DevPlan {
+  int64_t key[5] = {-1, -1, -1, -1, -1};  // n_kept, n_limbs, part, nparts, cta_group
+  DevBuf tiles;                            // uint4 [n_tiles]: {M tile, N tile, first site j, end site j}
+  int64_t n_tiles = 0;
+  uint64_t pairs = 0;
+  int64_t x[2] = {0, -1}, y[2] = {0, -1};  // min / max M-tile and N-tile index
+  int64_t tile_m = 0, tile_n = 0;
 };
 
 }  // namespace wld
@@ -134,11 +146,20 @@ struct wld_ctx {
   wld::DevBuf gain8;               // u8 [ldc]       per-sequence gain 2^(G-e) carried by the indicator operand
   wld::DevBuf quant;               // QuantDecision (device)
   wld::QuantDecision* quant_host = nullptr;  // pinned mirror
+  unsigned long long* sample_host = nullptr; // pinned: {candidates, pairs} of the sampling launch (behind quant_host)
   int quant_span_log2 = 0;
   double quant_rel_err = 0.0;
   wld::DevBuf opA;                 // bf16 [a_rows][k_padded]
   wld::DevBuf opB;                 // bf16 [b_groups*128][k_padded]
-  wld::DevBuf tiles;               // uint2 [n_tiles]
+  wld::DevBuf simt_tiles;          // uint2 [n_tiles] of the CUDA-core verification kernel
+  wld::DevPlan plans[2];           // tcgen05 schedules: [0] the exact kernel (n_limbs limbs), [1] the one-limb screen
+  // screen + refine (pair_umma.cu kScreen, pair_refine.cu)
+  int screen_opt = 1;              // wld_set_screen: 0 never, 1 automatic (sampled candidate rate), 2 always when valid
+  wld::DevBuf qi;                  // u64 [ldc]      the fixed-point weights as integers (pair_refine.cu)
+  wld::DevBuf opB1;                // u8 [b1_groups*128][k_padded]: indicator x TOP limb, one-limb layout (64 sites / group)
+  wld::DevBuf cand;                // uint2 [cand_cap] candidate site pairs of the screen
+  uint64_t cand_cap = 0;
+  int quant_top_min = 0;
   wld::DevBuf pairs;               // wld_pair [pair_cap]
   wld::DevBuf counters;            // u64 [4]: survivors, pairs_done, ...
   wld::DevBuf py_aux;              // uint2 [n_kept] {n5, margin}: WLD_COMPAT_PYTHON only (pair_python.cu)
@@ -155,11 +176,7 @@ struct wld_ctx {
   uint64_t pairs_computed = 0;
   wld_pair_info info{};
   float last_thr = 0.f;
-  // cached tile schedule on the device (key: n_kept, n_limbs, part, nparts, kernel)
-  int64_t plan_key[5] = {-1, -1, -1, -1, -1};
-  int64_t plan_tiles_n = 0;
-  uint64_t plan_pairs = 0;
-  int64_t plan_x[2] = {0, -1}, plan_y[2] = {0, -1};  // min / max M-tile and N-tile index of this partition's tiles
+  uint64_t plan_pairs = 0;         // site pairs of this partition (identical for every schedule of it)
   double weight_sum = 0.0;         // sum of the fixed-point weights q (upper bound of every pair's T)
 
   wld::StageTimer timers[WLD_STAGE_COUNT];
@@ -214,12 +231,17 @@ int run_filter(wld_ctx* c, int mode, float min_acgt, float min_minor, float max_
                double py_min_variability, ScopedStageTimer& tm);           // encode_filter.cu
 int run_henikoff(wld_ctx* c, ScopedStageTimer& tm, bool finish);           // henikoff.cu
 int run_henikoff_finish(wld_ctx* c, ScopedStageTimer& tm);                 // henikoff.cu: max + normalise
-int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm);                       // pair_prep.cu
+int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm, bool try_screen);      // pair_prep.cu: quantise, indicator operand (+ the screen's operand)
+int finish_quant(wld_ctx* c);                                              // pair_prep.cu: read the quantiser's decision back (synchronises)
+int run_expand_limbs(wld_ctx* c, ScopedStageTimer& tm, bool screen);       // pair_prep.cu: limb operand (all limbs / top limb only)
 // The pair launchers bracket ONLY the kernel launch with the WLD_STAGE_PAIR timer (host-side
 // planning and the tile-list upload happen before the start event).
 int run_pair_simt(wld_ctx* c, float thr);                                  // pair_simt.cu
-int run_pair_umma(wld_ctx* c, float thr);                                  // pair_umma.cu
-int ensure_tile_plan(wld_ctx* c);                                          // pair_umma.cu (needs c->geom.n_limbs)
+// mode 0: exact kernel (all limbs); 1: one-limb screen over every tile, candidates -> c->cand;
+// 2: the screen over a sample of the tiles, counting only (counters[8..9])
+int run_pair_umma(wld_ctx* c, float thr, int mode);                        // pair_umma.cu
+int ensure_tile_plan(wld_ctx* c, int which);                               // pair_umma.cu (which: 0 exact, 1 screen)
+int run_pair_refine(wld_ctx* c, float thr);                                // pair_refine.cu: exact statistics of the candidates
 int run_pair_order(wld_ctx* c, bool ordered, bool parent);                 // pair_order.cu
 const std::vector<uint8_t>& die_map(wld_ctx* c);                            // die_map.cu: SM -> L2 die (empty = unknown)
 int run_pair_python_prepare(wld_ctx* c);                                   // pair_python.cu
@@ -229,7 +251,7 @@ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 // Upper-triangular tile schedule of the tcgen05 pair kernel (pair_plan.cpp part of wld_api.cu).
 struct TilePlan {
-  std::vector<uint2> tiles;
+  std::vector<uint4> tiles;  // {M tile, N tile, first site j of the tile's window, end site j}
   uint64_t pairs = 0;
   int64_t tile_m = 64, tile_n = 42;
 };

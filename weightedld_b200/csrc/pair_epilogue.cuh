@@ -66,6 +66,24 @@ __device__ __forceinline__ bool ld_prefilter_f32(float AB, float Ab, float aB, f
   return den > 0.0f && (thr_negative || n * n >= thr_lo_f * den);
 }
 
+// One-limb screen (pair_umma.cu, kScreen).  Inputs: the four sums of gain x TOP limb of the fixed-point weights,
+// exact integers below 2^31 converted to fp32 (relative error <= 2^-24 each; their total is <= 2^31 because the
+// quantiser bounds every limb column sum).  With top_min the smallest top limb of a nonzero weight, the true sums
+// y (in units of 2^(bits (NL-1))) satisfy x <= y <= x (1 + eta), eta = 1/top_min, hence with P = AB ab, Q = Ab aB:
+//     |y1 y4 - y2 y3| <= |P - Q| + ((1 + eta)^2 - 1) max(P, Q)      and      every marginal of y >= that of x,
+// so  r2(y) <= (|P - Q| + kappa max(P, Q))^2 / (A a B b)  with kappa = (1 + eta)^2 - 1 + 1e-5; the 1e-5 covers the
+// fp32 roundings of P, Q and their difference (<= 8 * 2^-24 (P + Q)), and thr_lo_f (lowered by 1e-5 relative,
+// pair_umma.cu) covers those of the denominator and of the square.  x = 0 implies y = 0, so an empty marginal
+// (NaN in the reference, dropped by lib.rs:660) is decided exactly.  No overflow: P, Q < 2^62, n^2 < 2^126,
+// A a, B b <= 2^60.  A pair the exact path would keep therefore always passes; the test is symmetric under
+// exchanging the two rows (AB, Ab) <-> (aB, ab).
+__device__ __forceinline__ bool ld_screen_f32(float AB, float Ab, float aB, float ab, float kappa, float thr_lo_f) {
+  const float P = AB * ab, Q = Ab * aB;
+  const float n = fabsf(P - Q) + kappa * fmaxf(P, Q);
+  const float den1 = (AB + Ab) * (aB + ab), den2 = (AB + aB) * (Ab + ab);
+  return den1 > 0.0f && den2 > 0.0f && n * n >= (thr_lo_f * den1) * den2;
+}
+
 __host__ __device__ inline double ld_thr_lo(float thr) {
   const double t = (double)thr;
   return t - (t < 0 ? -t : t) * 1e-6 - 1e-24;
@@ -129,6 +147,26 @@ __device__ __forceinline__ bool ld_stats_exact(double AB, double Ab, double aB, 
 __device__ __forceinline__ bool py_flagged(const uint2* __restrict__ aux, uint32_t i, uint32_t j) {
   const uint2 a = aux[i], b = aux[j];
   return (b.x > 0u && b.x >= a.y) || (a.x > 0u && a.x >= b.y);
+}
+
+// Candidates of the screen: kept-site index pairs, compacted like the survivors (count may exceed cap: the host
+// then grows the buffer and repeats the screen; cap = 0 just counts).
+struct CandOut {
+  uint2* buf;
+  unsigned long long* count;
+  unsigned long long cap;
+};
+__device__ __forceinline__ void emit_cand_warp(bool cand, uint32_t site_a, uint32_t site_b, const CandOut& out) {
+  const unsigned ballot = __ballot_sync(0xffffffffu, cand);
+  if (ballot == 0) return;
+  const int lane = threadIdx.x & 31;
+  unsigned long long base = 0;
+  if (lane == __ffs(ballot) - 1) base = atomicAdd(out.count, (unsigned long long)__popc(ballot));
+  base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
+  if (cand) {
+    const unsigned long long slot = base + __popc(ballot & ((1u << lane) - 1u));
+    if (slot < out.cap) out.buf[slot] = make_uint2(site_a, site_b);
+  }
 }
 
 // Warp-aggregated compaction: one atomicAdd per warp, survivors written to consecutive slots.

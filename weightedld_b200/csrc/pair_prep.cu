@@ -76,6 +76,7 @@ __device__ __forceinline__ T block_reduce_1024(T v, T* s_buf, Op op) {
 __global__ void __launch_bounds__(1024) quantize_kernel(const float* __restrict__ w, int64_t n_seqs, int64_t ldc,
                                                         int nl_opt, int gain_opt, int bits_opt, unsigned long long exact_limit,
                                                         int may_narrow, double* __restrict__ q,
+                                                        unsigned long long* __restrict__ qi,
                                                         uint16_t* __restrict__ limbs, uint8_t* __restrict__ limbs8,
                                                         uint8_t* __restrict__ gain8, QuantDecision* __restrict__ out) {
   __shared__ float s_f[32];
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(1024) quantize_kernel(const float* __restrict_
   const double scale = B > 0 ? (double)((1ull << B) - 1ull) : 1.0;
   const uint32_t mask = bits > 0 ? (1u << bits) - 1u : 1u;
   double err = 0.0;
+  unsigned top_min = 0xffffffffu;  // smallest top limb of a nonzero fixed-point weight (the screen's bound, pair_epilogue.cuh)
   for (int64_t s = threadIdx.x; s < ldc; s += blockDim.x) {
     unsigned long long m = 0;
     int e = G;
@@ -172,7 +174,9 @@ __global__ void __launch_bounds__(1024) quantize_kernel(const float* __restrict_
       if (u > 0.0) err = fmax(err, fabs(ldexp((double)m, -e) / scale - u) / u);
     }
     q[s] = (double)(m * g);
+    qi[s] = m * g;
     gain8[s] = (uint8_t)g;
+    if (m > 0) top_min = min(top_min, (unsigned)(m >> (bits * (nl - 1))) & mask);
     for (int l = 0; l < nl; ++l) {
       const uint32_t v = (uint32_t)(m >> (bits * (nl - 1 - l))) & mask;
       limbs[(int64_t)l * ldc + s] = (uint16_t)v;  // raw limb value 0..255; converted at expansion
@@ -181,8 +185,17 @@ __global__ void __launch_bounds__(1024) quantize_kernel(const float* __restrict_
   }
   const unsigned long long err_bits = block_reduce_1024((unsigned long long)__double_as_longlong(err), s_u,
                                                         [](unsigned long long a, unsigned long long b) { return max(a, b); });
+  top_min = (unsigned)block_reduce_1024((unsigned long long)top_min, s_u,
+                                        [](unsigned long long a, unsigned long long b) { return min(a, b); });
   if (threadIdx.x == 0) {
     QuantDecision d{};
+    d.top_min = top_min == 0xffffffffu ? 0 : (int)top_min;
+    {  // kappa of ld_screen_f32: (1 + 1/top_min)^2 - 1 + 1e-5, rounded up
+      const double eta = 1.0 / (double)max(d.top_min, 1);
+      float k = (float)((1.0 + eta) * (1.0 + eta) - 1.0 + 1e-5);
+      if ((double)k < (1.0 + eta) * (1.0 + eta) - 1.0 + 1e-5) k = __uint_as_float(__float_as_uint(k) + 1u);
+      d.kappa = k;
+    }
     d.flags = (all_equal ? 2 : 0) | (unsupported ? 4 : 0);
     d.n_limbs = nl;
     d.limb_bits = bits;
@@ -350,33 +363,13 @@ __global__ void __launch_bounds__(256) expand_b_kernel(const uint8_t* __restrict
 
 }  // namespace
 
-int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm) {
+// Reads the quantiser's decision back (one synchronisation) and fixes the geometry of the exact kernel.
+int finish_quant(wld_ctx* c) {
   PairGeom& gm = c->geom;
-  const int64_t n = c->n_seqs, L = c->n_kept;
-  const bool i8 = c->pair_kernel == WLD_PAIR_KERNEL_UMMA_I8;
-  // exact-accumulation limit of a Gram entry: fp32 holds integers up to 2^24, s32 up to 2^31-1; the FP64
-  // verification kernel only needs the sum of all q below 2^53 (checked by the quantiser for every kernel)
-  const unsigned long long exact_limit = c->pair_kernel == WLD_PAIR_KERNEL_SIMT ? (1ull << 53)
-                                         : i8                                   ? ((1ull << 31) - 1)
-                                                                                : (1ull << 24);
-
-  WLD_CUDA(c, c->q.ensure(sizeof(double) * (size_t)c->ldc));
-  WLD_CUDA(c, c->limbs.ensure((sizeof(uint16_t) + 1) * 4 * (size_t)c->ldc));  // u16 [4][ldc] then u8 [4][ldc]
-  WLD_CUDA(c, c->gain8.ensure((size_t)c->ldc));
-  WLD_CUDA(c, c->quant.ensure(sizeof(QuantDecision)));
-  WLD_CUDA(c, c->counters.ensure(sizeof(unsigned long long) * 16));
-  WLD_CUDA(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream));
-  if (!c->quant_host) WLD_CUDA(c, cudaMallocHost(&c->quant_host, sizeof(QuantDecision)));
-
-  // One launch quantises the weights AND decides limbs / limb width / gain bits; one read-back tells the host.
-  quantize_kernel<<<1, 1024, 0, c->stream>>>(c->w32.as<float>(), n, c->ldc, c->n_limbs_opt, c->gain_opt, c->limb_bits_opt, exact_limit,
-                                             c->pair_kernel == WLD_PAIR_KERNEL_UMMA ? 1 : 0, c->q.as<double>(),
-                                             c->limbs.as<uint16_t>(),
-                                             c->limbs.as<uint8_t>() + sizeof(uint16_t) * 4 * (size_t)c->ldc,
-                                             c->gain8.as<uint8_t>(), c->quant.as<QuantDecision>());
-  tm.launched();
-  WLD_CUDA(c, cudaGetLastError());
   WLD_CUDA(c, cudaMemcpyAsync(c->quant_host, c->quant.p, sizeof(QuantDecision), cudaMemcpyDeviceToHost, c->stream));
+  // (the sampling launch's two counters ride along: counters[8] candidates, counters[9] pairs)
+  WLD_CUDA(c, cudaMemcpyAsync(c->sample_host, c->counters.as<unsigned long long>() + 8, 2 * sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, c->stream));
   WLD_CUDA(c, cudaStreamSynchronize(c->stream));
   const QuantDecision qd = *c->quant_host;
   if (qd.flags & 1) return c->fail(WLD_ERR_INVALID, "weights must be finite, >= 0 and not all zero");
@@ -387,58 +380,117 @@ int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm) {
   c->weight_sum = qd.weight_sum;
   c->quant_span_log2 = qd.span_log2;
   c->quant_rel_err = qd.rel_err;
+  c->quant_top_min = qd.top_min;
   gm.rows_per_site = 2 * gm.n_limbs;
   gm.sites_per_group = 128 / gm.rows_per_site;
+  gm.b_groups = std::max<int64_t>((c->n_kept + gm.sites_per_group - 1) / gm.sites_per_group, 1);
+  gm.b_groups = round_up(gm.b_groups, 2);  // an N tile is two groups
+  return WLD_OK;
+}
+
+// Quantises the weights and expands the indicator operand.  try_screen: also the one-limb operand of the screen,
+// all BEFORE the quantiser's decision is read back (neither depends on it), so that the sampling launch can
+// follow on the stream and one synchronisation (finish_quant) returns both results.
+int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm, bool try_screen) {
+  PairGeom& gm = c->geom;
+  const int64_t n = c->n_seqs, L = c->n_kept;
+  const bool i8 = c->pair_kernel == WLD_PAIR_KERNEL_UMMA_I8;
+  // exact-accumulation limit of a Gram entry: fp32 holds integers up to 2^24, s32 up to 2^31-1; the FP64
+  // verification kernel only needs the sum of all q below 2^53 (checked by the quantiser for every kernel)
+  const unsigned long long exact_limit = c->pair_kernel == WLD_PAIR_KERNEL_SIMT ? (1ull << 53)
+                                         : i8                                   ? ((1ull << 31) - 1)
+                                                                                : (1ull << 24);
+
+  WLD_CUDA(c, c->q.ensure(sizeof(double) * (size_t)c->ldc));
+  WLD_CUDA(c, c->qi.ensure(sizeof(unsigned long long) * (size_t)c->ldc));
+  WLD_CUDA(c, c->limbs.ensure((sizeof(uint16_t) + 1) * 4 * (size_t)c->ldc));  // u16 [4][ldc] then u8 [4][ldc]
+  WLD_CUDA(c, c->gain8.ensure((size_t)c->ldc));
+  WLD_CUDA(c, c->quant.ensure(sizeof(QuantDecision)));
+  WLD_CUDA(c, c->counters.ensure(sizeof(unsigned long long) * 16));
+  WLD_CUDA(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream));
+  if (!c->quant_host) {
+    WLD_CUDA(c, cudaMallocHost(&c->quant_host, sizeof(QuantDecision) + 2 * sizeof(unsigned long long)));
+    c->sample_host = reinterpret_cast<unsigned long long*>(c->quant_host + 1);
+  }
+  c->sample_host[0] = c->sample_host[1] = 0;
+
+  // One launch quantises the weights AND decides limbs / limb width / gain bits; one read-back tells the host.
+  quantize_kernel<<<1, 1024, 0, c->stream>>>(c->w32.as<float>(), n, c->ldc, c->n_limbs_opt, c->gain_opt, c->limb_bits_opt, exact_limit,
+                                             c->pair_kernel == WLD_PAIR_KERNEL_UMMA ? 1 : 0, c->q.as<double>(),
+                                             c->qi.as<unsigned long long>(), c->limbs.as<uint16_t>(),
+                                             c->limbs.as<uint8_t>() + sizeof(uint16_t) * 4 * (size_t)c->ldc,
+                                             c->gain8.as<uint8_t>(), c->quant.as<QuantDecision>());
+  tm.launched();
+  WLD_CUDA(c, cudaGetLastError());
   gm.elem_bytes = i8 ? 1 : 2;
   gm.k_padded = round_up(std::max<int64_t>(n, 1), i8 ? 128 : 64);  // one 128-byte swizzle atom per K block
   gm.a_rows = round_up(std::max<int64_t>(2 * L, 1), 128);
-  gm.b_groups = std::max<int64_t>((L + gm.sites_per_group - 1) / gm.sites_per_group, 1);
-  gm.b_groups = round_up(gm.b_groups, 2);  // an N tile is two groups
+  if (!try_screen) {
+    const int rc = finish_quant(c);
+    if (rc != WLD_OK) return rc;
+  }
+  if (c->pair_kernel == WLD_PAIR_KERNEL_SIMT) return WLD_OK;  // the CUDA-core verification kernel reads the code matrix and q directly
 
   const int64_t kp = gm.k_padded;
   const size_t es = (size_t)gm.elem_bytes;
   WLD_CUDA(c, c->opA.ensure(es * (size_t)gm.a_rows * (size_t)kp));
-  WLD_CUDA(c, c->opB.ensure(es * (size_t)gm.b_groups * 128 * (size_t)kp));
   const unsigned kblocks = (unsigned)((kp / (i8 ? 16 : 8) + 255) / 256);  // a thread expands 16 u8 / 8 bf16 elements
-  // Only the operand rows this partition's tiles read are expanded (multi-GPU: a contiguous range of the tile
-  // list touches a slice of the limb operand and, in the early strips, a prefix of the indicator operand).
-  int64_t site_lo = 0, site_hi = gm.a_rows / 2;     // sites whose indicator rows are needed
-  int64_t grp_lo = 0, grp_hi = gm.b_groups;         // 128-row groups of the limb operand that are needed
-  if (c->pair_kernel != WLD_PAIR_KERNEL_SIMT) {
-    const int rc = ensure_tile_plan(c);
+  // Only the operand rows this partition's tiles read are expanded (multi-GPU: a contiguous range of the cell
+  // list touches a slice of the limb operand and, in the early strips, a prefix of the indicator operand).  The
+  // rows of the indicator operand are the same for the screen's and the exact kernel's schedule.
+  const int which = try_screen ? 1 : 0;
+  {
+    const int rc = ensure_tile_plan(c, which);
     if (rc != WLD_OK) return rc;
-    if (c->plan_tiles_n == 0) return WLD_OK;
-    const int64_t tile_m = 64 * c->cta_group;
-    site_lo = c->plan_x[0] * tile_m;
-    site_hi = std::min<int64_t>(site_hi, (c->plan_x[1] + 1) * tile_m);
-    grp_lo = c->plan_y[0] * 2;
-    grp_hi = std::min<int64_t>(grp_hi, (c->plan_y[1] + 1) * 2);
-  } else {
-    return WLD_OK;  // the CUDA-core verification kernel reads the code matrix and q directly
   }
-  {
-    // grid.y limit is 65535: fold larger site counts into several launches
-    for (int64_t y0 = site_lo; y0 < site_hi; y0 += 65535) {
-      const unsigned ny = (unsigned)std::min<int64_t>(65535, site_hi - y0);
-      auto kern = i8 ? expand_a_kernel<true> : expand_a_kernel<false>;
-      kern<<<dim3(kblocks, ny), 256, 0, c->stream>>>(
-          c->codes.as<uint8_t>() + y0 * c->ldc, c->ldc, std::max<int64_t>(L - y0, 0), c->maj.as<int8_t>() + y0,
-          c->mnr.as<int8_t>() + y0, c->gain8.as<uint8_t>(), kp, c->opA.as<uint8_t>() + (size_t)(2 * y0 * kp) * es);
-      tm.launched();
-    }
+  const DevPlan& dp = c->plans[which];
+  if (dp.n_tiles == 0) return WLD_OK;
+  const int64_t tile_m = 64 * c->cta_group;
+  const int64_t site_lo = dp.x[0] * tile_m, site_hi = std::min<int64_t>(gm.a_rows / 2, (dp.x[1] + 1) * tile_m);
+  // grid.y limit is 65535: fold larger site counts into several launches
+  for (int64_t y0 = site_lo; y0 < site_hi; y0 += 65535) {
+    const unsigned ny = (unsigned)std::min<int64_t>(65535, site_hi - y0);
+    auto kern = i8 ? expand_a_kernel<true> : expand_a_kernel<false>;
+    kern<<<dim3(kblocks, ny), 256, 0, c->stream>>>(
+        c->codes.as<uint8_t>() + y0 * c->ldc, c->ldc, std::max<int64_t>(L - y0, 0), c->maj.as<int8_t>() + y0,
+        c->mnr.as<int8_t>() + y0, c->gain8.as<uint8_t>(), kp, c->opA.as<uint8_t>() + (size_t)(2 * y0 * kp) * es);
+    tm.launched();
   }
+  WLD_CUDA(c, cudaGetLastError());
+  if (try_screen) return run_expand_limbs(c, tm, true);
+  return WLD_OK;
+}
+
+// The limb operand: every limb of the exact kernel's layout (screen = false; needs finish_quant), or the TOP limb
+// alone in the one-limb layout (64 sites per 128-row group) for the screen.
+int run_expand_limbs(wld_ctx* c, ScopedStageTimer& tm, bool screen) {
+  const PairGeom& gm = c->geom;
+  const int64_t L = c->n_kept, kp = gm.k_padded;
+  const bool i8 = gm.elem_bytes == 1;
+  const size_t es = (size_t)gm.elem_bytes;
+  const int which = screen ? 1 : 0;
   {
-    const int spg = gm.sites_per_group;
-    const int64_t groups_per_launch = 65535 / (spg + 1);
-    for (int64_t g0 = grp_lo; g0 < grp_hi; g0 += groups_per_launch) {
-      const int64_t ng = std::min<int64_t>(groups_per_launch, grp_hi - g0);
-      auto kern = i8 ? expand_b_kernel<true> : expand_b_kernel<false>;
-      kern<<<dim3(kblocks, (unsigned)(ng * (spg + 1))), 256, 0, c->stream>>>(
-          c->codes.as<uint8_t>() + g0 * spg * c->ldc, c->ldc, std::max<int64_t>(L - g0 * spg, 0),
-          c->maj.as<int8_t>() + g0 * spg, c->mnr.as<int8_t>() + g0 * spg, c->limbs.as<uint16_t>(), gm.n_limbs, spg,
-          kp, c->opB.as<uint8_t>() + (size_t)(g0 * 128 * kp) * es);
-      tm.launched();
-    }
+    const int rc = ensure_tile_plan(c, which);
+    if (rc != WLD_OK) return rc;
+  }
+  const DevPlan& dp = c->plans[which];
+  if (dp.n_tiles == 0) return WLD_OK;
+  const int n_limbs = screen ? 1 : gm.n_limbs;
+  const int spg = 128 / (2 * n_limbs);
+  const int64_t b_groups = screen ? round_up(std::max<int64_t>((L + 63) / 64, 1), 2) : gm.b_groups;
+  DevBuf& op = screen ? c->opB1 : c->opB;
+  WLD_CUDA(c, op.ensure(es * (size_t)b_groups * 128 * (size_t)kp));
+  const unsigned kblocks = (unsigned)((kp / (i8 ? 16 : 8) + 255) / 256);
+  const int64_t grp_lo = dp.y[0] * 2, grp_hi = std::min<int64_t>(b_groups, (dp.y[1] + 1) * 2);
+  const int64_t groups_per_launch = 65535 / (spg + 1);
+  for (int64_t g0 = grp_lo; g0 < grp_hi; g0 += groups_per_launch) {
+    const int64_t ng = std::min<int64_t>(groups_per_launch, grp_hi - g0);
+    auto kern = i8 ? expand_b_kernel<true> : expand_b_kernel<false>;
+    kern<<<dim3(kblocks, (unsigned)(ng * (spg + 1))), 256, 0, c->stream>>>(
+        c->codes.as<uint8_t>() + g0 * spg * c->ldc, c->ldc, std::max<int64_t>(L - g0 * spg, 0),
+        c->maj.as<int8_t>() + g0 * spg, c->mnr.as<int8_t>() + g0 * spg, c->limbs.as<uint16_t>(), n_limbs, spg,
+        kp, op.as<uint8_t>() + (size_t)(g0 * 128 * kp) * es);
+    tm.launched();
   }
   WLD_CUDA(c, cudaGetLastError());
   return WLD_OK;

@@ -115,15 +115,14 @@ int run_pair_simt(wld_ctx* c, float thr) {
   c->info.tile_sites_n = kTile;
   c->info.executed_flop = 0.0;
   if (list.empty()) return WLD_OK;
-  WLD_CUDA(c, c->tiles.ensure(sizeof(uint2) * list.size()));
-  WLD_CUDA(c, cudaMemcpyAsync(c->tiles.p, list.data(), sizeof(uint2) * list.size(), cudaMemcpyHostToDevice, c->stream));
+  WLD_CUDA(c, c->simt_tiles.ensure(sizeof(uint2) * list.size()));
+  WLD_CUDA(c, cudaMemcpyAsync(c->simt_tiles.p, list.data(), sizeof(uint2) * list.size(), cudaMemcpyHostToDevice, c->stream));
   WLD_CUDA(c, cudaStreamSynchronize(c->stream));  // `list` is pageable and dies at return
-  std::memset(c->plan_key, 0xff, sizeof c->plan_key);  // the tile buffer no longer holds the tcgen05 schedule
   ScopedStageTimer tm(c, WLD_STAGE_PAIR);          // kernel only
   PairOut out{c->pairs.as<wld_pair>(), c->counters.as<unsigned long long>(), c->pair_cap};
   pair_simt_kernel<<<(unsigned)list.size(), 256, 0, c->stream>>>(
       c->codes.as<uint8_t>(), c->ldc, L, c->n_seqs, c->maj.as<int8_t>(), c->mnr.as<int8_t>(), c->q.as<double>(),
-      c->tiles.as<uint2>(), thr, ld_thr_lo(thr),
+      c->simt_tiles.as<uint2>(), thr, ld_thr_lo(thr),
       c->compat == WLD_COMPAT_PYTHON ? c->py_aux.as<uint2>() : nullptr, out, c->counters.as<unsigned long long>() + 1);
   tm.launched();
   WLD_CUDA(c, cudaGetLastError());

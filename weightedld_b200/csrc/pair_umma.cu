@@ -70,8 +70,9 @@ constexpr int kTmemCols = 512;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> CTA 0
 
 struct UmmaParams {
-  const uint2* tiles;
-  int n_tiles;
+  const uint4* tiles;   // {M tile, N tile, first site j, end site j}: only pairs with j inside the window count
+  int n_tiles;          // tiles this launch walks: tile k of the launch is tiles[k * tile_mul]
+  int tile_mul;         // 1, or the stride of a sampling launch
   int k_blocks;
   int n_kept;
   int limb_bits;
@@ -96,6 +97,9 @@ struct UmmaParams {
   uint64_t hint_a, hint_b;  // L2 eviction policy of the indicator (streamed) and limb (strip-resident) panels
   const uint2* py_aux; // WLD_COMPAT_PYTHON only (else null): per-site {n5, margin}, see py_flagged
   PairOut out;
+  // screen (kScreen): candidates instead of survivors; kappa widens |P - Q| by the truncation of the weights
+  CandOut cand;
+  const float* kappa;   // device: QuantDecision::kappa (the sampling launch runs before the host has read it)
   unsigned long long* pairs_done;
   int* error_flag;
 };
@@ -384,7 +388,7 @@ struct CandidateQueue {
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <int NL, bool kI8, int kCtas>
+template <int NL, bool kI8, int kCtas, bool kScreen>
 __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const UmmaParams p) {
@@ -497,7 +501,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
             __nanosleep(32);
           }
         }
-        const uint2 tile = p.tiles[t];
+        const uint4 tile = p.tiles[(size_t)t * (size_t)p.tile_mul];
         const int m_row = (int)tile.x * (kBlockM * kCtas) + (int)cta_rank * kBlockM;
         const int n_row = (int)tile.y * kBlockN + (int)cta_rank * Cfg::kBRows;
         // (Tiles that share a panel run in lockstep through K: one fetches a line, the others hit in L2.  Starting
@@ -564,12 +568,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
 #pragma unroll
     for (int l = 0; l < NL; ++l)
       scale_f[l] = __int_as_float((127 + p.limb_bits * (NL - 1 - l) - p.sum_shift) << 23);
+    float kappa = 0.0f;
+    if constexpr (kScreen) kappa = __ldg(p.kappa);
     CandidateQueue queue;
     queue.init(smem + Cfg::kQueueOffset + (warp - kEpiWarp0) * kQueueBytesPerWarp);
     unsigned long long done = 0;
     uint32_t tcount = 0;
     for (int t = first_tile; t < tile_end; t += tile_step, ++tcount) {
-      const uint2 tile = p.tiles[t];
+      const uint4 tile = p.tiles[(size_t)t * (size_t)p.tile_mul];
       const uint32_t buf = tcount & 1u, bphase = (tcount >> 1) & 1u;
       const int i_min = ((int)tile.x * kCtas + (int)cta_rank) * (kBlockM / 2) + quarter * 16;
       const int site_i = i_min + (lane >> 1);
@@ -577,9 +583,40 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
       mbar_wait(tfull_bar(buf), bphase, p.error_flag, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * kBlockN + half * 128;
-      // whole tile below the diagonal band for this warp?  (i >= every j) -> nothing to do
-      const bool any_work = i_min < min(site_j0 + min(2 * jp_end, SPG), p.n_kept) && site_j0 + 2 * jp_begin < p.n_kept;
-      if (any_work) {
+      // whole tile below the diagonal band, or outside the tile's window, for this warp?  -> nothing to do
+      const int j_hi = min(site_j0 + min(2 * jp_end, SPG), (int)tile.w), j_lo = max(site_j0 + 2 * jp_begin, (int)tile.z);
+      const bool any_work = i_min < j_hi && j_lo < j_hi;
+      if constexpr (kScreen) {
+        // ---- one-limb screen: RPS = 2, SPG = 64; four sites j (8 columns) per step.  x = exact s32 sums of
+        // gain x TOP limb; the true sums lie in [x, x (1 + 1/top_min)] (pair_prep.cu), so
+        //   r2 <= (|P - Q| + kappa max(P, Q))^2 / (A a B b),  P = AB ab, Q = Ab aB, marginals from x
+        // (ld_screen_f32).  The test is symmetric in the two rows of site i, so a lane uses (own row, peer row)
+        // as (AB, Ab | aB, ab) whichever of the two it holds.
+        static_assert(!kScreen || (NL == 1 && kI8), "the screen is the one-limb u8 kernel");
+        if (any_work) {
+#pragma unroll 1
+          for (int js = 0; js < SPG / 4; ++js) {
+            uint32_t v[8];
+            tmem_ld8(taddr + js * 8, v);
+            tmem_ld_wait();
+            float f[8];
+#pragma unroll
+            for (int x = 0; x < 8; ++x) f[x] = (float)(int)v[x];
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp) {
+              // lane alpha finishes site 4js + 2pp + alpha and sends its row's sums of the other site of the pair
+              const float own0 = alpha ? f[4 * pp + 2] : f[4 * pp + 0], own1 = alpha ? f[4 * pp + 3] : f[4 * pp + 1];
+              const float snd0 = alpha ? f[4 * pp + 0] : f[4 * pp + 2], snd1 = alpha ? f[4 * pp + 1] : f[4 * pp + 3];
+              const float rcv0 = __shfl_xor_sync(0xffffffffu, snd0, 1), rcv1 = __shfl_xor_sync(0xffffffffu, snd1, 1);
+              const int site_j = site_j0 + 4 * js + 2 * pp + alpha;
+              const bool valid = site_i < site_j && site_j >= (int)tile.z && site_j < (int)tile.w;  // lib.rs:651
+              done += valid;
+              const bool cand = valid && ld_screen_f32(own0, own1, rcv0, rcv1, kappa, p.thr_lo_f);
+              emit_cand_warp(cand, (uint32_t)site_i, (uint32_t)site_j, p.cand);
+            }
+          }
+        }
+      } else if (any_work) {
 #pragma unroll 1
         for (int jp = jp_begin; jp < jp_end; ++jp) {
           uint32_t v[2 * RPS];
@@ -613,7 +650,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
           const float fo1 = alpha ? F[1][1] : F[0][1];
           const int j_local = 2 * jp + alpha;
           const int site_j = site_j0 + j_local;
-          const bool valid = j_local < SPG && site_i < site_j && site_j < p.n_kept;  // lib.rs:651
+          const bool valid = j_local < SPG && site_i < site_j && site_j >= (int)tile.z && site_j < (int)tile.w;  // lib.rs:651
           done += valid;
           bool keep = valid && ld_prefilter_f32(alpha ? fr0 : fo0, alpha ? fr1 : fo1, alpha ? fo0 : fr0,
                                                 alpha ? fo1 : fr1, p.thr_lo_f, p.thr_negative != 0);
@@ -705,10 +742,10 @@ bool make_tensor_map(CUtensorMap* map, void* base, uint64_t rows, uint64_t kp, u
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int NL, bool kI8, int kCtas>
+template <int NL, bool kI8, int kCtas, bool kScreen>
 cudaError_t launch(int grid, cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB,
                    const UmmaParams& prm) {
-  auto kern = pair_umma_kernel<NL, kI8, kCtas>;
+  auto kern = pair_umma_kernel<NL, kI8, kCtas, kScreen>;
   constexpr int smem = StageCfg<kCtas>::kSmemBytes;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
@@ -728,120 +765,171 @@ cudaError_t launch(int grid, cudaStream_t stream, const CUtensorMap& tmA, const 
 }
 
 template <int kCtas>
-cudaError_t launch_any(int n_limbs, bool i8, int grid, cudaStream_t stream, const CUtensorMap& tmA,
+cudaError_t launch_any(int n_limbs, bool i8, bool screen, int grid, cudaStream_t stream, const CUtensorMap& tmA,
                        const CUtensorMap& tmB, const UmmaParams& prm) {
+  if (screen) return launch<1, true, kCtas, true>(grid, stream, tmA, tmB, prm);
   switch (n_limbs * 2 + (i8 ? 1 : 0)) {
-    case 2: return launch<1, false, kCtas>(grid, stream, tmA, tmB, prm);
-    case 3: return launch<1, true, kCtas>(grid, stream, tmA, tmB, prm);
-    case 4: return launch<2, false, kCtas>(grid, stream, tmA, tmB, prm);
-    case 5: return launch<2, true, kCtas>(grid, stream, tmA, tmB, prm);
-    case 6: return launch<3, false, kCtas>(grid, stream, tmA, tmB, prm);
-    case 7: return launch<3, true, kCtas>(grid, stream, tmA, tmB, prm);
-    case 8: return launch<4, false, kCtas>(grid, stream, tmA, tmB, prm);
-    case 9: return launch<4, true, kCtas>(grid, stream, tmA, tmB, prm);
+    case 2: return launch<1, false, kCtas, false>(grid, stream, tmA, tmB, prm);
+    case 3: return launch<1, true, kCtas, false>(grid, stream, tmA, tmB, prm);
+    case 4: return launch<2, false, kCtas, false>(grid, stream, tmA, tmB, prm);
+    case 5: return launch<2, true, kCtas, false>(grid, stream, tmA, tmB, prm);
+    case 6: return launch<3, false, kCtas, false>(grid, stream, tmA, tmB, prm);
+    case 7: return launch<3, true, kCtas, false>(grid, stream, tmA, tmB, prm);
+    case 8: return launch<4, false, kCtas, false>(grid, stream, tmA, tmB, prm);
+    case 9: return launch<4, true, kCtas, false>(grid, stream, tmA, tmB, prm);
     default: return cudaErrorInvalidValue;
   }
 }
 
 }  // namespace
 
-// Upper-triangular tile list, rasterised in strips of 8 N tiles so that the tiles in flight share
-// operand panels through L2; for multi-GPU runs every partition takes one contiguous range of that
-// list (load-balanced, no collective; replaces rayon's fan-out over triu_index, lib.rs:623-637).
+// The schedule (replaces rayon's fan-out over triu_index, lib.rs:623-637).
+//
+// PARTITIONS are defined on a canonical grid of 128 x 128-site cells, independent of the kernel variant: the
+// cells that hold a pair a < b, rasterised in strips of 8 cell columns, are cut into `nparts` contiguous ranges of
+// equal cell count (= equal tensor work; every strip holds its own stretch of the diagonal, so the epilogue work
+// is balanced too).  A partition therefore owns, in every cell row, ONE contiguous interval of site columns,
+// whatever the tile shape — each GPU may pick the one-limb screen or the exact n-limb kernel on its own and the
+// union over the GPUs still covers every pair exactly once.
+//
+// TILES of a kernel variant (M = 64 * ctas sites, N = 2 * floor(128 / (2 n_limbs)) sites) are listed in strips of
+// 8 N tiles so that the tiles in flight share operand panels through L2; a tile carries the window [j_lo, j_hi)
+// of site columns that belong to this partition (the whole tile except where it straddles a partition boundary).
 TilePlan plan_tiles(int64_t L, int n_limbs, int part, int nparts, int sm_count, int ctas) {
+  (void)sm_count;
   TilePlan plan;
   plan.tile_m = (kBlockM / 2) * ctas;
   plan.tile_n = 2 * (128 / (2 * n_limbs));
+  constexpr int64_t kCell = 128, kStrip = 8;
+  const int64_t n_c = (L + kCell - 1) / kCell;
+  // column interval (in cells) of every cell row that this partition owns
+  std::vector<int64_t> c_lo((size_t)std::max<int64_t>(n_c, 1), INT64_MAX), c_hi((size_t)std::max<int64_t>(n_c, 1), -1);
+  {
+    auto cell_has_pair = [&](int64_t ci, int64_t cj) { return ci * kCell < std::min(L, (cj + 1) * kCell) - 1; };
+    uint64_t total = 0;
+    for (int64_t cs = 0; cs < n_c; cs += kStrip)
+      for (int64_t ci = 0; ci < std::min(n_c, cs + kStrip); ++ci)
+        total += (uint64_t)std::max<int64_t>(0, std::min(cs + kStrip, n_c) - std::max(cs, ci)) -
+                 ((ci >= cs && ci < std::min(cs + kStrip, n_c) && !cell_has_pair(ci, ci)) ? 1 : 0);
+    const uint64_t lo = total * (uint64_t)part / (uint64_t)nparts, hi = total * (uint64_t)(part + 1) / (uint64_t)nparts;
+    uint64_t idx = 0;
+    for (int64_t cs = 0; cs < n_c && idx < hi; cs += kStrip) {
+      const int64_t ce = std::min(cs + kStrip, n_c);
+      for (int64_t ci = 0; ci < ce && idx < hi; ++ci)
+        for (int64_t cj = std::max(cs, ci); cj < ce && idx < hi; ++cj) {
+          if (!cell_has_pair(ci, cj)) continue;
+          if (idx >= lo) {
+            c_lo[(size_t)ci] = std::min(c_lo[(size_t)ci], cj);
+            c_hi[(size_t)ci] = std::max(c_hi[(size_t)ci], cj + 1);
+          }
+          ++idx;
+        }
+    }
+  }
   const int64_t tile_m = plan.tile_m, tile_n = plan.tile_n;
   const int64_t n_mt = (L + tile_m - 1) / tile_m, n_nt = (L + tile_n - 1) / tile_n;
-  std::vector<uint2> all;
-  // strip width in N tiles; WLD_STRIP overrides it for experiments
-  int64_t kStrip = 8;
-  if (const char* e = std::getenv("WLD_STRIP")) kStrip = std::max(1, std::atoi(e));
-  for (int64_t ns = 0; ns < n_nt; ns += kStrip) {
-    const int64_t ne = std::min(ns + kStrip, n_nt);
-    for (int64_t mi = 0; mi < n_mt; ++mi)
+  int64_t strip = kStrip;  // in N tiles; WLD_STRIP overrides it for experiments
+  if (const char* e = std::getenv("WLD_STRIP")) strip = std::max(1, std::atoi(e));
+  for (int64_t ns = 0; ns < n_nt; ns += strip) {
+    const int64_t ne = std::min(ns + strip, n_nt);
+    for (int64_t mi = 0; mi < n_mt; ++mi) {
+      const size_t ci = (size_t)(mi * tile_m / kCell);
+      if (c_hi[ci] < 0) continue;
+      const int64_t i0 = mi * tile_m, i1 = std::min(L, i0 + tile_m);
+      const int64_t own_lo = c_lo[ci] * kCell, own_hi = std::min(L, c_hi[ci] * kCell);
       for (int64_t nj = ns; nj < ne; ++nj) {
-        const int64_t j_last = std::min(L, (nj + 1) * tile_n) - 1;
-        if (mi * tile_m < j_last) all.push_back(make_uint2((unsigned)mi, (unsigned)nj));
+        const int64_t w_lo = std::max(nj * tile_n, own_lo), w_hi = std::min((nj + 1) * tile_n, own_hi);
+        if (w_lo >= w_hi || i0 >= w_hi - 1) continue;  // outside the partition / no pair a < b in the window
+        plan.tiles.push_back(make_uint4((unsigned)mi, (unsigned)nj, (unsigned)w_lo, (unsigned)w_hi));
+        if (i1 <= w_lo) {  // entirely above the diagonal: every (i, j) of the window is a pair
+          plan.pairs += (uint64_t)((i1 - i0) * (w_hi - w_lo));
+        } else {
+          for (int64_t i = i0; i < i1; ++i) plan.pairs += (uint64_t)std::max<int64_t>(0, w_hi - std::max(w_lo, i + 1));
+        }
       }
-  }
-  if (nparts <= 1) {
-    plan.tiles.swap(all);
-  } else {
-    // Contiguous ranges of the rasterised list: equal tile counts (= equal tensor work; every strip holds its own
-    // share of the diagonal, so the epilogue work is balanced too), each partition keeps whole strips together
-    // (its limb panels stay in L2 across waves) and touches only its own slice of the operands.
-    const size_t lo = all.size() * (size_t)part / (size_t)nparts, hi = all.size() * (size_t)(part + 1) / (size_t)nparts;
-    plan.tiles.assign(all.begin() + lo, all.begin() + hi);
-  }
-  (void)sm_count;
-  for (const uint2& t : plan.tiles) {  // pairs a < b inside the tile
-    const int64_t i0 = (int64_t)t.x * tile_m, i1 = std::min(L, i0 + tile_m);
-    const int64_t j0 = (int64_t)t.y * tile_n, j1 = std::min(L, j0 + tile_n);
-    if (i1 <= j0) {  // entirely above the diagonal: every (i, j) of the tile is a pair
-      plan.pairs += (uint64_t)((i1 - i0) * (j1 - j0));
-    } else {
-      for (int64_t i = i0; i < i1; ++i) plan.pairs += (uint64_t)std::max<int64_t>(0, j1 - std::max(j0, i + 1));
     }
   }
   return plan;
 }
 
-// The schedule only depends on (n_kept, n_limbs, partition, cta_group): it is planned once, kept on the
-// device between calls, and its extent (which M / N tiles this partition touches) tells pair_prep which
-// operand rows to expand.
-int ensure_tile_plan(wld_ctx* c) {
-  const PairGeom& gm = c->geom;
+// A schedule only depends on (n_kept, limbs, partition, cta_group): it is planned once, kept on the device
+// between calls, and its extent (which M / N tiles this partition touches) tells pair_prep which operand rows
+// to expand.  which = 0: the exact kernel (c->geom.n_limbs limbs); 1: the one-limb screen.
+int ensure_tile_plan(wld_ctx* c, int which) {
+  DevPlan& dp = c->plans[which];
   const int64_t L = c->n_kept;
   const int ctas = c->cta_group;
-  const int64_t key[5] = {L, gm.n_limbs, c->part, c->nparts, ctas};
-  if (std::memcmp(key, c->plan_key, sizeof key) == 0) return WLD_OK;
-  TilePlan plan = plan_tiles(L, gm.n_limbs, c->part, c->nparts, c->sm_count, ctas);
-  WLD_CUDA(c, c->tiles.ensure(sizeof(uint2) * std::max<size_t>(plan.tiles.size(), 1)));
+  const int n_limbs = which == 1 ? 1 : c->geom.n_limbs;
+  const int64_t key[5] = {L, n_limbs, c->part, c->nparts, ctas};
+  if (std::memcmp(key, dp.key, sizeof key) == 0) {
+    c->plan_pairs = dp.pairs;
+    return WLD_OK;
+  }
+  TilePlan plan = plan_tiles(L, n_limbs, c->part, c->nparts, c->sm_count, ctas);
+  WLD_CUDA(c, dp.tiles.ensure(sizeof(uint4) * std::max<size_t>(plan.tiles.size(), 1)));
   if (!plan.tiles.empty())
-    WLD_CUDA(c, cudaMemcpyAsync(c->tiles.p, plan.tiles.data(), sizeof(uint2) * plan.tiles.size(),
+    WLD_CUDA(c, cudaMemcpyAsync(dp.tiles.p, plan.tiles.data(), sizeof(uint4) * plan.tiles.size(),
                                 cudaMemcpyHostToDevice, c->stream));
   WLD_CUDA(c, cudaStreamSynchronize(c->stream));  // the host vector dies at the end of this function
-  std::memcpy(c->plan_key, key, sizeof key);
-  c->plan_tiles_n = (int64_t)plan.tiles.size();
-  c->plan_pairs = plan.pairs;
-  c->plan_x[0] = c->plan_y[0] = INT64_MAX;
-  c->plan_x[1] = c->plan_y[1] = -1;
-  for (const uint2& t : plan.tiles) {
-    c->plan_x[0] = std::min<int64_t>(c->plan_x[0], t.x);
-    c->plan_x[1] = std::max<int64_t>(c->plan_x[1], t.x);
-    c->plan_y[0] = std::min<int64_t>(c->plan_y[0], t.y);
-    c->plan_y[1] = std::max<int64_t>(c->plan_y[1], t.y);
+  std::memcpy(dp.key, key, sizeof key);
+  dp.n_tiles = (int64_t)plan.tiles.size();
+  dp.pairs = plan.pairs;
+  dp.tile_m = plan.tile_m;
+  dp.tile_n = plan.tile_n;
+  dp.x[0] = dp.y[0] = INT64_MAX;
+  dp.x[1] = dp.y[1] = -1;
+  for (const uint4& t : plan.tiles) {
+    dp.x[0] = std::min<int64_t>(dp.x[0], t.x);
+    dp.x[1] = std::max<int64_t>(dp.x[1], t.x);
+    dp.y[0] = std::min<int64_t>(dp.y[0], t.y);
+    dp.y[1] = std::max<int64_t>(dp.y[1], t.y);
   }
+  c->plan_pairs = dp.pairs;
   return WLD_OK;
 }
 
-int run_pair_umma(wld_ctx* c, float thr) {
+// mode 0: exact kernel; 1: screen, every tile, candidates into c->cand; 2: screen over a sample of the tiles,
+// counting only (candidates -> counters[8], pairs -> counters[9]).
+int run_pair_umma(wld_ctx* c, float thr, int mode) {
   const PairGeom& gm = c->geom;
-  const int64_t L = c->n_kept;
   const int ctas = c->cta_group;
+  const bool screen = mode != 0;
   {
-    const int rc = ensure_tile_plan(c);
+    const int rc = ensure_tile_plan(c, screen ? 1 : 0);
     if (rc != WLD_OK) return rc;
   }
-  const int64_t n_tiles = c->plan_tiles_n;
-  c->info.tiles = n_tiles;
-  c->info.tile_sites_m = (kBlockM / 2) * ctas;
-  c->info.tile_sites_n = 2 * gm.sites_per_group;
-  c->info.executed_flop = (double)n_tiles * 2.0 * (kBlockM * ctas) * kBlockN * (double)gm.k_padded;
+  const DevPlan& dp = c->plans[screen ? 1 : 0];
+  const int n_limbs = screen ? 1 : gm.n_limbs;
+  const int spg = 128 / (2 * n_limbs);
+  int64_t n_tiles = dp.n_tiles;
+  int tile_mul = 1;
+  const int64_t pairs_of_ctas = c->sm_count / ctas;
+  if (mode == 2) {  // about two waves of tiles, evenly spread over the list
+    tile_mul = (int)std::max<int64_t>(1, n_tiles / (2 * pairs_of_ctas));
+    n_tiles = (n_tiles + tile_mul - 1) / tile_mul;
+  }
+  if (mode != 2) {
+    c->info.tiles = n_tiles;
+    c->info.tile_sites_m = (kBlockM / 2) * ctas;
+    c->info.tile_sites_n = 2 * spg;
+    c->info.executed_flop = (double)n_tiles * 2.0 * (kBlockM * ctas) * kBlockN * (double)gm.k_padded;
+  }
   if (n_tiles == 0) return WLD_OK;
 
+  const int64_t b_groups = screen ? round_up(std::max<int64_t>((c->n_kept + 63) / 64, 1), 2) : gm.b_groups;
   CUtensorMap tmA, tmB;
   if (!make_tensor_map(&tmA, c->opA.p, (uint64_t)gm.a_rows, (uint64_t)gm.k_padded, kBlockM, gm.elem_bytes) ||
-      !make_tensor_map(&tmB, c->opB.p, (uint64_t)gm.b_groups * 128, (uint64_t)gm.k_padded, kBlockN / ctas, gm.elem_bytes))
+      !make_tensor_map(&tmB, screen ? c->opB1.p : c->opB.p, (uint64_t)b_groups * 128, (uint64_t)gm.k_padded, kBlockN / ctas,
+                       gm.elem_bytes))
     return c->fail(WLD_ERR_CUDA, "cuTensorMapEncodeTiled failed (driver without TMA support?)");
 
+  unsigned long long* cnt = c->counters.as<unsigned long long>();
   UmmaParams prm;
-  prm.tiles = c->tiles.as<uint2>();
+  prm.tiles = dp.tiles.as<uint4>();
   prm.n_tiles = (int)n_tiles;
+  prm.tile_mul = tile_mul;
   prm.k_blocks = (int)(gm.k_padded * gm.elem_bytes / kBlockKBytes);
-  prm.n_kept = (int)L;
+  prm.n_kept = (int)c->n_kept;
   prm.limb_bits = gm.limb_bits;
   prm.thr = thr;
   prm.thr_lo = ld_thr_lo(thr);
@@ -869,25 +957,36 @@ int run_pair_umma(wld_ctx* c, float thr) {
     while (std::ldexp(c->weight_sum, -shift) > 2097152.0) ++shift;
     prm.sum_shift = shift;
   }
-  prm.out = PairOut{c->pairs.as<wld_pair>(), c->counters.as<unsigned long long>(), c->pair_cap};
-  prm.pairs_done = c->counters.as<unsigned long long>() + 1;
-  prm.error_flag = reinterpret_cast<int*>(c->counters.as<unsigned long long>() + 2);
+  prm.out = PairOut{c->pairs.as<wld_pair>(), cnt, c->pair_cap};
+  prm.pairs_done = cnt + 1;
+  prm.error_flag = reinterpret_cast<int*>(cnt + 2);
+  prm.cand = CandOut{nullptr, cnt + 5, 0};
+  prm.kappa = &c->quant.as<QuantDecision>()->kappa;
+  if (screen) {
+    prm.thr_lo_f = std::min(prm.thr_lo_f, 2.0f);  // (a threshold above 1 can never pass; keeps thr * den finite)
+    if (mode == 1) {
+      prm.cand = CandOut{c->cand.as<uint2>(), cnt + 5, c->cand_cap};
+    } else {
+      prm.cand = CandOut{nullptr, cnt + 8, 0};
+      prm.pairs_done = cnt + 9;
+    }
+  }
 
-  int grid = (int)std::min<int64_t>(n_tiles, (int64_t)(c->sm_count / ctas)) * ctas;
+  int grid = (int)std::min<int64_t>(n_tiles, pairs_of_ctas) * ctas;
   // Die-aware schedule: each L2 die works on its own contiguous part of the (strip-rasterised) tile list, so
   // the panels a die's L2 holds are only the ones its own SMs reuse.  WLD_DIE=0 disables (experiments).
   prm.die_of_sm = nullptr;
   prm.n_sm = 0;
-  prm.die_counter = reinterpret_cast<unsigned int*>(c->counters.as<unsigned long long>() + 3);
+  prm.die_counter = reinterpret_cast<unsigned int*>(cnt + 3);
   prm.die_pairs[0] = prm.die_pairs[1] = 0;
   prm.die_split = 0;
   prm.die_mode = 1;
   prm.wave_sync = 0;
-  prm.wave_counter = reinterpret_cast<unsigned int*>(c->counters.as<unsigned long long>() + 4);
-  c->die_used = 0;
+  prm.wave_counter = reinterpret_cast<unsigned int*>(cnt + 4);
+  if (mode != 2) c->die_used = 0;
   {
     const char* e = std::getenv("WLD_DIE");
-    if (c->die_aware && !(e && e[0] == '0') && n_tiles >= 4 * (int64_t)(c->sm_count / ctas)) {
+    if (mode != 2 && c->die_aware && !(e && e[0] == '0') && n_tiles >= 4 * pairs_of_ctas) {
       const std::vector<uint8_t>& dm = die_map(c);
       if ((int)dm.size() == c->sm_count) {
         int sms[2] = {0, 0};
@@ -921,10 +1020,11 @@ int run_pair_umma(wld_ctx* c, float thr) {
     }
   }
   const bool i8 = gm.elem_bytes == 1;
-  if (gm.n_limbs < 1 || gm.n_limbs > 4) return c->fail(WLD_ERR_INVALID, "n_limbs must be 1..4");
-  ScopedStageTimer tm(c, WLD_STAGE_PAIR);  // kernel only
-  const cudaError_t e = ctas == 2 ? launch_any<2>(gm.n_limbs, i8, grid, c->stream, tmA, tmB, prm)
-                                  : launch_any<1>(gm.n_limbs, i8, grid, c->stream, tmA, tmB, prm);
+  if (n_limbs < 1 || n_limbs > 4) return c->fail(WLD_ERR_INVALID, "n_limbs must be 1..4");
+  if (screen && !i8) return c->fail(WLD_ERR_INVALID, "the screen needs the u8 operands");
+  ScopedStageTimer tm(c, mode == 2 ? WLD_STAGE_PAIR_SAMPLE : WLD_STAGE_PAIR);  // kernel only
+  const cudaError_t e = ctas == 2 ? launch_any<2>(n_limbs, i8, screen, grid, c->stream, tmA, tmB, prm)
+                                  : launch_any<1>(n_limbs, i8, screen, grid, c->stream, tmA, tmB, prm);
   tm.launched();
   if (e != cudaSuccess) return c->fail(WLD_ERR_CUDA, "pair_umma launch failed: %s", cudaGetErrorString(e));
   return WLD_OK;

@@ -12,6 +12,7 @@
 #include <thread>
 
 #include "common.cuh"
+#include "pair_epilogue.cuh"
 
 using namespace wld;
 
@@ -69,8 +70,9 @@ void wld_destroy(wld_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->raw_own, &c->hist, &c->keep, &c->rank, &c->maj_raw, &c->min_raw, &c->site_map, &c->maj,
                     &c->mnr, &c->kept_count, &c->codes, &c->table, &c->partial, &c->w64, &c->w32, &c->scalars,
-                    &c->q, &c->limbs, &c->opA, &c->opB, &c->tiles, &c->pairs, &c->counters, &c->py_aux, &c->die_of_sm,
-                    &c->sorted, &c->sort_keys, &c->sort_idx, &c->sort_temp, &c->gain8, &c->quant};
+                    &c->q, &c->limbs, &c->opA, &c->opB, &c->simt_tiles, &c->pairs, &c->counters, &c->py_aux, &c->die_of_sm,
+                    &c->sorted, &c->sort_keys, &c->sort_idx, &c->sort_temp, &c->gain8, &c->quant, &c->qi, &c->opB1,
+                    &c->cand, &c->plans[0].tiles, &c->plans[1].tiles};
   for (DevBuf* b : bufs) b->release();
   if (c->quant_host) cudaFreeHost(c->quant_host);
   for (int i = 0; i < wld_ctx::kMaxStagers; ++i) {
@@ -142,6 +144,13 @@ int wld_set_cta_group(wld_ctx* c, int ctas) {
   WLD_CHECK_CTX(c);
   if (ctas != 1 && ctas != 2) return c->fail(WLD_ERR_INVALID, "cta_group must be 1 or 2");
   c->cta_group = ctas;
+  return WLD_OK;
+}
+
+int wld_set_screen(wld_ctx* c, int mode) {
+  WLD_CHECK_CTX(c);
+  if (mode < 0 || mode > 2) return c->fail(WLD_ERR_INVALID, "screen mode must be 0 (never), 1 (automatic) or 2 (always)");
+  c->screen_opt = mode;
   return WLD_OK;
 }
 
@@ -488,10 +497,45 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
   c->last_thr = r2_threshold;
   c->info = wld_pair_info{};
   const int64_t L = c->n_kept;
+  for (int st : {WLD_STAGE_PAIR_SAMPLE, WLD_STAGE_PAIR_REFINE}) {
+    c->timers[st].valid = false;
+    c->timers[st].launches = 0;
+  }
   if (L >= 2 && c->n_seqs > 0) {
+    // Screen + refine (wld_set_screen) is considered for the u8 tensor kernel, the Rust dialect and a positive
+    // threshold, when the schedule is long enough for a sample to mean something (>= 4 waves of cells).
+    const int64_t cells_1d = (L + 127) / 128;
+    bool try_screen = c->screen_opt != 0 && c->pair_kernel == WLD_PAIR_KERNEL_UMMA_I8 && c->compat == WLD_COMPAT_RUST &&
+                      ld_thr_lo(r2_threshold) > 0.0 &&
+                      (c->screen_opt == 2 || cells_1d * (cells_1d + 1) / 2 / c->nparts >= 4 * (c->sm_count / c->cta_group));
     {
       ScopedStageTimer tm(c, WLD_STAGE_PAIR_PREP);
-      int rc = run_pair_prep(c, tm);
+      int rc = run_pair_prep(c, tm, try_screen);
+      if (rc != WLD_OK) return rc;
+    }
+    bool use_screen = false;
+    if (try_screen) {
+      if (c->screen_opt == 1) {
+        int rc = run_pair_umma(c, r2_threshold, 2);  // the screen over ~2 waves of tiles spread over the list: count only
+        if (rc != WLD_OK) return rc;
+      }
+      int rc = finish_quant(c);  // one synchronisation: the quantiser's decision and the sample's counters
+      if (rc != WLD_OK) return rc;
+      c->info.screen_top_min = c->quant_top_min;
+      c->info.sample_candidates = (int64_t)c->sample_host[0];
+      c->info.sample_pairs = (int64_t)c->sample_host[1];
+      // the bound needs every nonzero weight to fill its top limb reasonably (kappa = 2/top_min + ...), and a second limb to drop
+      const bool valid = c->geom.n_limbs >= 2 && c->geom.limb_bits == 8 && c->quant_top_min >= 32;
+      // a candidate costs about as much as 60-80 pairs of the exact kernel and the screen saves 2/3 - 3/4 of a pair
+      use_screen = valid && (c->screen_opt == 2 || c->sample_host[0] * 256 <= c->sample_host[1]);
+    }
+    if (c->pair_kernel != WLD_PAIR_KERNEL_SIMT && !use_screen) {
+      ScopedStageTimer tm(c, WLD_STAGE_PAIR_PREP);  // (shows the limb expansion only when the screen was tried first)
+      int rc = run_expand_limbs(c, tm, false);
+      if (rc != WLD_OK) return rc;
+    }
+    if (c->pair_kernel != WLD_PAIR_KERNEL_SIMT) {
+      int rc = ensure_tile_plan(c, use_screen ? 1 : 0);
       if (rc != WLD_OK) return rc;
     }
     const uint64_t total_pairs = (uint64_t)L * (uint64_t)(L - 1) / 2;
@@ -515,16 +559,28 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
       WLD_CUDA(c, c->pairs.ensure(sizeof(wld_pair) * (size_t)cap));
       c->pair_cap = c->pairs.bytes / sizeof(wld_pair);
     }
+    if (use_screen) {
+      // candidates: four times the rate the screen is chosen at (1 in 64), at least 2^16; grows like the survivors
+      const uint64_t want = std::max<uint64_t>(1ull << 16, c->plan_pairs / 64 + 1024);
+      c->cand_cap = c->cand.p ? c->cand.bytes / sizeof(uint2) : 0;
+      if (c->cand_cap < want) {
+        c->cand_cap = 0;
+        WLD_CUDA(c, c->cand.ensure(sizeof(uint2) * (size_t)want));
+        c->cand_cap = c->cand.bytes / sizeof(uint2);
+      }
+    }
     if (c->compat == WLD_COMPAT_PYTHON) {
       int rc = run_pair_python_prepare(c);
       if (rc != WLD_OK) return rc;
     }
     unsigned long long progress_last = 0;
-    for (int attempt = 0; attempt < 3; ++attempt) {
+    for (int attempt = 0; attempt < 4; ++attempt) {
       WLD_CUDA(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 8, c->stream));
       c->die_used = 0;
       {
-        int rc = c->pair_kernel == WLD_PAIR_KERNEL_SIMT ? run_pair_simt(c, r2_threshold) : run_pair_umma(c, r2_threshold);
+        int rc = c->pair_kernel == WLD_PAIR_KERNEL_SIMT ? run_pair_simt(c, r2_threshold)
+                                                        : run_pair_umma(c, r2_threshold, use_screen ? 1 : 0);
+        if (rc == WLD_OK && use_screen) rc = run_pair_refine(c, r2_threshold);
         // pairs whose per-pair allele call may differ from the per-site call (WeightedLD.py:186-211)
         if (rc == WLD_OK && c->compat == WLD_COMPAT_PYTHON) rc = run_pair_python_fixup(c, r2_threshold);
         if (rc != WLD_OK) return rc;
@@ -546,7 +602,7 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
           nanosleep(&ts, nullptr);
         }
       }
-      unsigned long long cnt[4] = {0, 0, 0, 0};
+      unsigned long long cnt[6] = {0, 0, 0, 0, 0, 0};
       cudaError_t e = cudaMemcpyAsync(cnt, c->counters.p, sizeof cnt, cudaMemcpyDeviceToHost, c->stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
       if (e != cudaSuccess)
@@ -559,6 +615,19 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
         continue;
       }
       c->pairs_computed = cnt[1];
+      if (use_screen) {
+        c->info.screen_candidates = (int64_t)cnt[5];
+        if (cnt[5] > c->cand_cap) {
+          // the count is exact and nothing was written past the end: grow and repeat the screen
+          const uint64_t want = cnt[5] + cnt[5] / 16 + 1024;
+          c->cand_cap = 0;
+          WLD_CUDA(c, c->cand.ensure(sizeof(uint2) * (size_t)want));
+          c->cand_cap = c->cand.bytes / sizeof(uint2);
+          ++c->info.screen_reruns;
+          if (attempt == 3) return c->fail(WLD_ERR_NOMEM, "candidate buffer kept overflowing");
+          continue;
+        }
+      }
       if (cnt[0] <= c->pair_cap) {
         c->n_survivors = cnt[0];
         break;
@@ -568,8 +637,9 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
       c->pair_cap = 0;
       WLD_CUDA(c, c->pairs.ensure(sizeof(wld_pair) * (size_t)want));
       c->pair_cap = c->pairs.bytes / sizeof(wld_pair);
-      if (attempt == 2) return c->fail(WLD_ERR_NOMEM, "survivor buffer kept overflowing");
+      if (attempt == 3) return c->fail(WLD_ERR_NOMEM, "survivor buffer kept overflowing");
     }
+    c->info.screen = use_screen ? 1 : 0;
     c->info.kernel = c->pair_kernel;
     c->info.die_schedule = c->die_used;
     c->info.n_limbs = c->geom.n_limbs;
@@ -625,8 +695,10 @@ int wld_plan_tiles(int64_t n_kept, int n_limbs, int cta_group, int part, int npa
   if (tiles_mn) {
     if (cap_tiles < plan.tiles.size()) return WLD_ERR_INVALID;
     for (size_t i = 0; i < plan.tiles.size(); ++i) {
-      tiles_mn[2 * i] = plan.tiles[i].x;
-      tiles_mn[2 * i + 1] = plan.tiles[i].y;
+      tiles_mn[4 * i] = plan.tiles[i].x;
+      tiles_mn[4 * i + 1] = plan.tiles[i].y;
+      tiles_mn[4 * i + 2] = plan.tiles[i].z;
+      tiles_mn[4 * i + 3] = plan.tiles[i].w;
     }
   }
   return WLD_OK;
