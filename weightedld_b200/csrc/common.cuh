@@ -155,7 +155,7 @@ struct wld_ctx {
   wld::DevPlan plans[2];           // tcgen05 schedules: [0] the exact kernel (n_limbs limbs), [1] the one-limb screen
   // screen + refine (pair_umma.cu kScreen, pair_refine.cu)
   int screen_opt = 1;              // wld_set_screen: 0 never, 1 automatic (sampled candidate rate), 2 always when valid
-  wld::DevBuf qi;                  // u64 [ldc]      the fixed-point weights as integers (pair_refine.cu)
+  wld::DevBuf glimb;               // u16 [4][ldc]   gain x limb per sequence and limb (pair_refine.cu)
   wld::DevBuf opB1;                // u8 [b1_groups*128][k_padded]: indicator x TOP limb, one-limb layout (64 sites / group)
   wld::DevBuf cand;                // uint2 [cand_cap] candidate site pairs of the screen
   uint64_t cand_cap = 0;

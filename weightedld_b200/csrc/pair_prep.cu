@@ -76,7 +76,7 @@ __device__ __forceinline__ T block_reduce_1024(T v, T* s_buf, Op op) {
 __global__ void __launch_bounds__(1024) quantize_kernel(const float* __restrict__ w, int64_t n_seqs, int64_t ldc,
                                                         int nl_opt, int gain_opt, int bits_opt, unsigned long long exact_limit,
                                                         int may_narrow, double* __restrict__ q,
-                                                        unsigned long long* __restrict__ qi,
+                                                        uint16_t* __restrict__ glimb,
                                                         uint16_t* __restrict__ limbs, uint8_t* __restrict__ limbs8,
                                                         uint8_t* __restrict__ gain8, QuantDecision* __restrict__ out) {
   __shared__ float s_f[32];
@@ -174,13 +174,13 @@ __global__ void __launch_bounds__(1024) quantize_kernel(const float* __restrict_
       if (u > 0.0) err = fmax(err, fabs(ldexp((double)m, -e) / scale - u) / u);
     }
     q[s] = (double)(m * g);
-    qi[s] = m * g;
     gain8[s] = (uint8_t)g;
     if (m > 0) top_min = min(top_min, (unsigned)(m >> (bits * (nl - 1))) & mask);
     for (int l = 0; l < nl; ++l) {
       const uint32_t v = (uint32_t)(m >> (bits * (nl - 1 - l))) & mask;
       limbs[(int64_t)l * ldc + s] = (uint16_t)v;  // raw limb value 0..255; converted at expansion
       limbs8[(int64_t)l * ldc + s] = (uint8_t)v;  // the same as bytes for the u8 operands (SWAR expansion)
+      glimb[(int64_t)l * ldc + s] = (uint16_t)(v * g);  // gain x limb < 2^15: what pair_refine.cu sums (dp2a)
     }
   }
   const unsigned long long err_bits = block_reduce_1024((unsigned long long)__double_as_longlong(err), s_u,
@@ -361,6 +361,53 @@ __global__ void __launch_bounds__(256) expand_b_kernel(const uint8_t* __restrict
   }
 }
 
+// Screen operands in one pass over the code matrix (u8 only).  The one-limb layout of the limb operand puts site j
+// at rows 2j, 2j+1 — the same indexing as the indicator operand — so a thread reads the 16 codes of (site, sequence
+// block) once and writes four 16-byte row segments: opA[2i + alpha] = indicator x gain (sites in [a_lo, a_hi)) and
+// opB1[2i + beta] = indicator x TOP limb (sites in [b_lo, b_hi)).  Sites >= n_kept are zero rows.
+__global__ void __launch_bounds__(256) expand_screen_kernel(const uint8_t* __restrict__ codes, int64_t ldc, int64_t n_kept,
+                                                            const int8_t* __restrict__ maj, const int8_t* __restrict__ mnr,
+                                                            const uint8_t* __restrict__ gain8, const uint8_t* __restrict__ top8,
+                                                            int64_t kp, int64_t site0, int64_t a_lo, int64_t a_hi, int64_t b_lo,
+                                                            int64_t b_hi, uint8_t* __restrict__ opA, uint8_t* __restrict__ opB1) {
+  const int64_t i = site0 + blockIdx.y;
+  const int64_t s0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 16;
+  if (s0 >= kp) return;
+  const bool do_a = i >= a_lo && i < a_hi, do_b = i >= b_lo && i < b_hi;
+  uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0;
+  if (i < n_kept) {
+    const uint4 cv = __ldg(reinterpret_cast<const uint4*>(codes + i * ldc + s0));
+    const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w};
+    const int sm = maj[i], sn = mnr[i];
+    const uint32_t rm = sm < 0 ? 0xffffffffu : (uint32_t)sm * 0x01010101u;  // 0xff never matches a code
+    const uint32_t rn = sn < 0 ? 0xffffffffu : (uint32_t)sn * 0x01010101u;
+    uint32_t mm[4], mn[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      mm[w] = __vcmpeq4(cw[w], rm);
+      mn[w] = __vcmpeq4(cw[w], rn);
+    }
+    if (do_a) {
+      const uint4 g = __ldg(reinterpret_cast<const uint4*>(gain8 + s0));  // 0 in the K padding
+      a0 = make_uint4(g.x & mm[0], g.y & mm[1], g.z & mm[2], g.w & mm[3]);
+      a1 = make_uint4(g.x & mn[0], g.y & mn[1], g.z & mn[2], g.w & mn[3]);
+    }
+    if (do_b) {
+      const uint4 t = __ldg(reinterpret_cast<const uint4*>(top8 + s0));
+      b0 = make_uint4(t.x & mm[0], t.y & mm[1], t.z & mm[2], t.w & mm[3]);
+      b1 = make_uint4(t.x & mn[0], t.y & mn[1], t.z & mn[2], t.w & mn[3]);
+    }
+  }
+  if (do_a) {
+    *reinterpret_cast<uint4*>(opA + (2 * i) * kp + s0) = a0;
+    *reinterpret_cast<uint4*>(opA + (2 * i + 1) * kp + s0) = a1;
+  }
+  if (do_b) {
+    *reinterpret_cast<uint4*>(opB1 + (2 * i) * kp + s0) = b0;
+    *reinterpret_cast<uint4*>(opB1 + (2 * i + 1) * kp + s0) = b1;
+  }
+}
+
 }  // namespace
 
 // Reads the quantiser's decision back (one synchronisation) and fixes the geometry of the exact kernel.
@@ -402,7 +449,7 @@ int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm, bool try_screen) {
                                                                                 : (1ull << 24);
 
   WLD_CUDA(c, c->q.ensure(sizeof(double) * (size_t)c->ldc));
-  WLD_CUDA(c, c->qi.ensure(sizeof(unsigned long long) * (size_t)c->ldc));
+  WLD_CUDA(c, c->glimb.ensure(sizeof(uint16_t) * 4 * (size_t)c->ldc));
   WLD_CUDA(c, c->limbs.ensure((sizeof(uint16_t) + 1) * 4 * (size_t)c->ldc));  // u16 [4][ldc] then u8 [4][ldc]
   WLD_CUDA(c, c->gain8.ensure((size_t)c->ldc));
   WLD_CUDA(c, c->quant.ensure(sizeof(QuantDecision)));
@@ -417,7 +464,7 @@ int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm, bool try_screen) {
   // One launch quantises the weights AND decides limbs / limb width / gain bits; one read-back tells the host.
   quantize_kernel<<<1, 1024, 0, c->stream>>>(c->w32.as<float>(), n, c->ldc, c->n_limbs_opt, c->gain_opt, c->limb_bits_opt, exact_limit,
                                              c->pair_kernel == WLD_PAIR_KERNEL_UMMA ? 1 : 0, c->q.as<double>(),
-                                             c->qi.as<unsigned long long>(), c->limbs.as<uint16_t>(),
+                                             c->glimb.as<uint16_t>(), c->limbs.as<uint16_t>(),
                                              c->limbs.as<uint8_t>() + sizeof(uint16_t) * 4 * (size_t)c->ldc,
                                              c->gain8.as<uint8_t>(), c->quant.as<QuantDecision>());
   tm.launched();
@@ -447,6 +494,23 @@ int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm, bool try_screen) {
   if (dp.n_tiles == 0) return WLD_OK;
   const int64_t tile_m = 64 * c->cta_group;
   const int64_t site_lo = dp.x[0] * tile_m, site_hi = std::min<int64_t>(gm.a_rows / 2, (dp.x[1] + 1) * tile_m);
+  if (try_screen) {
+    // both screen operands from one read of the code matrix (row 2i + {0, 1} of either holds site i)
+    const int64_t b_rows = round_up(std::max<int64_t>((L + 63) / 64, 1), 2) * 128;  // an N tile is two 128-row groups
+    WLD_CUDA(c, c->opB1.ensure((size_t)b_rows * (size_t)kp));
+    const int64_t b_lo = dp.y[0] * 128, b_hi = std::min<int64_t>(b_rows / 2, (dp.y[1] + 1) * 128);  // sites of the N tiles in use
+    const int64_t lo = std::min(site_lo, b_lo), hi = std::max(site_hi, b_hi);
+    const uint8_t* top8 = c->limbs.as<uint8_t>() + sizeof(uint16_t) * 4 * (size_t)c->ldc;  // limb 0 = most significant
+    for (int64_t y0 = lo; y0 < hi; y0 += 65535) {
+      const unsigned ny = (unsigned)std::min<int64_t>(65535, hi - y0);
+      expand_screen_kernel<<<dim3(kblocks, ny), 256, 0, c->stream>>>(
+          c->codes.as<uint8_t>(), c->ldc, L, c->maj.as<int8_t>(), c->mnr.as<int8_t>(), c->gain8.as<uint8_t>(), top8, kp, y0,
+          site_lo, site_hi, b_lo, b_hi, c->opA.as<uint8_t>(), c->opB1.as<uint8_t>());
+      tm.launched();
+    }
+    WLD_CUDA(c, cudaGetLastError());
+    return WLD_OK;
+  }
   // grid.y limit is 65535: fold larger site counts into several launches
   for (int64_t y0 = site_lo; y0 < site_hi; y0 += 65535) {
     const unsigned ny = (unsigned)std::min<int64_t>(65535, site_hi - y0);
@@ -457,7 +521,6 @@ int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm, bool try_screen) {
     tm.launched();
   }
   WLD_CUDA(c, cudaGetLastError());
-  if (try_screen) return run_expand_limbs(c, tm, true);
   return WLD_OK;
 }
 

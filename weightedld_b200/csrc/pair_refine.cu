@@ -9,9 +9,13 @@
 // (lib.rs:482-518, 660).  These are the sums the exact n-limb tensor kernel accumulates, so the surviving
 // records are identical bit for bit; only the order in the survivor buffer differs, and pair_order.cu sorts it.
 //
-// Cost: 2 code rows (2 * ldc bytes, mostly L2 hits: candidates arrive grouped by tile) + the weights (8 * ldc
-// bytes, L2 resident) per candidate, ~14 integer instructions per sequence.  The f64 statistics run on batches
-// of up to 32 candidates, one per lane, because B200's FP64 pipe is narrow.
+// Cost per candidate: its two code rows (2 * ldc bytes from L2; candidates arrive grouped by tile) and ~10 integer
+// instructions per sequence.  The sums are taken limb by limb with the 16 x 8-bit dot product (dp2a): the
+// quantiser leaves v_l[s] = gain[s] * limb_l[s] (< 2^15) per sequence and limb, a cell's indicator is a byte mask
+// (0x80 where the sequence belongs to the cell), and acc[cell][l] += v_l[s] * mask[s] runs two sequences per
+// instruction in u32, flushed into u64 every 2048 sequences.  The v_l (2 NL bytes per sequence, the larger stream)
+// are staged in shared memory once per group of 16 candidates.  The f64 statistics run once per candidate (one
+// lane), B200's FP64 pipe being narrow.
 #include "common.cuh"
 #include "pair_epilogue.cuh"
 
@@ -19,8 +23,10 @@ namespace wld {
 namespace {
 
 constexpr int kRefineWarps = 8;
-
-__device__ __forceinline__ uint32_t rep4(int sym) { return sym < 0 ? 0xffffffffu : (uint32_t)sym * 0x01010101u; }  // 0xff never matches a code
+constexpr int kPerWarp = 2;                              // candidates a warp carries through one pass
+constexpr int kGroup = kRefineWarps * kPerWarp;          // candidates per block pass: they share the staged weights
+constexpr int kChunk = 2048;                             // sequences staged in shared memory at a time
+constexpr int kSteps = kChunk / 128;                     // a warp covers 128 sequences per step (4 per lane)
 
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
 #pragma unroll
@@ -28,69 +34,108 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
   return v;
 }
 
+// z = 8 * code_a + code_b per byte (<= 45); a cell is one value of z.  0x3f never occurs: the cell of a missing allele.
+__device__ __forceinline__ uint32_t cell_key(int sym_a, int sym_b) {
+  return (sym_a < 0 || sym_b < 0) ? 0x3f3f3f3fu : (uint32_t)(sym_a * 8 + sym_b) * 0x01010101u;
+}
+// 0x80 in every byte where z == key (both below 0x40, so x = z ^ key < 0x40 and x + 0x7f carries into bit 7 iff x != 0)
+__device__ __forceinline__ uint32_t match80(uint32_t z, uint32_t key) { return ~((z ^ key) + 0x7f7f7f7fu) & 0x80808080u; }
+
+template <int NL>
 __global__ void __launch_bounds__(32 * kRefineWarps) pair_refine_kernel(
     const uint8_t* __restrict__ codes, int64_t ldc, const int8_t* __restrict__ maj, const int8_t* __restrict__ mnr,
-    const unsigned long long* __restrict__ qi, const uint2* __restrict__ cand, const unsigned long long* __restrict__ n_cand,
-    unsigned long long cap, float thr, PairOut out) {
-  const int lane = threadIdx.x & 31;
+    const uint16_t* __restrict__ glimb, int limb_bits, const uint2* __restrict__ cand,
+    const unsigned long long* __restrict__ n_cand, unsigned long long cap, float thr, PairOut out) {
+  __shared__ __align__(16) uint16_t s_v[NL][kChunk];  // gain x limb of the chunk's sequences
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned long long n = min(*n_cand, cap);
-  const unsigned long long n_warps = (unsigned long long)gridDim.x * kRefineWarps;
-  // lane k of the warp keeps the sums of the k-th candidate of the current batch
-  unsigned long long mAB = 0, mAb = 0, maB = 0, mab = 0;
-  uint32_t mi = 0, mj = 0;
-  int batch = 0;
-  auto flush = [&]() {
-    bool keep = lane < batch;
-    float d = 0.f, dp = 0.f, r2 = 0.f;
-    if (keep) {
-      const double AB = (double)mAB, Ab = (double)mAb, aB = (double)maB, ab = (double)mab;  // < 2^53: exact
-      const double A = AB + Ab, B = AB + aB, T = A + (aB + ab);
-      // an empty marginal is NaN in the reference and dropped by lib.rs:660 (the screen never proposes one)
-      keep = A > 0.0 && B > 0.0 && T - A > 0.0 && T - B > 0.0 && ld_stats_exact(AB, Ab, aB, ab, thr, d, dp, r2);
+  for (unsigned long long g0 = (unsigned long long)blockIdx.x * kGroup; g0 < n; g0 += (unsigned long long)gridDim.x * kGroup) {
+    uint2 ij[kPerWarp];
+    const uint8_t* ra[kPerWarp];
+    const uint8_t* rb[kPerWarp];
+    uint32_t key[kPerWarp][4];                // AB, Ab, aB, ab
+    unsigned long long sum[kPerWarp][4];
+    bool live[kPerWarp];
+#pragma unroll
+    for (int c = 0; c < kPerWarp; ++c) {
+      const unsigned long long k = g0 + (unsigned long long)(warp * kPerWarp + c);
+      live[c] = k < n;
+      ij[c] = live[c] ? cand[k] : make_uint2(0u, 0u);
+      ra[c] = codes + (int64_t)ij[c].x * ldc;
+      rb[c] = codes + (int64_t)ij[c].y * ldc;
+      const int aM = maj[ij[c].x], am = mnr[ij[c].x], bM = maj[ij[c].y], bm = mnr[ij[c].y];
+      key[c][0] = cell_key(aM, bM); key[c][1] = cell_key(aM, bm);
+      key[c][2] = cell_key(am, bM); key[c][3] = cell_key(am, bm);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) sum[c][t] = 0;
     }
-    emit_pairs_warp(keep, mi, mj, d, dp, r2, out);
-    batch = 0;
-  };
-  for (unsigned long long k = (unsigned long long)blockIdx.x * kRefineWarps + (threadIdx.x >> 5); k < n; k += n_warps) {
-    const uint2 ij = cand[k];
-    const uint8_t* ra = codes + (int64_t)ij.x * ldc;
-    const uint8_t* rb = codes + (int64_t)ij.y * ldc;
-    const uint32_t aM = rep4(maj[ij.x]), am = rep4(mnr[ij.x]), bM = rep4(maj[ij.y]), bm = rep4(mnr[ij.y]);
-    unsigned long long AB = 0, Ab = 0, aB = 0, ab = 0;
-    for (int64_t s0 = 16 * lane; s0 < ldc; s0 += 512) {  // ldc is a multiple of 128; the padding holds code 5 and q = 0
-      const uint4 ca = __ldg(reinterpret_cast<const uint4*>(ra + s0));
-      const uint4 cb = __ldg(reinterpret_cast<const uint4*>(rb + s0));
-      const uint32_t wa[4] = {ca.x, ca.y, ca.z, ca.w}, wb[4] = {cb.x, cb.y, cb.z, cb.w};
+    for (int64_t c0 = 0; c0 < ldc; c0 += kChunk) {  // ldc is a multiple of 128; the padding holds code 5
+      const int len = (int)min((int64_t)kChunk, ldc - c0);
+      __syncthreads();  // the previous chunk has been consumed
 #pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        const uint32_t eaM = __vcmpeq4(wa[w], aM), eam = __vcmpeq4(wa[w], am);
-        const uint32_t ebM = __vcmpeq4(wb[w], bM), ebm = __vcmpeq4(wb[w], bm);
-        const uint32_t xAB = eaM & ebM, xAb = eaM & ebm, xaB = eam & ebM, xab = eam & ebm;
-        if ((xAB | xAb | xaB | xab) == 0u) continue;
-        const ulonglong2 q01 = __ldg(reinterpret_cast<const ulonglong2*>(qi + s0 + 4 * w));
-        const ulonglong2 q23 = __ldg(reinterpret_cast<const ulonglong2*>(qi + s0 + 4 * w + 2));
-        const unsigned long long qv[4] = {q01.x, q01.y, q23.x, q23.y};
+      for (int l = 0; l < NL; ++l)
+        for (int s = 8 * threadIdx.x; s < len; s += 8 * 32 * kRefineWarps)
+          *reinterpret_cast<uint4*>(&s_v[l][s]) = __ldg(reinterpret_cast<const uint4*>(glimb + (int64_t)l * ldc + c0 + s));
+      __syncthreads();
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const uint32_t bit = 0x80u << (8 * b);
-          if (xAB & bit) AB += qv[b];
-          if (xAb & bit) Ab += qv[b];
-          if (xaB & bit) aB += qv[b];
-          if (xab & bit) ab += qv[b];
+      for (int c = 0; c < kPerWarp; ++c) {
+        if (!live[c]) continue;  // warp-uniform
+        // all code words of the chunk first (32 loads in flight per warp), then the arithmetic
+        uint32_t z[kSteps];
+#pragma unroll
+        for (int u = 0; u < kSteps; ++u) {
+          const int s = 128 * u + 4 * lane;
+          const bool in = 128 * u < len;  // warp-uniform: len is a multiple of 128
+          const uint32_t wa = in ? __ldg(reinterpret_cast<const uint32_t*>(ra[c] + c0 + s)) : 0x05050505u;
+          const uint32_t wb = in ? __ldg(reinterpret_cast<const uint32_t*>(rb[c] + c0 + s)) : 0x05050505u;
+          z[u] = wa * 8u + wb;  // bytes stay below 0x40: no carries
         }
+        uint32_t acc[4][NL];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+          for (int l = 0; l < NL; ++l) acc[t][l] = 0;
+#pragma unroll
+        for (int u = 0; u < kSteps; ++u) {
+          if (128 * u >= len) break;
+          const int s = 128 * u + 4 * lane;
+          uint32_t m[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) m[t] = match80(z[u], key[c][t]);
+#pragma unroll
+          for (int l = 0; l < NL; ++l) {
+            const uint2 v = *reinterpret_cast<const uint2*>(&s_v[l][s]);  // sequences s, s+1 | s+2, s+3
+#pragma unroll
+            for (int t = 0; t < 4; ++t) acc[t][l] = __dp2a_hi(v.y, m[t], __dp2a_lo(v.x, m[t], acc[t][l]));
+          }
+        }
+        // <= 64 sequences x 2^15 x 0x80 per lane and chunk: below 2^32; recombine the limbs in 64 bits
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+          for (int l = 0; l < NL; ++l) sum[c][t] += (unsigned long long)(acc[t][l] >> 7) << (limb_bits * (NL - 1 - l));
       }
     }
-    AB = warp_sum_u64(AB);
-    Ab = warp_sum_u64(Ab);
-    aB = warp_sum_u64(aB);
-    ab = warp_sum_u64(ab);
-    if (lane == batch) {
-      mAB = AB; mAb = Ab; maB = aB; mab = ab;
-      mi = ij.x; mj = ij.y;
+    // lane c of the warp finishes candidate c (the f64 pipe is narrow: one evaluation per candidate, not 32)
+    bool keep = false;
+    float d = 0.f, dp = 0.f, r2 = 0.f;
+    uint32_t mi = 0, mj = 0;
+#pragma unroll
+    for (int c = 0; c < kPerWarp; ++c) {
+      unsigned long long t[4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) t[x] = warp_sum_u64(sum[c][x]);
+      if (lane == c && live[c]) {
+        const double AB = (double)t[0], Ab = (double)t[1], aB = (double)t[2], ab = (double)t[3];  // < 2^53: exact
+        const double A = AB + Ab, B = AB + aB, T = A + (aB + ab);
+        // an empty marginal is NaN in the reference and dropped by lib.rs:660 (the screen never proposes one)
+        keep = A > 0.0 && B > 0.0 && T - A > 0.0 && T - B > 0.0 && ld_stats_exact(AB, Ab, aB, ab, thr, d, dp, r2);
+        mi = ij[c].x;
+        mj = ij[c].y;
+      }
     }
-    if (++batch == 32) flush();
+    emit_pairs_warp(keep, mi, mj, d, dp, r2, out);
   }
-  if (batch > 0) flush();
 }
 
 }  // namespace
@@ -99,10 +144,14 @@ int run_pair_refine(wld_ctx* c, float thr) {
   unsigned long long* cnt = c->counters.as<unsigned long long>();
   PairOut out{c->pairs.as<wld_pair>(), cnt, c->pair_cap};
   ScopedStageTimer tm(c, WLD_STAGE_PAIR_REFINE);
-  // the candidate count lives on the device: a fixed grid of warps strides over it
-  pair_refine_kernel<<<c->sm_count * 4, 32 * kRefineWarps, 0, c->stream>>>(
-      c->codes.as<uint8_t>(), c->ldc, c->maj.as<int8_t>(), c->mnr.as<int8_t>(), c->qi.as<unsigned long long>(),
-      c->cand.as<uint2>(), cnt + 5, c->cand_cap, thr, out);
+  // the candidate count lives on the device: a fixed grid of blocks strides over it
+  const dim3 grid((unsigned)(c->sm_count * 4)), block(32 * kRefineWarps);
+  const int nl = c->geom.n_limbs;
+  auto kern = nl == 2 ? pair_refine_kernel<2> : nl == 3 ? pair_refine_kernel<3> : pair_refine_kernel<4>;
+  if (nl < 2 || nl > 4) return c->fail(WLD_ERR_INVALID, "the refinement needs 2..4 limbs");
+  kern<<<grid, block, 0, c->stream>>>(c->codes.as<uint8_t>(), c->ldc, c->maj.as<int8_t>(), c->mnr.as<int8_t>(),
+                                      c->glimb.as<uint16_t>(), c->geom.limb_bits, c->cand.as<uint2>(), cnt + 5, c->cand_cap,
+                                      thr, out);
   tm.launched();
   WLD_CUDA(c, cudaGetLastError());
   return WLD_OK;

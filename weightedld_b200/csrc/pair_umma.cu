@@ -904,8 +904,9 @@ int run_pair_umma(wld_ctx* c, float thr, int mode) {
   int64_t n_tiles = dp.n_tiles;
   int tile_mul = 1;
   const int64_t pairs_of_ctas = c->sm_count / ctas;
-  if (mode == 2) {  // about two waves of tiles, evenly spread over the list
-    tile_mul = (int)std::max<int64_t>(1, n_tiles / (2 * pairs_of_ctas));
+  if (mode == 2) {  // two waves of tiles (one when the schedule is short: multi-GPU shares), evenly spread over the list
+    const int64_t waves = n_tiles >= 64 * pairs_of_ctas ? 2 : 1;
+    tile_mul = (int)std::max<int64_t>(1, n_tiles / (waves * pairs_of_ctas));
     n_tiles = (n_tiles + tile_mul - 1) / tile_mul;
   }
   if (mode != 2) {

@@ -71,7 +71,7 @@ void wld_destroy(wld_ctx* c) {
   DevBuf* bufs[] = {&c->raw_own, &c->hist, &c->keep, &c->rank, &c->maj_raw, &c->min_raw, &c->site_map, &c->maj,
                     &c->mnr, &c->kept_count, &c->codes, &c->table, &c->partial, &c->w64, &c->w32, &c->scalars,
                     &c->q, &c->limbs, &c->opA, &c->opB, &c->simt_tiles, &c->pairs, &c->counters, &c->py_aux, &c->die_of_sm,
-                    &c->sorted, &c->sort_keys, &c->sort_idx, &c->sort_temp, &c->gain8, &c->quant, &c->qi, &c->opB1,
+                    &c->sorted, &c->sort_keys, &c->sort_idx, &c->sort_temp, &c->gain8, &c->quant, &c->glimb, &c->opB1,
                     &c->cand, &c->plans[0].tiles, &c->plans[1].tiles};
   for (DevBuf* b : bufs) b->release();
   if (c->quant_host) cudaFreeHost(c->quant_host);
@@ -560,8 +560,8 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
       c->pair_cap = c->pairs.bytes / sizeof(wld_pair);
     }
     if (use_screen) {
-      // candidates: four times the rate the screen is chosen at (1 in 64), at least 2^16; grows like the survivors
-      const uint64_t want = std::max<uint64_t>(1ull << 16, c->plan_pairs / 64 + 1024);
+      // candidates: four times the rate the screen is chosen at (1 in 64), between 2^16 and 2^26 (512 MB); grows like the survivors
+      const uint64_t want = std::min<uint64_t>(std::max<uint64_t>(1ull << 16, c->plan_pairs / 64 + 1024), 1ull << 26);
       c->cand_cap = c->cand.p ? c->cand.bytes / sizeof(uint2) : 0;
       if (c->cand_cap < want) {
         c->cand_cap = 0;
