@@ -207,3 +207,20 @@ def test_partitions_may_mix_screen_and_exact_kernel(nparts):
     assert done == whole["done"]
     merged = wld.merge_shards(whole["n_kept"], shards, whole["site_map"])
     assert merged.tobytes() == whole["pairs"].tobytes()
+
+
+@pytest.mark.gpu
+def test_refinement_gives_up_when_the_sample_was_blind(monkeypatch):
+    """A heterogeneous input can hide its high-LD region from the sample.  The refinement then finds far more
+    candidates than refining one by one is worth, declines, and the exact kernel runs over the same pairs."""
+    hi = synth(1000, 6000, seed=12, founders=64, block=400, clonal=True, stray=0.02, private_rate=0.002)
+    a = run(hi, "never")
+    monkeypatch.setenv("WLD_SAMPLE_BLIND", "1")
+    b = run(hi, "auto")
+    assert b["info"].screen == 0 and b["info"].screen_candidates > b["done"] // 128   # screened, gave up, exact kernel
+    assert a["pairs"].tobytes() == b["pairs"].tobytes() and len(a["pairs"]) > 0.05 * a["done"]
+    # the same in two partitions
+    import weightedld_b200 as wld
+    kept = wld.FETCH_KEPT_INDEX | wld.FETCH_UNORDERED
+    shards = [run(hi, "auto", partition=(p, 2), flags=kept)["pairs"] for p in range(2)]
+    assert wld.merge_shards(a["n_kept"], shards, a["site_map"]).tobytes() == a["pairs"].tobytes()

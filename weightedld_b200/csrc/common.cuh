@@ -241,7 +241,7 @@ int run_pair_simt(wld_ctx* c, float thr);                                  // pa
 // 2: the screen over a sample of the tiles, counting only (counters[8..9])
 int run_pair_umma(wld_ctx* c, float thr, int mode);                        // pair_umma.cu
 int ensure_tile_plan(wld_ctx* c, int which);                               // pair_umma.cu (which: 0 exact, 1 screen)
-int run_pair_refine(wld_ctx* c, float thr);                                // pair_refine.cu: exact statistics of the candidates
+int run_pair_refine(wld_ctx* c, float thr, unsigned long long give_up);    // pair_refine.cu: exact statistics of the candidates (none if more than give_up)
 int run_pair_order(wld_ctx* c, bool ordered, bool parent);                 // pair_order.cu
 const std::vector<uint8_t>& die_map(wld_ctx* c);                            // die_map.cu: SM -> L2 die (empty = unknown)
 int run_pair_python_prepare(wld_ctx* c);                                   // pair_python.cu

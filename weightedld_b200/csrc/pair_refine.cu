@@ -45,9 +45,16 @@ template <int NL>
 __global__ void __launch_bounds__(32 * kRefineWarps) pair_refine_kernel(
     const uint8_t* __restrict__ codes, int64_t ldc, const int8_t* __restrict__ maj, const int8_t* __restrict__ mnr,
     const uint16_t* __restrict__ glimb, int limb_bits, const uint2* __restrict__ cand,
-    const unsigned long long* __restrict__ n_cand, unsigned long long cap, float thr, PairOut out) {
+    const unsigned long long* __restrict__ n_cand, unsigned long long cap, unsigned long long give_up,
+    unsigned long long* __restrict__ gave_up, float thr, PairOut out) {
   __shared__ __align__(16) uint16_t s_v[NL][kChunk];  // gain x limb of the chunk's sequences
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (*n_cand > give_up) {
+    // far more candidates than the sample promised (heterogeneous input): refining them one by one would cost more
+    // than the exact tensor kernel over every pair — tell the host, which runs that instead
+    if (blockIdx.x == 0 && threadIdx.x == 0) *gave_up = 1ull;
+    return;
+  }
   const unsigned long long n = min(*n_cand, cap);
   for (unsigned long long g0 = (unsigned long long)blockIdx.x * kGroup; g0 < n; g0 += (unsigned long long)gridDim.x * kGroup) {
     uint2 ij[kPerWarp];
@@ -140,7 +147,7 @@ __global__ void __launch_bounds__(32 * kRefineWarps) pair_refine_kernel(
 
 }  // namespace
 
-int run_pair_refine(wld_ctx* c, float thr) {
+int run_pair_refine(wld_ctx* c, float thr, unsigned long long give_up) {
   unsigned long long* cnt = c->counters.as<unsigned long long>();
   PairOut out{c->pairs.as<wld_pair>(), cnt, c->pair_cap};
   ScopedStageTimer tm(c, WLD_STAGE_PAIR_REFINE);
@@ -151,7 +158,7 @@ int run_pair_refine(wld_ctx* c, float thr) {
   if (nl < 2 || nl > 4) return c->fail(WLD_ERR_INVALID, "the refinement needs 2..4 limbs");
   kern<<<grid, block, 0, c->stream>>>(c->codes.as<uint8_t>(), c->ldc, c->maj.as<int8_t>(), c->mnr.as<int8_t>(),
                                       c->glimb.as<uint16_t>(), c->geom.limb_bits, c->cand.as<uint2>(), cnt + 5, c->cand_cap,
-                                      thr, out);
+                                      give_up, cnt + 6, thr, out);
   tm.launched();
   WLD_CUDA(c, cudaGetLastError());
   return WLD_OK;

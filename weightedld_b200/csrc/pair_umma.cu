@@ -73,6 +73,7 @@ struct UmmaParams {
   const uint4* tiles;   // {M tile, N tile, first site j, end site j}: only pairs with j inside the window count
   int n_tiles;          // tiles this launch walks: tile k of the launch is tiles[k * tile_mul]
   int tile_mul;         // 1, or the stride of a sampling launch
+  int k_mul;            // 1, or the stride over K blocks of a sampling launch (an unbiased subsample of the sequences)
   int k_blocks;
   int n_kept;
   int limb_bits;
@@ -510,12 +511,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
           mbar_wait(empty_bar(stage), phase ^ 1u, p.error_flag, 1);
           if constexpr (kCtas == 2) {
             if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::kBytes);
-            tma_load_2d_cg2(sA + stage * kAStageBytes, &tmA, kb * kBlockK, m_row, full_bar(stage), p.hint_a);
-            tma_load_2d_cg2(sB + stage * Cfg::kBBytes, &tmB, kb * kBlockK, n_row, full_bar(stage), p.hint_b);
+            tma_load_2d_cg2(sA + stage * kAStageBytes, &tmA, kb * p.k_mul * kBlockK, m_row, full_bar(stage), p.hint_a);
+            tma_load_2d_cg2(sB + stage * Cfg::kBBytes, &tmB, kb * p.k_mul * kBlockK, n_row, full_bar(stage), p.hint_b);
           } else {
             mbar_expect_tx(full_bar(stage), Cfg::kBytes);
-            tma_load_2d(sA + stage * kAStageBytes, &tmA, kb * kBlockK, m_row, full_bar(stage), p.hint_a);
-            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, kb * kBlockK, n_row, full_bar(stage), p.hint_b);
+            tma_load_2d(sA + stage * kAStageBytes, &tmA, kb * p.k_mul * kBlockK, m_row, full_bar(stage), p.hint_a);
+            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, kb * p.k_mul * kBlockK, n_row, full_bar(stage), p.hint_b);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -930,6 +931,13 @@ int run_pair_umma(wld_ctx* c, float thr, int mode) {
   prm.n_tiles = (int)n_tiles;
   prm.tile_mul = tile_mul;
   prm.k_blocks = (int)(gm.k_padded * gm.elem_bytes / kBlockKBytes);
+  prm.k_mul = 1;
+  if (mode == 2 && prm.k_blocks > 64) {
+    // The sample only has to tell "a few candidates in 10^5 pairs" from "a few in 10": every k_mul-th block of 128
+    // sequences (about 6 000 of them, spread over the whole alignment) estimates that as well as all of them.
+    prm.k_mul = (prm.k_blocks + 47) / 48;
+    prm.k_blocks = (prm.k_blocks + prm.k_mul - 1) / prm.k_mul;
+  }
   prm.n_kept = (int)c->n_kept;
   prm.limb_bits = gm.limb_bits;
   prm.thr = thr;

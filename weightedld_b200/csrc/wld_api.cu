@@ -527,7 +527,9 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
       // the bound needs every nonzero weight to fill its top limb reasonably (kappa = 2/top_min + ...), and a second limb to drop
       const bool valid = c->geom.n_limbs >= 2 && c->geom.limb_bits == 8 && c->quant_top_min >= 32;
       // a candidate costs about as much as 60-80 pairs of the exact kernel and the screen saves 2/3 - 3/4 of a pair
-      use_screen = valid && (c->screen_opt == 2 || c->sample_host[0] * 256 <= c->sample_host[1]);
+      // (WLD_SAMPLE_BLIND=1, tests: pretend the sample saw nothing, as it may on a heterogeneous input)
+      const char* blind = std::getenv("WLD_SAMPLE_BLIND");
+      use_screen = valid && (c->screen_opt == 2 || (blind && blind[0] == '1') || c->sample_host[0] * 256 <= c->sample_host[1]);
     }
     if (c->pair_kernel != WLD_PAIR_KERNEL_SIMT && !use_screen) {
       ScopedStageTimer tm(c, WLD_STAGE_PAIR_PREP);  // (shows the limb expansion only when the screen was tried first)
@@ -580,7 +582,9 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
       {
         int rc = c->pair_kernel == WLD_PAIR_KERNEL_SIMT ? run_pair_simt(c, r2_threshold)
                                                         : run_pair_umma(c, r2_threshold, use_screen ? 1 : 0);
-        if (rc == WLD_OK && use_screen) rc = run_pair_refine(c, r2_threshold);
+        // automatic mode: twice the candidate rate the screen is chosen at is the point of no return (pair_refine.cu)
+        if (rc == WLD_OK && use_screen)
+          rc = run_pair_refine(c, r2_threshold, c->screen_opt == 2 ? ~0ull : std::max<uint64_t>(c->plan_pairs / 128, 1ull << 16));
         // pairs whose per-pair allele call may differ from the per-site call (WeightedLD.py:186-211)
         if (rc == WLD_OK && c->compat == WLD_COMPAT_PYTHON) rc = run_pair_python_fixup(c, r2_threshold);
         if (rc != WLD_OK) return rc;
@@ -602,7 +606,7 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
           nanosleep(&ts, nullptr);
         }
       }
-      unsigned long long cnt[6] = {0, 0, 0, 0, 0, 0};
+      unsigned long long cnt[7] = {0, 0, 0, 0, 0, 0, 0};
       cudaError_t e = cudaMemcpyAsync(cnt, c->counters.p, sizeof cnt, cudaMemcpyDeviceToHost, c->stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
       if (e != cudaSuccess)
@@ -617,6 +621,16 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
       c->pairs_computed = cnt[1];
       if (use_screen) {
         c->info.screen_candidates = (int64_t)cnt[5];
+        if (cnt[6]) {
+          // the refinement declined: the exact kernel over this partition's pairs (the same pairs: canonical cells)
+          use_screen = false;
+          ScopedStageTimer tm(c, WLD_STAGE_PAIR_PREP);
+          int rc = run_expand_limbs(c, tm, false);
+          if (rc == WLD_OK) rc = ensure_tile_plan(c, 0);
+          if (rc != WLD_OK) return rc;
+          --attempt;
+          continue;
+        }
         if (cnt[5] > c->cand_cap) {
           // the count is exact and nothing was written past the end: grow and repeat the screen
           const uint64_t want = cnt[5] + cnt[5] / 16 + 1024;
