@@ -58,6 +58,13 @@ def make_input(name: str) -> np.ndarray:
     return make_alignment(n, l, seed=seed)
 
 
+def workload_config(desc: str, n_seqs: int, n_cols: int, n_kept: int) -> dict:
+    """`config` of the JSON line — the same dictionary in our arm and in the reference arm."""
+    return {"workload": desc, "n_seqs": n_seqs, "n_cols": n_cols, "n_kept": int(n_kept),
+            "site_pairs": int(n_kept) * (int(n_kept) - 1) // 2, "r2_threshold": R2_THRESHOLD, "filter": list(FILTER),
+            "l2": "inputs (0.5-3 GB of text, GBs of operands) far larger than the 126 MB L2: no flush needed between steps"}
+
+
 def peaks() -> dict:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -186,7 +193,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "weighted LD site-pairs/sec", "value": value, "unit": "site-pairs/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "n_seqs": n, "n_cols": l, "n_kept": info["n_kept"], "r2_threshold": R2_THRESHOLD},
+            "config": workload_config(desc, n, l, info["n_kept"]),
+            "parallelism": f"{info['cores']} host threads, one 256x256-site reference tile per task",
             "cpu_baseline": {"value": value, "unit": "site-pairs/s", "cores": info["cores"], "kind": info["kind"],
                              "sample": info["sample"]},
             "e2e": {"value": value, "unit": "site-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -413,9 +421,8 @@ def run_ours(args):
                       1: "f64 (SIMT verification kernel)",
                       2: "u8 limbs x s32 accumulate (exact integers), f64 epilogue"}[info.kernel],
             "data": "synthetic",
-            "config": {"workload": desc, "n_seqs": n_seqs, "n_cols": n_cols, "n_kept": n_kept, "site_pairs": total_pairs,
-                       "survivors": surv_all, "r2_threshold": R2_THRESHOLD, "filter": list(FILTER),
-                       "parallelism": f"triangle-partition x{world}", "l2": "inputs larger than L2 (no flush needed)"},
+            "config": workload_config(desc, n_seqs, n_cols, n_kept),   # identical in both arms
+            "survivors": surv_all, "parallelism": f"triangle-partition x{world}",
             "stages_ms": {k: v / args.steps for k, v in stages.items()},
             "roofline": roof,
             "screen": {"used": bool(info.screen), "candidates": int(info.screen_candidates), "top_min": int(info.screen_top_min),

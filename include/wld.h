@@ -168,7 +168,10 @@ WLD_API int wld_set_pair_capacity(wld_ctx* ctx, uint64_t pairs);
  *   mode 0: never; 1 (default): when it pays — the candidate rate is measured on a sample of the tiles first,
  *   and high-LD inputs (more than 1 pair in 256 a candidate) go straight to the exact kernel; 2: whenever the
  *   bound is valid (tests).  The screen needs the u8 kernel, the Rust dialect, a positive threshold, at least
- *   two limbs and top_min >= 32; otherwise the exact kernel runs.  wld_pair_info.screen tells which ran. */
+ *   two limbs and top_min >= 32; otherwise the exact kernel runs.  wld_pair_info.screen tells which ran.
+ *   Should the screen of mode 1 turn up far more candidates than its sample promised (above 1 pair in 128: a
+ *   heterogeneous input), the refinement declines and the exact kernel runs over the same pairs after all
+ *   (then screen = 0 with screen_candidates > 0). */
 WLD_API int wld_set_screen(wld_ctx* ctx, int mode);
 
 /* ---- stage 1: encode + histogram + filter -------------------------------------------------- */
