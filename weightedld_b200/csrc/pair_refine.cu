@@ -84,21 +84,19 @@ __global__ void __launch_bounds__(32 * kRefineWarps) pair_refine_kernel(
         for (int s = 8 * threadIdx.x; s < len; s += 8 * 32 * kRefineWarps)
           *reinterpret_cast<uint4*>(&s_v[l][s]) = __ldg(reinterpret_cast<const uint4*>(glimb + (int64_t)l * ldc + c0 + s));
       __syncthreads();
-      // all code words of the chunk, of every candidate of the warp, first (64 loads in flight per warp), then the arithmetic
-      uint32_t z[kPerWarp][kSteps];
-#pragma unroll
-      for (int c = 0; c < kPerWarp; ++c)
-#pragma unroll
-        for (int u = 0; u < kSteps; ++u) {
-          const int s = 128 * u + 4 * lane;
-          const bool in = live[c] && 128 * u < len;  // warp-uniform: len is a multiple of 128
-          const uint32_t wa = in ? __ldg(reinterpret_cast<const uint32_t*>(ra[c] + c0 + s)) : 0x05050505u;
-          const uint32_t wb = in ? __ldg(reinterpret_cast<const uint32_t*>(rb[c] + c0 + s)) : 0x05050505u;
-          z[c][u] = wa * 8u + wb;  // bytes stay below 0x40: no carries
-        }
 #pragma unroll
       for (int c = 0; c < kPerWarp; ++c) {
         if (!live[c]) continue;  // warp-uniform
+        // all code words of the chunk first (32 loads in flight per warp), then the arithmetic
+        uint32_t z[kSteps];
+#pragma unroll
+        for (int u = 0; u < kSteps; ++u) {
+          const int s = 128 * u + 4 * lane;
+          const bool in = 128 * u < len;  // warp-uniform: len is a multiple of 128
+          const uint32_t wa = in ? __ldg(reinterpret_cast<const uint32_t*>(ra[c] + c0 + s)) : 0x05050505u;
+          const uint32_t wb = in ? __ldg(reinterpret_cast<const uint32_t*>(rb[c] + c0 + s)) : 0x05050505u;
+          z[u] = wa * 8u + wb;  // bytes stay below 0x40: no carries
+        }
         uint32_t acc[4][NL];
 #pragma unroll
         for (int t = 0; t < 4; ++t)
@@ -110,7 +108,7 @@ __global__ void __launch_bounds__(32 * kRefineWarps) pair_refine_kernel(
           const int s = 128 * u + 4 * lane;
           uint32_t m[4];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) m[t] = match80(z[c][u], key[c][t]);
+          for (int t = 0; t < 4; ++t) m[t] = match80(z[u], key[c][t]);
 #pragma unroll
           for (int l = 0; l < NL; ++l) {
             const uint2 v = *reinterpret_cast<const uint2*>(&s_v[l][s]);  // sequences s, s+1 | s+2, s+3
