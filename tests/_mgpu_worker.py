@@ -24,6 +24,11 @@ def main():
     loader = ShardedLoader(chars.shape[0], chars.shape[1], rank, world, torch.device("cuda", local))
     full = loader.load(host)                       # own rows over PCIe + all-gather over NVLink
     assert torch.equal(full.cpu(), torch.from_numpy(chars))
+    # the same in three pieces (H2D of piece c+1 overlaps the all-gather of piece c; the last piece is short), twice
+    piped = ShardedLoader(chars.shape[0], chars.shape[1], rank, world, torch.device("cuda", local), chunks=3)
+    assert piped.chunks == 3
+    for _ in range(2):
+        assert torch.equal(piped.load(host).cpu(), torch.from_numpy(chars))
     with wld.Context(local) as ctx:
         ctx.set_stream(torch.cuda.current_stream().cuda_stream)
         ctx.set_partition(rank, world)

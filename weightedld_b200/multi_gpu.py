@@ -23,9 +23,14 @@ def shard_rows(n_seqs: int, rank: int, world: int) -> tuple[int, int, int]:
 
 
 class ShardedLoader:
-    """Reusable buffers for the sharded host->device copy + all-gather of one alignment shape."""
+    """Reusable buffers for the sharded host->device copy + all-gather of one alignment shape.
 
-    def __init__(self, n_seqs: int, n_cols: int, rank: int, world: int, device, group=None):
+    The rank's rows travel in `chunks` pieces: while NCCL all-gathers piece c over NVLink, piece c+1 is already
+    on the PCIe link (a second stream), so the distribution costs about max(H2D, all-gather) instead of their
+    sum.  A piece of every rank lands in a small staging buffer and is copied to its rows of the full matrix
+    (the matrix keeps the callers' sequence order)."""
+
+    def __init__(self, n_seqs: int, n_cols: int, rank: int, world: int, device, group=None, chunks: int | None = None):
         import torch
 
         self.n_seqs, self.n_cols, self.rank, self.world, self.group = n_seqs, n_cols, rank, world, group
@@ -33,6 +38,17 @@ class ShardedLoader:
         self.pitch = -(-max(n_cols, 1) // 16) * 16  # 16-byte pitch: vectorised histogram path
         self.full = torch.empty((self.per * world, self.pitch), dtype=torch.uint8, device=device)
         self.h2d_bytes = (self.hi - self.lo) * n_cols
+        if chunks is None:  # pieces of >= 8 MB per rank, at most 4
+            chunks = max(1, min(4, (self.per * self.pitch) // (8 << 20)))
+        if world == 1 or torch.device(device).type != "cuda":
+            chunks = 1
+        self.chunks = chunks
+        self.cs = -(-self.per // chunks)  # rows per piece
+        if world > 1 and chunks > 1:
+            self.copy_stream = torch.cuda.Stream(device=device)
+            self.mine = torch.empty((self.per, self.pitch), dtype=torch.uint8, device=device)
+            self.piece = torch.empty((world, self.cs, self.pitch), dtype=torch.uint8, device=device)
+            self.events = [torch.cuda.Event() for _ in range(chunks)]
 
     def load(self, host_rows):
         """host_rows: (n_seqs, n_cols) uint8 torch tensor in (ideally pinned) host memory, identical on
@@ -41,11 +57,37 @@ class ShardedLoader:
         import torch.distributed as dist
 
         src = host_rows if host_rows.shape[0] == self.hi - self.lo else host_rows[self.lo:self.hi]
-        mine = self.full[self.rank * self.per: self.rank * self.per + (self.hi - self.lo), : self.n_cols]
-        mine.copy_(src, non_blocking=True)
-        if self.world > 1:
-            dist.all_gather_into_tensor(self.full, self.full[self.rank * self.per: (self.rank + 1) * self.per],
-                                        group=self.group)
+        n_own = self.hi - self.lo
+        if self.world == 1 or self.chunks == 1:
+            mine = self.full[self.rank * self.per: self.rank * self.per + n_own, : self.n_cols]
+            mine.copy_(src, non_blocking=True)
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.full, self.full[self.rank * self.per: (self.rank + 1) * self.per],
+                                            group=self.group)
+            return self.full[: self.n_seqs, : self.n_cols]
+        cur = torch.cuda.current_stream()
+        self.copy_stream.wait_stream(cur)  # earlier readers of the buffers are done
+        with torch.cuda.stream(self.copy_stream):
+            for c in range(self.chunks):
+                a = c * self.cs
+                rows = max(0, min(self.cs, n_own - a))
+                if rows:
+                    self.mine[a:a + rows, : self.n_cols].copy_(src[a:a + rows], non_blocking=True)
+                self.events[c].record(self.copy_stream)
+        full3 = self.full.view(self.world, self.per, self.pitch)
+        for c in range(self.chunks):
+            a, b = c * self.cs, min((c + 1) * self.cs, self.per)
+            if b <= a:
+                break
+            cur.wait_event(self.events[c])
+            piece = self.piece[:, : b - a]
+            if b - a == self.cs:
+                dist.all_gather_into_tensor(piece, self.mine[a:b], group=self.group)
+                full3[:, a:b].copy_(piece)
+            else:  # short last piece: gather into a contiguous scratch of its own size
+                scratch = self.piece.view(-1)[: self.world * (b - a) * self.pitch].view(self.world, b - a, self.pitch)
+                dist.all_gather_into_tensor(scratch, self.mine[a:b], group=self.group)
+                full3[:, a:b].copy_(scratch)
         return self.full[: self.n_seqs, : self.n_cols]
 
 
