@@ -155,17 +155,18 @@ def merge_on_device(ctx, n_survivors: int, rank: int, world: int, out: np.ndarra
     dist.all_gather_into_tensor(counts, mine, group=group)
     counts = counts.tolist()
     item = PAIR_DTYPE.itemsize
-    shard = ctx.fetch_pairs_device(n_survivors) if rank != 0 else None
-    if rank == 0:
-        bufs = [torch.empty(max(c, 1) * item, dtype=torch.uint8, device=dev) for c in counts]
-        reqs = [dist.irecv(bufs[r][: counts[r] * item], src=r, group=group) for r in range(1, world) if counts[r]]
-        for q in reqs:
-            q.wait()
-        torch.cuda.current_stream().synchronize()
-        for r in range(1, world):
-            if counts[r]:
-                ctx.append_pairs(bufs[r][: counts[r] * item])
-        return ctx.fetch_pairs(sum(counts), FETCH_PARENT_INDEX, out=buffer(sum(counts)))
-    if n_survivors:
-        dist.send(shard, dst=0, group=group)
-    return None
+    widest = max(counts[1:])
+    if widest == 0:
+        return ctx.fetch_pairs(counts[0], FETCH_PARENT_INDEX, out=buffer(counts[0])) if rank == 0 else None
+    # ONE gather to rank 0: every shard padded to the widest one (rank 0 contributes an empty slot)
+    send = torch.empty(widest * item, dtype=torch.uint8, device=dev)
+    if rank != 0 and n_survivors:
+        send[: n_survivors * item].copy_(ctx.fetch_pairs_device(n_survivors))
+    slots = [torch.empty(widest * item, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+    dist.gather(send, slots, dst=0, group=group)
+    if rank != 0:
+        return None
+    foreign = torch.cat([slots[r][: counts[r] * item] for r in range(1, world) if counts[r]])
+    torch.cuda.current_stream().synchronize()
+    ctx.append_pairs(foreign)  # one device-to-device append, then one ordering pass over the union
+    return ctx.fetch_pairs(sum(counts), FETCH_PARENT_INDEX, out=buffer(sum(counts)))
