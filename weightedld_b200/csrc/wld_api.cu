@@ -654,6 +654,11 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
       if (attempt == 3) return c->fail(WLD_ERR_NOMEM, "survivor buffer kept overflowing");
     }
     c->info.screen = use_screen ? 1 : 0;
+    if (std::getenv("WLD_DEBUG"))
+      std::fprintf(stderr, "[libwld] pair stage of device %d: %s; sample %lld candidates in %lld pairs, screen %lld candidates in %llu pairs, top_min %d, %d limbs\n",
+                   c->device, use_screen ? "one-limb screen + exact refinement" : (c->info.screen_candidates ? "screen gave up -> exact kernel" : "exact kernel"),
+                   (long long)c->info.sample_candidates, (long long)c->info.sample_pairs, (long long)c->info.screen_candidates,
+                   (unsigned long long)c->pairs_computed, c->quant_top_min, c->geom.n_limbs);
     c->info.kernel = c->pair_kernel;
     c->info.die_schedule = c->die_used;
     c->info.n_limbs = c->geom.n_limbs;
