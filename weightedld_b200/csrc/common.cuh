@@ -166,7 +166,7 @@ struct wld_ctx {
   wld::DevBuf sorted, sort_keys, sort_idx, sort_temp;  // output ordering scratch (pair_order.cu)
   int sorted_key = -1;             // what `sorted` currently holds: bit0 ordered, bit1 parent indices; -1 nothing
   // pinned staging for large copies to / from pageable host memory (wld_api.cu, staged_copy)
-  static constexpr int kMaxStagers = 8;
+  static constexpr int kMaxStagers = 16;
   void* stage_buf[kMaxStagers] = {};
   cudaStream_t stage_stream[kMaxStagers] = {};
   int n_stagers = 0;

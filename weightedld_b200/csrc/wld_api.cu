@@ -25,7 +25,7 @@ bool host_is_pinned(const void* p);
 int ensure_stagers(wld_ctx* c);
 int staged_copy(wld_ctx* c, void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t row_bytes,
                 size_t rows, cudaMemcpyKind dir, const uint8_t* const* src_rows = nullptr);
-constexpr size_t kStageChunk = 8u << 20;
+constexpr size_t kStageChunk = 4u << 20;  // pinning memory costs ~0.6 ms per MB on this driver: 16 chunks = 64 MB at most
 constexpr size_t kStagedMin = 16u << 20;  // below this a plain copy is as fast
 
 }  // namespace
@@ -75,10 +75,9 @@ void wld_destroy(wld_ctx* c) {
                     &c->cand, &c->plans[0].tiles, &c->plans[1].tiles};
   for (DevBuf* b : bufs) b->release();
   if (c->quant_host) cudaFreeHost(c->quant_host);
-  for (int i = 0; i < wld_ctx::kMaxStagers; ++i) {
-    if (c->stage_buf[i]) cudaFreeHost(c->stage_buf[i]);
+  if (c->stage_buf[0]) cudaFreeHost(c->stage_buf[0]);  // one allocation, sliced (ensure_stagers)
+  for (int i = 0; i < wld_ctx::kMaxStagers; ++i)
     if (c->stage_stream[i]) cudaStreamDestroy(c->stage_stream[i]);
-  }
   for (auto& t : c->timers) {
     if (t.beg) cudaEventDestroy(t.beg);
     if (t.end) cudaEventDestroy(t.end);
@@ -744,18 +743,30 @@ bool host_is_pinned(const void* p) {
 int ensure_stagers(wld_ctx* c) {
   if (c->n_stagers) return WLD_OK;
   const unsigned hw = std::thread::hardware_concurrency();
-  const int want = (int)std::min<unsigned>(wld_ctx::kMaxStagers, std::max(2u, hw / 4));
+  // half of the host threads (a memcpy into the pinned chunk runs at ~8 GB/s per thread; PCIe 5 x16 takes ~55 GB/s)
+  int want = (int)std::min<unsigned>(wld_ctx::kMaxStagers, std::max(2u, hw / 2));
+  // ONE pinned allocation for all chunks (each cudaMallocHost call costs milliseconds whatever its size)
+  void* base = nullptr;
+  while (want >= 1 && cudaMallocHost(&base, kStageChunk * (size_t)want) != cudaSuccess) {
+    cudaGetLastError();
+    base = nullptr;
+    want /= 2;
+  }
+  if (!base) return c->fail(WLD_ERR_NOMEM, "cannot allocate pinned staging buffers");
   for (int i = 0; i < want; ++i) {
-    if (cudaMallocHost(&c->stage_buf[i], kStageChunk) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->stage_stream[i], cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&c->stage_stream[i], cudaStreamNonBlocking) != cudaSuccess) {
       cudaGetLastError();
-      if (c->stage_buf[i]) cudaFreeHost(c->stage_buf[i]);
-      c->stage_buf[i] = nullptr;
       break;
     }
+    c->stage_buf[i] = static_cast<uint8_t*>(base) + kStageChunk * (size_t)i;
     ++c->n_stagers;
   }
-  return c->n_stagers >= 1 ? WLD_OK : c->fail(WLD_ERR_NOMEM, "cannot allocate pinned staging buffers");
+  if (c->n_stagers < 1) {
+    cudaFreeHost(base);
+    c->stage_buf[0] = nullptr;
+    return c->fail(WLD_ERR_NOMEM, "cannot create staging streams");
+  }
+  return WLD_OK;
 }
 
 // dir: cudaMemcpyDeviceToHost or cudaMemcpyHostToDevice.  Row form: `rows` rows of `row_bytes`, pitches in bytes
