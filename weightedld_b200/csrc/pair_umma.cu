@@ -5,9 +5,9 @@
 // Reference: all_weighted_ld_pairs lib.rs:578-684 (tile fan-out, b>a, r2 > thr) and
 // single_weighted_ld_pair lib.rs:390-521 (the four weighted sums + statistics).
 //
-// Math.  opA rows (2i+alpha) are the 0/1 indicators of site i's major (alpha=0) / minor (alpha=1)
-// symbol, opB rows (site j, beta, limb l) are indicator_beta(j) * limb_l(weight); see
-// pair_prep.cu.  One output tile of a CTA pair (cta_group::2; kCtas = 1 halves M) is
+// Math.  opA rows (2i+alpha) are the indicators of site i's major (alpha=0) / minor (alpha=1) symbol, times the
+// sequence's gain 2^(G-e) (block-exponent weights); opB rows (site j, beta, limb l) are indicator_beta(j) *
+// limb_l(weight mantissa); see pair_prep.cu.  One output tile of a CTA pair (cta_group::2; kCtas = 1 halves M) is
 //     D[256 x 256] = opA[mi*256 .. +256, :] * opB[nj*256 .. +256, :]^T        (K = sequences)
 // i.e. 128 sites i  x  2*SPG sites j.  D[(i,alpha)][(j,beta,l)] is an exact integer (s32 for u8
 // operands, fp32 below 2^24 for bf16 operands); the epilogue recombines limbs
@@ -31,8 +31,15 @@
 //   Tile order: strips of 8 N tiles; each L2 die's CTA pairs walk their own contiguous part of the
 //   list (die_map.cu) so the limb strip a die's L2 holds is reused only by that die's SMs.
 //
-// Roofline: tensor pipe.  Algorithmic op per site pair per launch = 8*N*NL (4 weighted dot
-// products of length N per limb); executed = 2*256*256*Kp per tile.
+//
+// Two roles (template parameter kScreen):
+//   exact   NL limbs; the epilogue above; survivors out.
+//   screen  ONE limb (opB1 = indicator x TOP limb, 128 x 128-site tiles): the epilogue bounds r2 from above
+//           (ld_screen_f32, pair_epilogue.cuh) and compacts the site pairs it cannot rule out as candidates for
+//           pair_refine.cu; a sampling launch of it (tile stride, K-block stride) only counts them.
+//
+// Roofline: tensor pipe.  Algorithmic op per site pair per launch = 8*N per limb pass (4 weighted dot
+// products of length N): NL passes in the exact role, one in the screen; executed = 2*256*256*Kp per tile.
 #include <climits>
 #include <cmath>
 #include <cstdlib>
