@@ -367,6 +367,17 @@ def run_ours(args):
     assert done_all == total_pairs, (done_all, total_pairs)
 
     info = ctx.pair_info()
+    # every rank's own figures (rank 0 prints them): the step is as long as the slowest partition
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([stages["pair"] / args.steps, sum(stages.values()) / args.steps, float(info.tiles),
+                             float(info.screen_candidates), float(state["n_surv"])], device="cuda", dtype=torch.float64)
+        allr = torch.zeros(world * mine.numel(), device="cuda", dtype=torch.float64)
+        dist.all_gather_into_tensor(allr, mine)
+        allr = allr.view(world, -1).cpu().numpy()
+        per_rank = {"pair_ms": [round(float(x), 4) for x in allr[:, 0]], "stages_sum_ms": [round(float(x), 4) for x in allr[:, 1]],
+                    "tiles": [int(x) for x in allr[:, 2]], "candidates": [int(x) for x in allr[:, 3]],
+                    "survivors": [int(x) for x in allr[:, 4]]}
     pk = peaks()
     pair_ms = stages["pair"] / args.steps
     # The dominant kernel: the exact n-limb Gram, or — screen + refine — the ONE-limb Gram that every pair goes through
@@ -444,6 +455,7 @@ def run_ours(args):
                     "input_distribution": "host buffer -> one GPU" if world == 1 else
                     f"rows sharded over {world} PCIe links + NCCL all-gather over NVLink"},
             "mgpu_identical": mgpu_identical,
+            "per_rank": per_rank,
             "gpu_launches": launches["n"],
             "clocks": clocks.summary(),
         }
