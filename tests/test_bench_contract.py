@@ -40,3 +40,7 @@ def test_our_arm_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     assert d["config"]["workload"].startswith("synthetic") and "model" not in d["config"]
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert {"used", "candidates", "sample_pairs", "sample_candidates"} <= set(d["screen"])
+    # both arms name the workload with the same dictionary (the driver compares them)
+    ref = run_bench("--impl", "reference", "--workload", "tiny", "--steps", "1", "--warmup", "1")
+    assert ref["config"] == d["config"] and "l2" in d["config"]
