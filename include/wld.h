@@ -172,6 +172,7 @@ WLD_API int wld_set_pair_capacity(wld_ctx* ctx, uint64_t pairs);
  *   Should the screen of mode 1 turn up far more candidates than its sample promised (above 1 pair in 128: a
  *   heterogeneous input), the refinement declines and the exact kernel runs over the same pairs after all
  *   (then screen = 0 with screen_candidates > 0). */
+/* (The environment variable WLD_SCREEN=0|1|2 sets the initial mode of every context: A/B runs of whole programs.) */
 WLD_API int wld_set_screen(wld_ctx* ctx, int mode);
 
 /* ---- stage 1: encode + histogram + filter -------------------------------------------------- */

@@ -75,3 +75,25 @@ def test_cli_synthetic_matches_library(tmp_path, oracle):
     store = wld.all_weighted_ld_pairs(fs, wld.henikoff_weights(fs), 0.1)
     wld.write_pair_stats(tmp_path / "lib.tsv", store)
     assert (tmp_path / "p.tsv").read_text() == (tmp_path / "lib.tsv").read_text() and len(store) > 100
+
+
+def test_cli_screen_and_exact_kernel_write_the_same_files(tmp_path):
+    """A site count large enough for the automatic screen + refine path: the TSV must be the same,
+    byte for byte, as with the exact n-limb kernel (WLD_SCREEN=0), on one GPU and split over two partitions."""
+    import os
+    from weightedld_b200.synth import make_alignment
+    chars = make_alignment(600, 6500, seed=17, block=150, newline_col=True)
+    with open(tmp_path / "s.fasta", "wb") as fh:
+        for i, row in enumerate(chars):
+            fh.write(f">seq{i}\n".encode() + row.tobytes())
+    outs = {}
+    for name, env in (("auto", {}), ("exact", {"WLD_SCREEN": "0"}), ("always", {"WLD_SCREEN": "2"})):
+        r = subprocess.run([str(BIN), "--fasta-input", str(tmp_path / "s.fasta"), "--pair-output", str(tmp_path / f"{name}.tsv"),
+                            "--weights-output", str(tmp_path / f"{name}.w.tsv")],
+                           capture_output=True, text=True, env=dict(os.environ, WLD_DEBUG="1", RUST_LOG="debug", **env))
+        assert r.returncode == 0, r.stderr
+        outs[name] = ((tmp_path / f"{name}.tsv").read_bytes(), (tmp_path / f"{name}.w.tsv").read_bytes(), r.stderr)
+    assert "one-limb screen + exact refinement" in outs["auto"][2] and "one-limb screen" in outs["always"][2]
+    assert "exact kernel" in outs["exact"][2] and "one-limb screen +" not in outs["exact"][2]
+    assert outs["auto"][0] == outs["exact"][0] == outs["always"][0] and len(outs["auto"][0]) > 5000
+    assert outs["auto"][1] == outs["exact"][1]

@@ -55,6 +55,8 @@ int wld_create(int device, wld_ctx** out) {
     return c->fail(WLD_ERR_CUDA, "device %d is sm_%d%d; libwld is built for sm_100a (B200) only", device, prop.major,
                    prop.minor);
   c->sm_count = prop.multiProcessorCount;
+  if (const char* e = std::getenv("WLD_SCREEN"))  // A/B of whole programs (the CLI): same meaning as wld_set_screen
+    if (e[0] >= '0' && e[0] <= '2' && e[1] == 0) c->screen_opt = e[0] - '0';
   WLD_CUDA(c, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
   return WLD_OK;
