@@ -511,3 +511,22 @@ def test_two_contexts_in_two_threads_are_independent(wld):
     for t in threads:
         t.join()
     assert not errs and got == want
+
+
+def test_host_ordering_fallback_matches_device_ordering(wld, monkeypatch):
+    """When the device has no room for the ordering scratch, wld_fetch_pairs orders the survivors on the host
+    (same order: reference tile, then a, then b; parent indices).  WLD_FORCE_HOST_ORDER=1 takes that path."""
+    chars = synth(500, 2600, seed=77, block=80)
+    with wld.Context(0) as ctx:
+        ctx.load_alignment(chars)
+        ctx.filter_sites()
+        ctx.henikoff()
+        n, _ = ctx.ld_pairs(0.05)
+        dev = ctx.fetch_pairs(n).copy()
+        dev_kept = ctx.fetch_pairs(n, wld.FETCH_KEPT_INDEX).copy()
+        monkeypatch.setenv("WLD_FORCE_HOST_ORDER", "1")
+        host = ctx.fetch_pairs(n).copy()
+        host_kept = ctx.fetch_pairs(n, wld.FETCH_KEPT_INDEX).copy()
+        with pytest.raises(wld.WldError):          # a range of the ordered result needs the device scratch
+            ctx.fetch_pairs_range(1, 10)
+    assert n > 2000 and dev.tobytes() == host.tobytes() and dev_kept.tobytes() == host_kept.tobytes()

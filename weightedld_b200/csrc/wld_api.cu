@@ -862,6 +862,11 @@ int order_for_fetch(wld_ctx* c, int flags, const wld_pair** dev, bool* host_fall
     return WLD_OK;
   }
   const int key = (ordered ? 1 : 0) | (parent ? 2 : 0);
+  if (const char* e = std::getenv("WLD_FORCE_HOST_ORDER"))  // tests: take the no-device-memory path below
+    if (e[0] == '1') {
+      *host_fallback = true;
+      return WLD_OK;
+    }
   if (c->sorted_key != key) {
     c->sorted_key = -1;
     const int rc = run_pair_order(c, ordered, parent);
