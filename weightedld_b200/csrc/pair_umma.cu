@@ -43,6 +43,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "pair_epilogue.cuh"
@@ -56,9 +57,12 @@ constexpr int kBlockKBytes = 128;  // one 128-byte swizzle atom along K: 64 bf16
 constexpr int kUmmaKBytes = 32;    // one MMA consumes 32 bytes of K: 16 bf16 (kind::f16) or 32 u8 (kind::i8)
 constexpr int kAStageBytes = kBlockM * kBlockKBytes;  // 16 KB per CTA
 // Per-epilogue-warp candidate queue (see CandidateQueue): 64 entries of {4 x int64 sums, site_i, site_j}.
-constexpr int kQueueCap = 64;
+#ifndef WLD_EPI_WARPS
+#define WLD_EPI_WARPS 8  // 8 or 16 (A/B builds: make EXTRA=-DWLD_EPI_WARPS=16)
+#endif
+constexpr int kQueueCap = WLD_EPI_WARPS == 16 ? 48 : 64;  // 16 warps: the queues must still fit beside the 6-stage ring
 constexpr int kQueueBytesPerWarp = kQueueCap * (4 * 8 + 2 * 4);  // 2560 B
-constexpr int kNumEpiWarpsC = 8;
+constexpr int kNumEpiWarpsC = WLD_EPI_WARPS;
 // kCtas = 1: one CTA computes a 128 x 256 tile and stages all 256 B rows (32 KB) -> 4 stages of 48 KB.
 // kCtas = 2: a CTA pair (cta_group::2) computes 256 x 256; each CTA stages its 128 A rows and HALF of
 //            the B rows (16 KB) -> 6 stages of 32 KB; one third less L2->SMEM traffic per MMA.
@@ -70,9 +74,9 @@ template <int kCtas> struct StageCfg {
   static constexpr int kQueueOffset = kStages * kBytes + 256;  // after the stage ring and the barriers
   static constexpr int kSmemBytes = 1024 /*alignment slack*/ + kQueueOffset + kNumEpiWarpsC * kQueueBytesPerWarp;
 };
-constexpr int kNumThreads = 384;
+constexpr int kNumThreads = 128 + 32 * kNumEpiWarpsC;
 constexpr int kEpiWarp0 = 4;
-constexpr int kNumEpiWarps = 8;
+constexpr int kNumEpiWarps = kNumEpiWarpsC;
 constexpr int kTmemCols = 512;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> CTA 0
 
@@ -81,6 +85,7 @@ struct UmmaParams {
   int n_tiles;          // tiles this launch walks: tile k of the launch is tiles[k * tile_mul]
   int tile_mul;         // 1, or the stride of a sampling launch
   int k_mul;            // 1, or the stride over K blocks of a sampling launch (an unbiased subsample of the sequences)
+  int debug_skip;       // experiments only (WLD_EXPERIMENT_SKIP_EPILOGUE=1): the epilogue releases the accumulator untouched
   int k_blocks;
   int n_kept;
   int limb_bits;
@@ -498,7 +503,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
       const int my_die = wave_sync ? sched[3] : 0;
       bool sync_ok = true;
       unsigned wave = 0;
+      // the descriptor of the NEXT tile is fetched while this one streams (a dependent global load at every tile
+      // start would stall the ring for ~1 us: 12 % of a tile at K = 2 000 sequences)
+      uint4 tile = first_tile < tile_end ? p.tiles[(size_t)first_tile * (size_t)p.tile_mul] : make_uint4(0, 0, 0, 0);
       for (int t = first_tile; t < tile_end; t += tile_step, ++wave) {
+        const uint4 tile_next = t + tile_step < tile_end ? p.tiles[(size_t)(t + tile_step) * (size_t)p.tile_mul] : tile;
         if (wave_sync && sync_ok) {
           // tiles of all earlier waves of this die have had their loads issued (bounded: if a pair of the die is
           // missing, synchronisation is abandoned rather than the GPU hung)
@@ -509,7 +518,6 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
             __nanosleep(32);
           }
         }
-        const uint4 tile = p.tiles[(size_t)t * (size_t)p.tile_mul];
         const int m_row = (int)tile.x * (kBlockM * kCtas) + (int)cta_rank * kBlockM;
         const int n_row = (int)tile.y * kBlockN + (int)cta_rank * Cfg::kBRows;
         // (Tiles that share a panel run in lockstep through K: one fetches a line, the others hit in L2.  Starting
@@ -528,6 +536,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         if (wave_sync) atomicAdd(&p.wave_counter[my_die], 1u);
+        tile = tile_next;
       }
     }
     __syncwarp();
@@ -582,8 +591,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
     queue.init(smem + Cfg::kQueueOffset + (warp - kEpiWarp0) * kQueueBytesPerWarp);
     unsigned long long done = 0;
     uint32_t tcount = 0;
+    uint4 tile_cur = first_tile < tile_end ? p.tiles[(size_t)first_tile * (size_t)p.tile_mul] : make_uint4(0, 0, 0, 0);
     for (int t = first_tile; t < tile_end; t += tile_step, ++tcount) {
-      const uint4 tile = p.tiles[(size_t)t * (size_t)p.tile_mul];
+      const uint4 tile = tile_cur;
+      if (t + tile_step < tile_end) tile_cur = p.tiles[(size_t)(t + tile_step) * (size_t)p.tile_mul];  // needed one tile later
       const uint32_t buf = tcount & 1u, bphase = (tcount >> 1) & 1u;
       const int i_min = ((int)tile.x * kCtas + (int)cta_rank) * (kBlockM / 2) + quarter * 16;
       const int site_i = i_min + (lane >> 1);
@@ -593,7 +604,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * kBlockN + half * 128;
       // whole tile below the diagonal band, or outside the tile's window, for this warp?  -> nothing to do
       const int j_hi = min(site_j0 + min(2 * jp_end, SPG), (int)tile.w), j_lo = max(site_j0 + 2 * jp_begin, (int)tile.z);
-      const bool any_work = i_min < j_hi && j_lo < j_hi;
+      const bool any_work = i_min < j_hi && j_lo < j_hi && p.debug_skip == 0;
       if constexpr (kScreen) {
         // ---- one-limb screen: RPS = 2, SPG = 64; four sites j (8 columns) per step.  x = exact s32 sums of
         // gain x TOP limb; the true sums lie in [x, x (1 + 1/top_min)] (pair_prep.cu), so
@@ -602,27 +613,48 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
         // as (AB, Ab | aB, ab) whichever of the two it holds.
         static_assert(!kScreen || (NL == 1 && kI8), "the screen is the one-limb u8 kernel");
         if (any_work) {
-#pragma unroll 1
-          for (int js = 0; js < SPG / 4; ++js) {
+          // warp-uniform fast path: the warp's 16 sites i all precede its 64 sites j and the window covers them
+          const bool all_valid = i_min + 15 < site_j0 && site_j0 >= (int)tile.z && site_j0 + SPG <= (int)tile.w;
+          uint32_t n_valid = 0;
+          auto sweep = [&](auto all_valid_c) {
+            constexpr bool kAllValid = decltype(all_valid_c)::value;
             uint32_t v[8];
-            tmem_ld8(taddr + js * 8, v);
-            tmem_ld_wait();
-            float f[8];
+            tmem_ld8(taddr + part * (SPG / 4 / kParts) * 8, v);
+            constexpr int kSweep = SPG / 4 / kParts;  // steps of this warp: [js0, js0 + kSweep)
+            const int js0 = part * kSweep;
+#pragma unroll 1
+            for (int js = js0; js < js0 + kSweep; ++js) {
+              tmem_ld_wait();
+              float f[8];
 #pragma unroll
-            for (int x = 0; x < 8; ++x) f[x] = (float)(int)v[x];
+              for (int x = 0; x < 8; ++x) f[x] = (float)(int)v[x];
+              if (js + 1 < js0 + kSweep) tmem_ld8(taddr + (js + 1) * 8, v);  // the next four sites travel while these are tested
+              bool cand[2];
+              int site_j[2];
 #pragma unroll
-            for (int pp = 0; pp < 2; ++pp) {
-              // lane alpha finishes site 4js + 2pp + alpha and sends its row's sums of the other site of the pair
-              const float own0 = alpha ? f[4 * pp + 2] : f[4 * pp + 0], own1 = alpha ? f[4 * pp + 3] : f[4 * pp + 1];
-              const float snd0 = alpha ? f[4 * pp + 0] : f[4 * pp + 2], snd1 = alpha ? f[4 * pp + 1] : f[4 * pp + 3];
-              const float rcv0 = __shfl_xor_sync(0xffffffffu, snd0, 1), rcv1 = __shfl_xor_sync(0xffffffffu, snd1, 1);
-              const int site_j = site_j0 + 4 * js + 2 * pp + alpha;
-              const bool valid = site_i < site_j && site_j >= (int)tile.z && site_j < (int)tile.w;  // lib.rs:651
-              done += valid;
-              const bool cand = valid && ld_screen_f32(own0, own1, rcv0, rcv1, kappa, p.thr_lo_f);
-              emit_cand_warp(cand, (uint32_t)site_i, (uint32_t)site_j, p.cand);
+              for (int pp = 0; pp < 2; ++pp) {
+                // lane alpha finishes site 4js + 2pp + alpha and sends its row's sums of the other site of the pair
+                const float own0 = alpha ? f[4 * pp + 2] : f[4 * pp + 0], own1 = alpha ? f[4 * pp + 3] : f[4 * pp + 1];
+                const float snd0 = alpha ? f[4 * pp + 0] : f[4 * pp + 2], snd1 = alpha ? f[4 * pp + 1] : f[4 * pp + 3];
+                const float rcv0 = __shfl_xor_sync(0xffffffffu, snd0, 1), rcv1 = __shfl_xor_sync(0xffffffffu, snd1, 1);
+                site_j[pp] = site_j0 + 4 * js + 2 * pp + alpha;
+                cand[pp] = ld_screen_f32(own0, own1, rcv0, rcv1, kappa, p.thr_lo_f);
+                if constexpr (!kAllValid) {
+                  const bool valid = site_i < site_j[pp] && site_j[pp] >= (int)tile.z && site_j[pp] < (int)tile.w;  // lib.rs:651
+                  n_valid += valid;
+                  cand[pp] = cand[pp] && valid;
+                }
+              }
+              if (__any_sync(0xffffffffu, cand[0] || cand[1])) {  // rare
+                emit_cand_warp(cand[0], (uint32_t)site_i, (uint32_t)site_j[0], p.cand);
+                emit_cand_warp(cand[1], (uint32_t)site_i, (uint32_t)site_j[1], p.cand);
+              }
             }
-          }
+            if constexpr (kAllValid) n_valid = SPG / 2 / kParts;  // every lane finished 2 pairs per step
+          };
+          if (all_valid) sweep(std::true_type{});
+          else sweep(std::false_type{});
+          done += n_valid;
         }
       } else if (any_work) {
 #pragma unroll 1
@@ -939,6 +971,10 @@ int run_pair_umma(wld_ctx* c, float thr, int mode) {
   prm.tile_mul = tile_mul;
   prm.k_blocks = (int)(gm.k_padded * gm.elem_bytes / kBlockKBytes);
   prm.k_mul = 1;
+  {
+    const char* e = std::getenv("WLD_EXPERIMENT_SKIP_EPILOGUE");  // timing experiments: results are NOT computed
+    prm.debug_skip = (e && e[0] == '1') ? 1 : 0;
+  }
   if (mode == 2 && prm.k_blocks > 64) {
     // The sample only has to tell "a few candidates in 10^5 pairs" from "a few in 10": every k_mul-th block of 128
     // sequences (about 6 000 of them, spread over the whole alignment) estimates that as well as all of them.
