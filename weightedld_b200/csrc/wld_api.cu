@@ -556,12 +556,15 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
     }
     cap = std::max<uint64_t>(cap, 1024);
     // the capacity is what the buffer holds, never a cached number (a failed growth leaves an empty buffer)
-    c->pair_cap = c->pairs.p ? c->pairs.bytes / sizeof(wld_pair) : 0;
-    if (c->pair_cap < cap) {
-      c->pair_cap = 0;
-      WLD_CUDA(c, c->pairs.ensure(sizeof(wld_pair) * (size_t)cap));
-      c->pair_cap = c->pairs.bytes / sizeof(wld_pair);
-    }
+    auto ensure_pair_cap = [&](uint64_t want) -> int {
+      c->pair_cap = c->pairs.p ? c->pairs.bytes / sizeof(wld_pair) : 0;
+      if (c->pair_cap < want) {
+        c->pair_cap = 0;
+        WLD_CUDA(c, c->pairs.ensure(sizeof(wld_pair) * (size_t)want));
+        c->pair_cap = c->pairs.bytes / sizeof(wld_pair);
+      }
+      return WLD_OK;
+    };
     if (use_screen) {
       // candidates: four times the rate the screen is chosen at (1 in 64), between 2^16 and 2^26 (512 MB); grows like the survivors
       const uint64_t want = std::min<uint64_t>(std::max<uint64_t>(1ull << 16, c->plan_pairs / 64 + 1024), 1ull << 26);
@@ -571,6 +574,13 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
         WLD_CUDA(c, c->cand.ensure(sizeof(uint2) * (size_t)want));
         c->cand_cap = c->cand.bytes / sizeof(uint2);
       }
+      // every survivor is a candidate first: no need for a survivor buffer larger than the candidate buffer (a one-shot
+      // run, the CLI, would otherwise pay for allocating gigabytes it cannot fill)
+      int rc = ensure_pair_cap(c->pair_cap_opt ? cap : std::min<uint64_t>(cap, c->cand_cap));
+      if (rc != WLD_OK) return rc;
+    } else {
+      int rc = ensure_pair_cap(cap);
+      if (rc != WLD_OK) return rc;
     }
     if (c->compat == WLD_COMPAT_PYTHON) {
       int rc = run_pair_python_prepare(c);
@@ -629,6 +639,7 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
           ScopedStageTimer tm(c, WLD_STAGE_PAIR_PREP);
           int rc = run_expand_limbs(c, tm, false);
           if (rc == WLD_OK) rc = ensure_tile_plan(c, 0);
+          if (rc == WLD_OK) rc = ensure_pair_cap(cap);  // the exact kernel's default capacity after all
           if (rc != WLD_OK) return rc;
           --attempt;
           continue;
@@ -639,6 +650,10 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
           c->cand_cap = 0;
           WLD_CUDA(c, c->cand.ensure(sizeof(uint2) * (size_t)want));
           c->cand_cap = c->cand.bytes / sizeof(uint2);
+          if (!c->pair_cap_opt) {
+            const int rc = ensure_pair_cap(std::min<uint64_t>(cap, c->cand_cap));
+            if (rc != WLD_OK) return rc;
+          }
           ++c->info.screen_reruns;
           if (attempt == 3) return c->fail(WLD_ERR_NOMEM, "candidate buffer kept overflowing");
           continue;
