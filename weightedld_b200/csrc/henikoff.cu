@@ -81,11 +81,12 @@ __global__ void __launch_bounds__(kAccThreads) accumulate_kernel(const uint8_t* 
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   const uint8_t* p = codes + k0 * ldc + s0;
   auto add_pair = [&](int pr, uint32_t wa, uint32_t wb) {
+    // the four table indices 6 * code_a + code_b at once: codes are 0..5 (gather_kernel writes nothing else, the
+    // padding is 5), so no byte of 6 * wa + wb exceeds 35 and nothing carries
+    const uint32_t z = wa * 6u + wb;
+    const double* row = s_tab2[pr];
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const uint32_t ca = min((wa >> (8 * b)) & 0xffu, 5u), cb = min((wb >> (8 * b)) & 0xffu, 5u);
-      acc[b] = __dadd_rn(acc[b], s_tab2[pr][ca * 6u + cb]);
-    }
+    for (int b = 0; b < 4; ++b) acc[b] = __dadd_rn(acc[b], row[(z >> (8 * b)) & 0xffu]);
   };
   int pr = 0;
   for (; 2 * pr + 8 <= nk; pr += 4) {  // four pairs = eight site rows in flight (the loop is latency-bound)
