@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <future>
 #include <ios>
 #include <mutex>
 #include <thread>
@@ -594,15 +595,85 @@ std::string format_py4(double v) {
 }
 
 namespace {
-// Formats `n` records with `fmt_line` on all host threads and writes the pieces IN ORDER at `*file_pos`:
-// every thread formats a contiguous run into its own buffer, the run lengths give each buffer its file
-// offset, and the threads pwrite() their buffers concurrently (page-cache copies scale with threads).
+// Formats `n` records with `fmt_line` on all host threads and writes the pieces IN ORDER behind the writer's file
+// position: every thread formats a contiguous run into its own buffer and the run lengths give each buffer its file
+// offset.  The bytes then go into the file from all threads at once — through a shared mapping of the file's new
+// range (concurrent write() calls on one file serialise on its inode lock; page faults on a mapping do not), or with
+// pwrite() where the output cannot be mapped (a pipe, a device) — in the BACKGROUND, while the caller fetches and
+// formats the next chunk.
 struct WriteTiming { double format_s = 0, write_s = 0; };
 WriteTiming g_write_timing;
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
+struct OrderedWriter {
+  int fd;
+  off_t pos = 0;               // end of what has been handed to the writer so far
+  bool can_map = true;         // cleared on the first failure to extend / map the file
+  std::future<int> pending;    // errno of the write in flight (0 = fine)
+
+  explicit OrderedWriter(int f) : fd(f) {}
+  void wait() {
+    if (pending.valid()) {
+      const int e = pending.get();
+      if (e) throw std::ios_base::failure(std::string(std::strerror(e)) + " (os error " + std::to_string(e) + ")");
+    }
+  }
+  // takes ownership of the formatted pieces; returns at once
+  void submit(std::vector<std::string>&& pieces) {
+    wait();  // one write in flight: keeps the order of failures simple and the memory bounded
+    std::vector<off_t> at(pieces.size());
+    const off_t begin = pos;
+    for (size_t t = 0; t < pieces.size(); ++t) {
+      at[t] = pos;
+      pos += (off_t)pieces[t].size();
+    }
+    const off_t end = pos;
+    pending = std::async(std::launch::async, [this, begin, end, at = std::move(at), pieces = std::move(pieces)]() -> int {
+      const double t0 = now_s();
+      auto each = [&](auto&& f) {
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < pieces.size(); ++t) th.emplace_back([&, t] { f(t); });
+        f(0);
+        for (auto& x : th) x.join();
+      };
+      int err = 0;
+      bool done = false;
+      if (can_map && end > begin) {
+        const long page = sysconf(_SC_PAGESIZE);
+        const off_t map_lo = begin / page * page;
+        if (::ftruncate(fd, end) == 0) {
+          void* m = ::mmap(nullptr, (size_t)(end - map_lo), PROT_READ | PROT_WRITE, MAP_SHARED, fd, map_lo);
+          if (m != MAP_FAILED) {
+            char* base = static_cast<char*>(m) - map_lo;  // base[file offset]
+            each([&](size_t t) { std::memcpy(base + at[t], pieces[t].data(), pieces[t].size()); });
+            ::munmap(m, (size_t)(end - map_lo));
+            done = true;
+          }
+        }
+        if (!done) can_map = false;
+      }
+      if (!done) {
+        std::vector<int> errs(pieces.size(), 0);
+        each([&](size_t t) {
+          const char* p = pieces[t].data();
+          size_t left = pieces[t].size();
+          off_t o = at[t];
+          while (left) {
+            const ssize_t w = ::pwrite(fd, p, left, o);
+            if (w < 0) { if (errno == EINTR) continue; errs[t] = errno; return; }
+            p += w; left -= (size_t)w; o += w;
+          }
+        });
+        for (int e : errs) if (e && !err) err = e;
+      }
+      g_write_timing.write_s += now_s() - t0;
+      return err;
+    });
+  }
+};
+
 template <class LineFn>
-void write_records_parallel(int fd, off_t* file_pos, const wld_pair* recs, size_t n, LineFn&& fmt_line) {
+void write_records_parallel(OrderedWriter& w, const wld_pair* recs, size_t n, LineFn&& fmt_line) {
   if (n == 0) return;
   const double t_begin = now_s();
   const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
@@ -619,36 +690,15 @@ void write_records_parallel(int fd, off_t* file_pos, const wld_pair* recs, size_
     }
     s.resize(used);
   };
-  auto run = [&](auto&& f) {
-    if (nthr == 1) { f(0); return; }
+  if (nthr == 1) {
+    format(0);
+  } else {
     std::vector<std::thread> th;
-    for (size_t t = 0; t < nthr; ++t) th.emplace_back([&, t] { f(t); });
+    for (size_t t = 0; t < nthr; ++t) th.emplace_back([&, t] { format(t); });
     for (auto& x : th) x.join();
-  };
-  run(format);
-  const double t_fmt = now_s();
-  std::vector<off_t> at(nthr);
-  off_t pos = *file_pos;
-  for (size_t t = 0; t < nthr; ++t) {
-    at[t] = pos;
-    pos += (off_t)out[t].size();
   }
-  std::vector<int> errs(nthr, 0);
-  run([&](size_t t) {
-    const char* p = out[t].data();
-    size_t left = out[t].size();
-    off_t o = at[t];
-    while (left) {
-      const ssize_t w = ::pwrite(fd, p, left, o);
-      if (w < 0) { if (errno == EINTR) continue; errs[t] = errno; return; }
-      p += w; left -= (size_t)w; o += w;
-    }
-  });
-  for (int e : errs)
-    if (e) throw std::ios_base::failure(std::string(std::strerror(e)) + " (os error " + std::to_string(e) + ")");
-  *file_pos = pos;
-  g_write_timing.format_s += t_fmt - t_begin;
-  g_write_timing.write_s += now_s() - t_fmt;
+  g_write_timing.format_s += now_s() - t_begin;
+  w.submit(std::move(out));
 }
 
 int open_out(const std::string& path) {
@@ -683,18 +733,19 @@ void write_pair_stats_python(const std::string& path, const PairStore& store, co
     return;
   }
   const int fd = open_out(path);
-  off_t pos = 0;
-  write_header(fd, &pos, "posa\tposb\tD\tD'\tR2\n");
+  OrderedWriter w(fd);
+  write_header(fd, &w.pos, "posa\tposb\tD\tD'\tR2\n");
   try {
-    write_records_parallel(fd, &pos, sorted.data(), sorted.size(), line);
+    write_records_parallel(w, sorted.data(), sorted.size(), line);
+    w.wait();
   } catch (...) { ::close(fd); throw; }
   ::close(fd);
 }
 
 void write_pair_stats(const std::string& path, const PairStore& store, const std::vector<int64_t>& labels) {
   const int fd = open_out(path);
-  off_t pos = 0;
-  write_header(fd, &pos, "site_a\tsite_b\td\td'\tr2\n");
+  OrderedWriter w(fd);
+  write_header(fd, &w.pos, "site_a\tsite_b\td\td'\tr2\n");
   auto line = [&](const wld_pair& p, char* buf) {
     int k = 0;
     if (labels.empty()) {
@@ -718,12 +769,13 @@ void write_pair_stats(const std::string& path, const PairStore& store, const std
   try {
     // streamed: the next chunk is fetched from the device while this one is formatted and written
     store.for_each_chunk((size_t)4 << 20, [&](const wld_pair* recs, size_t, size_t count) {
-      write_records_parallel(fd, &pos, recs, count, line);
+      write_records_parallel(w, recs, count, line);
     });
+    w.wait();
   } catch (...) { ::close(fd); throw; }
   ::close(fd);
   if (std::getenv("WLD_CLI_TIMING"))
-    std::fprintf(stderr, "[weighted_ld] pair writer: %.1f ms total, %.1f ms formatting, %.1f ms pwrite, rest = waiting for the device copy; %u host threads\n",
+    std::fprintf(stderr, "[weighted_ld] pair writer: %.1f ms total, %.1f ms formatting, %.1f ms writing (in the background, mapped file), rest = waiting for the device copy; %u host threads\n",
                  (now_s() - t0) * 1e3, g_write_timing.format_s * 1e3, g_write_timing.write_s * 1e3, std::thread::hardware_concurrency());
 }
 
