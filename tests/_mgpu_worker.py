@@ -29,6 +29,11 @@ def main():
     assert piped.chunks == 3
     for _ in range(2):
         assert torch.equal(piped.load(host).cpu(), torch.from_numpy(chars))
+    # pageable host memory goes through the loader's pinned staging buffer (forced here: the input is small)
+    big = np.tile(chars, (8, 2))                      # 5 600 x 10 000 = 56 MB
+    pl = ShardedLoader(big.shape[0], big.shape[1], rank, world, torch.device("cuda", local))
+    for _ in range(2):
+        assert torch.equal(pl.load(torch.from_numpy(big)).cpu(), torch.from_numpy(big))
     with wld.Context(local) as ctx:
         ctx.set_stream(torch.cuda.current_stream().cuda_stream)
         ctx.set_partition(rank, world)

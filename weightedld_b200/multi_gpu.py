@@ -50,6 +50,28 @@ class ShardedLoader:
             self.piece = torch.empty((world, self.cs, self.pitch), dtype=torch.uint8, device=device)
             self.events = [torch.cuda.Event() for _ in range(chunks)]
 
+    def _pinned_stage(self):
+        """(pinned (per, n_cols) uint8 tensor, fill(src_np, first_row, rows)) — allocated on first use."""
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+
+        import torch
+
+        if getattr(self, "_stage", None) is None:
+            self._stage = torch.empty((self.per, self.n_cols), dtype=torch.uint8).pin_memory()
+            self._stage_np = self._stage.numpy()
+            self._pool = ThreadPoolExecutor(max_workers=max(2, min(8, (os.cpu_count() or 4) // 2)))
+
+        def fill(src_np, a, rows):
+            import numpy as np
+
+            n = self._pool._max_workers
+            cuts = [a + rows * k // n for k in range(n + 1)]
+            # np.copyto releases the GIL: the slices are copied in parallel
+            list(self._pool.map(lambda k: np.copyto(self._stage_np[cuts[k]:cuts[k + 1]], src_np[cuts[k]:cuts[k + 1]]), range(n)))
+
+        return self._stage, fill
+
     def load(self, host_rows):
         """host_rows: (n_seqs, n_cols) uint8 torch tensor in (ideally pinned) host memory, identical on
         every rank — or just this rank's rows [lo, hi).  Returns the full (n_seqs, n_cols) device view."""
@@ -58,7 +80,18 @@ class ShardedLoader:
 
         src = host_rows if host_rows.shape[0] == self.hi - self.lo else host_rows[self.lo:self.hi]
         n_own = self.hi - self.lo
+        stage_rows = (lambda a, rows: None)
+        if self.full.is_cuda and not src.is_pinned() and n_own * self.n_cols >= (16 << 20):
+            # pageable host memory (what a Rust Vec<u8> caller holds): the rows pass through a pinned buffer, filled by
+            # a few host threads piece by piece, so that the copy engine sees pinned memory and piece c+1 is being
+            # staged while piece c is on the bus
+            pinned, fill = self._pinned_stage()
+            torch.cuda.synchronize(self.full.device)  # copies of the previous load out of the pinned buffer are done
+            src_np = src.numpy()
+            stage_rows = lambda a, rows: fill(src_np, a, rows)
+            src = pinned
         if self.world == 1 or self.chunks == 1:
+            stage_rows(0, n_own)
             mine = self.full[self.rank * self.per: self.rank * self.per + n_own, : self.n_cols]
             mine.copy_(src, non_blocking=True)
             if self.world > 1:
@@ -72,6 +105,7 @@ class ShardedLoader:
                 a = c * self.cs
                 rows = max(0, min(self.cs, n_own - a))
                 if rows:
+                    stage_rows(a, rows)
                     self.mine[a:a + rows, : self.n_cols].copy_(src[a:a + rows], non_blocking=True)
                 self.events[c].record(self.copy_stream)
         full3 = self.full.view(self.world, self.per, self.pitch)
