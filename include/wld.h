@@ -165,13 +165,16 @@ WLD_API int wld_set_pair_capacity(wld_ctx* ctx, uint64_t pairs);
  * was summed), and recompute only the pairs that bound does not rule out — exactly, from the code matrix and the
  * full integer weights, through the same f64 statistics of lib.rs:482-518.  The survivors are the same records,
  * bit for bit, as the exact n-limb kernel's (all_weighted_ld_pairs, lib.rs:578-684).
- *   mode 0: never; 1 (default): when it pays — the candidate rate is measured on a sample of the tiles first,
- *   and high-LD inputs (more than 1 pair in 256 a candidate) go straight to the exact kernel; 2: whenever the
- *   bound is valid (tests).  The screen needs the u8 kernel, the Rust dialect, a positive threshold, at least
+ *   mode 0: never; 1 (default): when it pays — the candidate rate is measured on a sample of the tiles first:
+ *   up to 1 candidate in 256 pairs -> screen + per-pair refinement; more, but in at most 40 % of the sampled tiles
+ *   (LD confined to a band or to blocks) -> screen, then the exact kernel over the 128 x 128-site cells it flags;
+ *   else (high LD everywhere) straight to the exact kernel; 2: screen + per-pair refinement whenever the bound is
+ *   valid (tests).  The screen needs the u8 kernel, the Rust dialect, a positive threshold, at least
  *   two limbs and top_min >= 32; otherwise the exact kernel runs.  wld_pair_info.screen tells which ran.
  *   Should the screen of mode 1 turn up far more candidates than its sample promised (above 1 pair in 128: a
- *   heterogeneous input), the refinement declines and the exact kernel runs over the same pairs after all
- *   (then screen = 0 with screen_candidates > 0). */
+ *   heterogeneous input), the refinement declines and the exact kernel takes over: on the 128 x 128-site cells in
+ *   which the screen found a candidate when those are a minority (wld_pair_info.screen = 2: LD confined to a band or
+ *   to blocks), else on all pairs (screen = 0 with screen_candidates > 0). */
 /* (The environment variable WLD_SCREEN=0|1|2 sets the initial mode of every context: A/B runs of whole programs.) */
 WLD_API int wld_set_screen(wld_ctx* ctx, int mode);
 
@@ -320,7 +323,8 @@ typedef struct wld_pair_info {
   int32_t gain_bits;       /* G, see wld_set_gain_bits */
   int32_t weight_span_log2;/* x: the smallest nonzero weight lies in [2^-(x+1), 2^-x) of the largest */
   int32_t screen;          /* 0: every pair went through the exact n-limb kernel; 1: one-limb screen + exact
-                              refinement of its candidates (same survivors, bit for bit; see wld_set_screen) */
+                              refinement of its candidates; 2: one-limb screen + the exact kernel over the 128 x 128-site
+                              cells in which it found candidates (same survivors, bit for bit; see wld_set_screen) */
   double weight_rel_err;   /* realised max over nonzero weights of |q/scale - w/max| / (w/max).  A priori:
                               <= 2^-B when x <= G, else <= 2^(x-G-B).  Every weighted sum of lib.rs:469-479
                               (all terms >= 0) carries at most this relative error before the f64 epilogue. */
@@ -330,6 +334,10 @@ typedef struct wld_pair_info {
   int64_t sample_candidates;   /* ... and how many of them were candidates */
   int32_t screen_top_min;      /* smallest top limb of a nonzero weight: the screen's bound is x <= y <= x (1 + 1/top_min) */
   int32_t screen_reruns;       /* times the screen was repeated because the candidate buffer was too small */
+  int64_t screen_cells;        /* screen = 2 (or a screen that gave up): cells (screen tiles) of this partition ... */
+  int64_t screen_cells_flagged;/* ... and how many of them held a candidate */
+  int64_t sample_tiles;        /* tiles of the sampling launch ... */
+  int64_t sample_tiles_flagged;/* ... and how many of them held a candidate */
 } wld_pair_info;
 WLD_API int wld_get_pair_info(wld_ctx* ctx, wld_pair_info* out);
 

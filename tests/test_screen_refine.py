@@ -172,11 +172,12 @@ def test_automatic_choice_low_and_high_ld():
     lo = synth(1000, 6000, seed=11)                                  # ~0.02 % of the pairs pass
     a, b = run(lo, "never"), run(lo, "auto")
     assert b["info"].screen == 1 and b["info"].sample_pairs > 100_000
-    assert b["info"].sample_candidates * 256 <= b["info"].sample_pairs
+    assert b["info"].sample_candidates * 512 <= b["info"].sample_pairs
     assert a["pairs"].tobytes() == b["pairs"].tobytes() and len(a["pairs"]) > 100
     hi = synth(1000, 6000, seed=12, founders=64, block=400, clonal=True, stray=0.02, private_rate=0.002)
     a, b = run(hi, "never"), run(hi, "auto")
     assert b["info"].screen == 0 and b["info"].sample_candidates * 256 > b["info"].sample_pairs
+    assert b["info"].sample_tiles_flagged * 2 > b["info"].sample_tiles      # candidates everywhere: no point in screening
     assert len(a["pairs"]) > 0.05 * a["done"] and a["pairs"].tobytes() == b["pairs"].tobytes()
     # a small problem (fewer than four waves of cells) is not worth a sample: exact kernel
     small = synth(500, 1500, seed=13)
@@ -223,4 +224,32 @@ def test_refinement_gives_up_when_the_sample_was_blind(monkeypatch):
     import weightedld_b200 as wld
     kept = wld.FETCH_KEPT_INDEX | wld.FETCH_UNORDERED
     shards = [run(hi, "auto", partition=(p, 2), flags=kept)["pairs"] for p in range(2)]
+    assert wld.merge_shards(a["n_kept"], shards, a["site_map"]).tobytes() == a["pairs"].tobytes()
+
+
+@pytest.mark.gpu
+def test_block_ld_goes_through_the_screen_and_the_exact_kernel_on_flagged_cells():
+    """LD confined to blocks along the diagonal: too many candidates to recompute pair by pair, but in a minority of the
+    128 x 128-site cells.  The automatic mode screens everything with one limb and runs the exact kernel on the flagged
+    cells only (wld_pair_info.screen == 2) — same bytes as the exact kernel over every pair."""
+    import weightedld_b200 as wld
+    chars = synth(1000, 6500, seed=51, founders=6, block=300)
+    a = run(chars, "never")
+    b = run(chars, "auto")
+    bi = b["info"]
+    assert bi.sample_candidates * 512 > bi.sample_pairs and bi.sample_tiles_flagged * 5 <= bi.sample_tiles * 2
+    assert bi.screen == 2 and 0 < bi.screen_cells_flagged * 2 <= bi.screen_cells
+    assert a["done"] == b["done"] == a["n_kept"] * (a["n_kept"] - 1) // 2
+    assert len(a["pairs"]) > 0.005 * a["done"] and a["pairs"].tobytes() == b["pairs"].tobytes()
+    # fewer tiles than the exact kernel over everything
+    assert bi.tiles < 0.5 * a["info"].tiles
+    # partitions: each decides on its own (two halves are still long enough schedules for a sample)
+    kept = wld.FETCH_KEPT_INDEX | wld.FETCH_UNORDERED
+    shards, done, modes = [], 0, []
+    for p in range(2):
+        r = run(chars, "auto", partition=(p, 2), flags=kept)
+        shards.append(r["pairs"])
+        done += r["done"]
+        modes.append(r["info"].screen)
+    assert done == a["done"] and modes == [2, 2]
     assert wld.merge_shards(a["n_kept"], shards, a["site_map"]).tobytes() == a["pairs"].tobytes()

@@ -40,6 +40,8 @@ class PairInfo(C.Structure):
         ("weight_span_log2", C.c_int32), ("screen", C.c_int32), ("weight_rel_err", C.c_double),
         ("screen_candidates", C.c_int64), ("sample_pairs", C.c_int64), ("sample_candidates", C.c_int64),
         ("screen_top_min", C.c_int32), ("screen_reruns", C.c_int32),
+        ("screen_cells", C.c_int64), ("screen_cells_flagged", C.c_int64),
+        ("sample_tiles", C.c_int64), ("sample_tiles_flagged", C.c_int64),
     ]
 
 

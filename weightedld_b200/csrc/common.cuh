@@ -48,6 +48,8 @@ struct StageTimer {
   cudaEvent_t beg = nullptr, end = nullptr;
   bool valid = false;
   int launches = 0;
+  float carry_ms = 0.f;   // time of earlier launches of the same stage in this call (a screen before the cell pass)
+  int carry_launches = 0;
 };
 
 // Pair-stage operand geometry (see DESIGN.md "data layout in HBM").
@@ -84,6 +86,7 @@ struct DevPlan {
   uint64_t pairs = 0;
   int64_t x[2] = {0, -1}, y[2] = {0, -1};  // min / max M-tile and N-tile index
   int64_t tile_m = 0, tile_n = 0;
+  std::vector<uint4> host;                 // the same list on the host (the cell plan is cut out of it)
 };
 
 }  // namespace wld
@@ -146,13 +149,17 @@ struct wld_ctx {
   wld::DevBuf gain8;               // u8 [ldc]       per-sequence gain 2^(G-e) carried by the indicator operand
   wld::DevBuf quant;               // QuantDecision (device)
   wld::QuantDecision* quant_host = nullptr;  // pinned mirror
-  unsigned long long* sample_host = nullptr; // pinned: {candidates, pairs} of the sampling launch (behind quant_host)
+  unsigned long long* sample_host = nullptr; // pinned: {candidates, pairs, flagged tiles} of the sampling launch (behind quant_host)
   int quant_span_log2 = 0;
   double quant_rel_err = 0.0;
   wld::DevBuf opA;                 // bf16 [a_rows][k_padded]
   wld::DevBuf opB;                 // bf16 [b_groups*128][k_padded]
   wld::DevBuf simt_tiles;          // uint2 [n_tiles] of the CUDA-core verification kernel
-  wld::DevPlan plans[2];           // tcgen05 schedules: [0] the exact kernel (n_limbs limbs), [1] the one-limb screen
+  wld::DevPlan plans[3];           // tcgen05 schedules: [0] the exact kernel (n_limbs limbs), [1] the one-limb screen,
+                                   // [2] the exact kernel over the cells the screen flagged (rebuilt per run)
+  wld::DevBuf cell_flags;          // u8 [screen tiles]: 1 = the screen found a candidate in this tile
+  wld::DevBuf sample_flags;        // u32 [sampled tiles]: the same for the sampling launch
+  int64_t sample_tiles = 0;        // tiles of the last sampling launch
   // screen + refine (pair_umma.cu kScreen, pair_refine.cu)
   int screen_opt = 1;              // wld_set_screen: 0 never, 1 automatic (sampled candidate rate), 2 always when valid
   wld::DevBuf glimb;               // u16 [4][ldc]   gain x limb per sequence and limb (pair_refine.cu)
@@ -237,10 +244,12 @@ int run_expand_limbs(wld_ctx* c, ScopedStageTimer& tm, bool screen);       // pa
 // The pair launchers bracket ONLY the kernel launch with the WLD_STAGE_PAIR timer (host-side
 // planning and the tile-list upload happen before the start event).
 int run_pair_simt(wld_ctx* c, float thr);                                  // pair_simt.cu
-// mode 0: exact kernel (all limbs); 1: one-limb screen over every tile, candidates -> c->cand;
-// 2: the screen over a sample of the tiles, counting only (counters[8..9])
+// mode 0: exact kernel (all limbs); 1: one-limb screen over every tile, candidates -> c->cand, flagged tiles ->
+// c->cell_flags; 2: the screen over a sample of the tiles, counting only (counters[8..9]); 3: exact kernel over plans[2]
 int run_pair_umma(wld_ctx* c, float thr, int mode);                        // pair_umma.cu
 int ensure_tile_plan(wld_ctx* c, int which);                               // pair_umma.cu (which: 0 exact, 1 screen)
+// plans[2] := the exact kernel's tiles (windows clipped) of the screen tiles whose flag is set; *n_flagged = their number
+int build_cell_plan(wld_ctx* c, const std::vector<uint8_t>& flags, int64_t* n_flagged);  // pair_umma.cu
 int run_pair_refine(wld_ctx* c, float thr, unsigned long long give_up);    // pair_refine.cu: exact statistics of the candidates (none if more than give_up)
 int run_pair_order(wld_ctx* c, bool ordered, bool parent);                 // pair_order.cu
 const std::vector<uint8_t>& die_map(wld_ctx* c);                            // die_map.cu: SM -> L2 die (empty = unknown)

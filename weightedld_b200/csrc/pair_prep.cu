@@ -415,7 +415,7 @@ int finish_quant(wld_ctx* c) {
   PairGeom& gm = c->geom;
   WLD_CUDA(c, cudaMemcpyAsync(c->quant_host, c->quant.p, sizeof(QuantDecision), cudaMemcpyDeviceToHost, c->stream));
   // (the sampling launch's two counters ride along: counters[8] candidates, counters[9] pairs)
-  WLD_CUDA(c, cudaMemcpyAsync(c->sample_host, c->counters.as<unsigned long long>() + 8, 2 * sizeof(unsigned long long),
+  WLD_CUDA(c, cudaMemcpyAsync(c->sample_host, c->counters.as<unsigned long long>() + 8, 3 * sizeof(unsigned long long),
                               cudaMemcpyDeviceToHost, c->stream));
   WLD_CUDA(c, cudaStreamSynchronize(c->stream));
   const QuantDecision qd = *c->quant_host;
@@ -456,10 +456,10 @@ int run_pair_prep(wld_ctx* c, ScopedStageTimer& tm, bool try_screen) {
   WLD_CUDA(c, c->counters.ensure(sizeof(unsigned long long) * 16));
   WLD_CUDA(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 16, c->stream));
   if (!c->quant_host) {
-    WLD_CUDA(c, cudaMallocHost(&c->quant_host, sizeof(QuantDecision) + 2 * sizeof(unsigned long long)));
+    WLD_CUDA(c, cudaMallocHost(&c->quant_host, sizeof(QuantDecision) + 3 * sizeof(unsigned long long)));
     c->sample_host = reinterpret_cast<unsigned long long*>(c->quant_host + 1);
   }
-  c->sample_host[0] = c->sample_host[1] = 0;
+  c->sample_host[0] = c->sample_host[1] = c->sample_host[2] = 0;
 
   // One launch quantises the weights AND decides limbs / limb width / gain bits; one read-back tells the host.
   quantize_kernel<<<1, 1024, 0, c->stream>>>(c->w32.as<float>(), n, c->ldc, c->n_limbs_opt, c->gain_opt, c->limb_bits_opt, exact_limit,

@@ -112,6 +112,9 @@ struct UmmaParams {
   PairOut out;
   // screen (kScreen): candidates instead of survivors; kappa widens |P - Q| by the truncation of the weights
   CandOut cand;
+  uint8_t* cell_flags;  // screen, full launch: cell_flags[tile] = 1 when the tile holds a candidate (else null)
+  unsigned int* sample_flags;          // sampling launch: one word per sampled tile (first hit counts it) ...
+  unsigned long long* sample_flagged;  // ... into this counter: sampled tiles that hold a candidate
   const float* kappa;   // device: QuantDecision::kappa (the sampling launch runs before the host has read it)
   unsigned long long* pairs_done;
   int* error_flag;
@@ -616,6 +619,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
           // warp-uniform fast path: the warp's 16 sites i all precede its 64 sites j and the window covers them
           const bool all_valid = i_min + 15 < site_j0 && site_j0 >= (int)tile.z && site_j0 + SPG <= (int)tile.w;
           uint32_t n_valid = 0;
+          bool hit = false;  // warp-uniform: this warp found a candidate in this tile
           auto sweep = [&](auto all_valid_c) {
             constexpr bool kAllValid = decltype(all_valid_c)::value;
             uint32_t v[8];
@@ -646,6 +650,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
                 }
               }
               if (__any_sync(0xffffffffu, cand[0] || cand[1])) {  // rare
+                hit = true;
                 emit_cand_warp(cand[0], (uint32_t)site_i, (uint32_t)site_j[0], p.cand);
                 emit_cand_warp(cand[1], (uint32_t)site_i, (uint32_t)site_j[1], p.cand);
               }
@@ -655,6 +660,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) pair_umma_kernel(const __grid_
           if (all_valid) sweep(std::true_type{});
           else sweep(std::false_type{});
           done += n_valid;
+          if (hit && lane == 0) {
+            if (p.cell_flags != nullptr) p.cell_flags[(size_t)t * (size_t)p.tile_mul] = 1;
+            if (p.sample_flags != nullptr && atomicExch(&p.sample_flags[t], 1u) == 0u) atomicAdd(p.sample_flagged, 1ull);
+          }
         }
       } else if (any_work) {
 #pragma unroll 1
@@ -924,7 +933,48 @@ int ensure_tile_plan(wld_ctx* c, int which) {
     dp.y[0] = std::min<int64_t>(dp.y[0], t.y);
     dp.y[1] = std::max<int64_t>(dp.y[1], t.y);
   }
+  dp.host.swap(plan.tiles);
   c->plan_pairs = dp.pairs;
+  return WLD_OK;
+}
+
+// The exact kernel restricted to the cells in which the screen found candidates: every flagged screen tile
+// (a 128-site cell column window of one M tile) is covered by the exact kernel's N tiles with their windows clipped
+// to it.  Cells without a flag hold no pair that can pass the threshold (the screen's bound), so nothing is lost.
+// The list keeps the strip-major order of the screen's list.
+int build_cell_plan(wld_ctx* c, const std::vector<uint8_t>& flags, int64_t* n_flagged) {
+  const DevPlan& sp = c->plans[1];
+  DevPlan& dp = c->plans[2];
+  const int64_t tile_m = (kBlockM / 2) * c->cta_group;
+  const int64_t tile_n = 2 * (128 / (2 * c->geom.n_limbs));
+  std::vector<uint4> tiles;
+  uint64_t pairs = 0;
+  int64_t flagged = 0;
+  for (size_t k = 0; k < sp.host.size() && k < flags.size(); ++k) {
+    if (!flags[k]) continue;
+    ++flagged;
+    const uint4 cell = sp.host[k];  // {M tile, cell column, j_lo, j_hi}
+    const int64_t i0 = (int64_t)cell.x * tile_m, i1 = std::min<int64_t>(c->n_kept, i0 + tile_m);
+    for (int64_t nj = (int64_t)cell.z / tile_n; nj * tile_n < (int64_t)cell.w; ++nj) {
+      const int64_t w_lo = std::max<int64_t>(nj * tile_n, cell.z), w_hi = std::min<int64_t>((nj + 1) * tile_n, cell.w);
+      if (w_lo >= w_hi || i0 >= w_hi - 1) continue;
+      tiles.push_back(make_uint4(cell.x, (unsigned)nj, (unsigned)w_lo, (unsigned)w_hi));
+      if (i1 <= w_lo) pairs += (uint64_t)((i1 - i0) * (w_hi - w_lo));
+      else
+        for (int64_t i = i0; i < i1; ++i) pairs += (uint64_t)std::max<int64_t>(0, w_hi - std::max(w_lo, i + 1));
+    }
+  }
+  *n_flagged = flagged;
+  WLD_CUDA(c, dp.tiles.ensure(sizeof(uint4) * std::max<size_t>(tiles.size(), 1)));
+  if (!tiles.empty())
+    WLD_CUDA(c, cudaMemcpyAsync(dp.tiles.p, tiles.data(), sizeof(uint4) * tiles.size(), cudaMemcpyHostToDevice, c->stream));
+  WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+  dp.key[0] = -1;  // never reused
+  dp.n_tiles = (int64_t)tiles.size();
+  dp.pairs = pairs;
+  dp.tile_m = tile_m;
+  dp.tile_n = tile_n;
+  dp.host.swap(tiles);
   return WLD_OK;
 }
 
@@ -933,12 +983,12 @@ int ensure_tile_plan(wld_ctx* c, int which) {
 int run_pair_umma(wld_ctx* c, float thr, int mode) {
   const PairGeom& gm = c->geom;
   const int ctas = c->cta_group;
-  const bool screen = mode != 0;
-  {
+  const bool screen = mode == 1 || mode == 2;
+  if (mode != 3) {
     const int rc = ensure_tile_plan(c, screen ? 1 : 0);
     if (rc != WLD_OK) return rc;
   }
-  const DevPlan& dp = c->plans[screen ? 1 : 0];
+  const DevPlan& dp = c->plans[mode == 3 ? 2 : screen ? 1 : 0];
   const int n_limbs = screen ? 1 : gm.n_limbs;
   const int spg = 128 / (2 * n_limbs);
   int64_t n_tiles = dp.n_tiles;
@@ -1013,14 +1063,22 @@ int run_pair_umma(wld_ctx* c, float thr, int mode) {
   prm.pairs_done = cnt + 1;
   prm.error_flag = reinterpret_cast<int*>(cnt + 2);
   prm.cand = CandOut{nullptr, cnt + 5, 0};
+  prm.cell_flags = nullptr;
+  prm.sample_flags = nullptr;
+  prm.sample_flagged = cnt + 10;
   prm.kappa = &c->quant.as<QuantDecision>()->kappa;
   if (screen) {
     prm.thr_lo_f = std::min(prm.thr_lo_f, 2.0f);  // (a threshold above 1 can never pass; keeps thr * den finite)
     if (mode == 1) {
+      prm.cell_flags = c->cell_flags.as<uint8_t>();
       prm.cand = CandOut{c->cand.as<uint2>(), cnt + 5, c->cand_cap};
     } else {
       prm.cand = CandOut{nullptr, cnt + 8, 0};
       prm.pairs_done = cnt + 9;
+      WLD_CUDA(c, c->sample_flags.ensure(sizeof(unsigned int) * (size_t)n_tiles));
+      WLD_CUDA(c, cudaMemsetAsync(c->sample_flags.p, 0, sizeof(unsigned int) * (size_t)n_tiles, c->stream));
+      prm.sample_flags = c->sample_flags.as<unsigned int>();
+      c->sample_tiles = n_tiles;
     }
   }
 

@@ -74,7 +74,8 @@ void wld_destroy(wld_ctx* c) {
                     &c->mnr, &c->kept_count, &c->codes, &c->table, &c->partial, &c->w64, &c->w32, &c->scalars,
                     &c->q, &c->limbs, &c->opA, &c->opB, &c->simt_tiles, &c->pairs, &c->counters, &c->py_aux, &c->die_of_sm,
                     &c->sorted, &c->sort_keys, &c->sort_idx, &c->sort_temp, &c->gain8, &c->quant, &c->glimb, &c->opB1,
-                    &c->cand, &c->plans[0].tiles, &c->plans[1].tiles};
+                    &c->cand, &c->plans[0].tiles, &c->plans[1].tiles, &c->plans[2].tiles, &c->cell_flags,
+                    &c->sample_flags};
   for (DevBuf* b : bufs) b->release();
   if (c->quant_host) cudaFreeHost(c->quant_host);
   if (c->stage_buf[0]) cudaFreeHost(c->stage_buf[0]);  // one allocation, sliced (ensure_stagers)
@@ -502,6 +503,8 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
     c->timers[st].valid = false;
     c->timers[st].launches = 0;
   }
+  c->timers[WLD_STAGE_PAIR].carry_ms = 0.f;
+  c->timers[WLD_STAGE_PAIR].carry_launches = 0;
   if (L >= 2 && c->n_seqs > 0) {
     // Screen + refine (wld_set_screen) is considered for the u8 tensor kernel, the Rust dialect and a positive
     // threshold, when the schedule is long enough for a sample to mean something (>= 4 waves of cells).
@@ -515,6 +518,7 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
       if (rc != WLD_OK) return rc;
     }
     bool use_screen = false;
+    bool expect_cells = false;  // the screen first, then the exact kernel on the cells it flags (LD confined to a minority of cells)
     if (try_screen) {
       if (c->screen_opt == 1) {
         int rc = run_pair_umma(c, r2_threshold, 2);  // the screen over ~2 waves of tiles spread over the list: count only
@@ -527,10 +531,28 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
       c->info.sample_pairs = (int64_t)c->sample_host[1];
       // the bound needs every nonzero weight to fill its top limb reasonably (kappa = 2/top_min + ...), and a second limb to drop
       const bool valid = c->geom.n_limbs >= 2 && c->geom.limb_bits == 8 && c->quant_top_min >= 32;
-      // a candidate costs about as much as 60-80 pairs of the exact kernel and the screen saves 2/3 - 3/4 of a pair
+      // Costs in units of the exact kernel over every pair: the screen itself 1/limbs; then EITHER every candidate is
+      // recomputed on its own (pair_refine.cu: ~10 ns at 10 000 sequences against 0.022 ns per pair and limb in the tensor
+      // kernel, i.e. 455/limbs per unit of candidate rate) OR the exact kernel runs on the cells that hold candidates
+      // (their share of the sampled tiles, plus a third for tiles clipped to cell borders, plus fixed costs).  The cheaper is
+      // planned; if neither leaves a margin of 10 %, the exact kernel runs alone.
       // (WLD_SAMPLE_BLIND=1, tests: pretend the sample saw nothing, as it may on a heterogeneous input)
       const char* blind = std::getenv("WLD_SAMPLE_BLIND");
-      use_screen = valid && (c->screen_opt == 2 || (blind && blind[0] == '1') || c->sample_host[0] * 256 <= c->sample_host[1]);
+      const double limbs = (double)std::max(c->geom.n_limbs, 1);
+      const double f_c = c->sample_host[1] ? (double)c->sample_host[0] / (double)c->sample_host[1] : 0.0;
+      const double f_t = c->sample_tiles > 0 ? (double)c->sample_host[2] / (double)c->sample_tiles : 1.0;
+      const double cost_pairs = 455.0 / limbs * f_c;
+      const double cost_cells = 1.3 * f_t + 0.02;  // + the limb operand of the whole partition, a plan, a round trip
+      if (valid && c->screen_opt == 2) {
+        use_screen = true;
+      } else if (valid && blind && blind[0] == '1') {
+        use_screen = true;
+      } else if (valid && 1.0 / limbs + std::min(cost_pairs, cost_cells) < 0.9) {
+        use_screen = true;
+        expect_cells = cost_cells < cost_pairs;
+      }
+      c->info.sample_tiles = c->sample_tiles;
+      c->info.sample_tiles_flagged = (int64_t)c->sample_host[2];
     }
     if (c->pair_kernel != WLD_PAIR_KERNEL_SIMT && !use_screen) {
       ScopedStageTimer tm(c, WLD_STAGE_PAIR_PREP);  // (shows the limb expansion only when the screen was tried first)
@@ -587,15 +609,22 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
       if (rc != WLD_OK) return rc;
     }
     unsigned long long progress_last = 0;
+    bool cells_only = false;            // the exact kernel over the cells the screen flagged (plans[2])
+    uint64_t screened_pairs = 0;        // pairs the screen went through before that
     for (int attempt = 0; attempt < 4; ++attempt) {
       WLD_CUDA(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 8, c->stream));
       c->die_used = 0;
+      if (use_screen) {
+        const size_t n_screen_tiles = (size_t)std::max<int64_t>(c->plans[1].n_tiles, 1);
+        WLD_CUDA(c, c->cell_flags.ensure(n_screen_tiles));
+        WLD_CUDA(c, cudaMemsetAsync(c->cell_flags.p, 0, n_screen_tiles, c->stream));
+      }
       {
         int rc = c->pair_kernel == WLD_PAIR_KERNEL_SIMT ? run_pair_simt(c, r2_threshold)
-                                                        : run_pair_umma(c, r2_threshold, use_screen ? 1 : 0);
+                                                        : run_pair_umma(c, r2_threshold, use_screen ? 1 : cells_only ? 3 : 0);
         // automatic mode: twice the candidate rate the screen is chosen at is the point of no return (pair_refine.cu)
         if (rc == WLD_OK && use_screen)
-          rc = run_pair_refine(c, r2_threshold, c->screen_opt == 2 ? ~0ull : std::max<uint64_t>(c->plan_pairs / 128, 1ull << 16));
+          rc = run_pair_refine(c, r2_threshold, c->screen_opt == 2 ? ~0ull : expect_cells ? 0ull : std::max<uint64_t>(c->plan_pairs / 128, 1ull << 16));
         // pairs whose per-pair allele call may differ from the per-site call (WeightedLD.py:186-211)
         if (rc == WLD_OK && c->compat == WLD_COMPAT_PYTHON) rc = run_pair_python_fixup(c, r2_threshold);
         if (rc != WLD_OK) return rc;
@@ -624,22 +653,48 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
         return c->fail(WLD_ERR_CUDA, "pair kernel failed: %s (pipeline watchdog code %d)", cudaGetErrorString(e),
                        (int)cnt[2]);
       const char* experiment = std::getenv("WLD_EXPERIMENT_SKIP_EPILOGUE");  // timing experiments count no pairs
-      if (c->die_used && ((int)cnt[2] == 7 || (cnt[1] != c->plan_pairs && !(experiment && experiment[0] == '1')))) {
+      const uint64_t expected_pairs = cells_only ? c->plans[2].pairs : c->plan_pairs;
+      if (c->die_used && ((int)cnt[2] == 7 || (cnt[1] != expected_pairs && !(experiment && experiment[0] == '1')))) {
         // the CTA pairs did not land on the dies as planned (GPU shared with other work?): plain schedule
         c->die_aware = 0;
         --attempt;
         continue;
       }
-      c->pairs_computed = cnt[1];
+      c->pairs_computed = cells_only ? screened_pairs : cnt[1];
       if (use_screen) {
         c->info.screen_candidates = (int64_t)cnt[5];
         if (cnt[6]) {
-          // the refinement declined: the exact kernel over this partition's pairs (the same pairs: canonical cells)
+          // The refinement declined (too many candidates to recompute one by one).  The exact kernel takes over — on the
+          // cells in which the screen found a candidate when those are a minority (LD confined to a band or to blocks:
+          // every other cell is ruled out by the screen's bound), else on all of this partition's pairs.
           use_screen = false;
+          std::vector<uint8_t> flags((size_t)c->plans[1].n_tiles);
+          if (!flags.empty())
+            WLD_CUDA(c, cudaMemcpyAsync(flags.data(), c->cell_flags.p, flags.size(), cudaMemcpyDeviceToHost, c->stream));
+          WLD_CUDA(c, cudaStreamSynchronize(c->stream));
+          int64_t n_flagged = 0;
+          for (uint8_t f : flags) n_flagged += f != 0;
+          {  // the screen's time stays part of the pair stage
+            StageTimer& pt = c->timers[WLD_STAGE_PAIR];
+            float ms = 0.f;
+            if (pt.valid && cudaEventElapsedTime(&ms, pt.beg, pt.end) == cudaSuccess) {
+              pt.carry_ms += ms;
+              pt.carry_launches += pt.launches;
+            }
+          }
+          c->info.screen_cells = c->plans[1].n_tiles;
+          c->info.screen_cells_flagged = n_flagged;
           ScopedStageTimer tm(c, WLD_STAGE_PAIR_PREP);
           int rc = run_expand_limbs(c, tm, false);
           if (rc == WLD_OK) rc = ensure_tile_plan(c, 0);
-          if (rc == WLD_OK) rc = ensure_pair_cap(cap);  // the exact kernel's default capacity after all
+          if (rc == WLD_OK && 2 * n_flagged <= c->plans[1].n_tiles) {
+            rc = build_cell_plan(c, flags, &n_flagged);
+            cells_only = rc == WLD_OK;
+            screened_pairs = cnt[1];
+            if (rc == WLD_OK) rc = ensure_pair_cap(std::min<uint64_t>(cap, std::max<uint64_t>(c->plans[2].pairs, 1024)));
+          } else if (rc == WLD_OK) {
+            rc = ensure_pair_cap(cap);  // the exact kernel's default capacity after all
+          }
           if (rc != WLD_OK) return rc;
           --attempt;
           continue;
@@ -670,10 +725,10 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
       c->pair_cap = c->pairs.bytes / sizeof(wld_pair);
       if (attempt == 3) return c->fail(WLD_ERR_NOMEM, "survivor buffer kept overflowing");
     }
-    c->info.screen = use_screen ? 1 : 0;
+    c->info.screen = use_screen ? 1 : cells_only ? 2 : 0;
     if (std::getenv("WLD_DEBUG"))
       std::fprintf(stderr, "[libwld] pair stage of device %d: %s; sample %lld candidates in %lld pairs, screen %lld candidates in %llu pairs, top_min %d, %d limbs\n",
-                   c->device, use_screen ? "one-limb screen + exact refinement" : (c->info.screen_candidates ? "screen gave up -> exact kernel" : "exact kernel"),
+                   c->device, use_screen ? "one-limb screen + exact refinement" : cells_only ? "one-limb screen + exact kernel on the flagged cells" : (c->info.screen_candidates ? "screen gave up -> exact kernel" : "exact kernel"),
                    (long long)c->info.sample_candidates, (long long)c->info.sample_pairs, (long long)c->info.screen_candidates,
                    (unsigned long long)c->pairs_computed, c->quant_top_min, c->geom.n_limbs);
     c->info.kernel = c->pair_kernel;
@@ -1034,13 +1089,14 @@ int wld_stage_ms(wld_ctx* c, int stage, float* ms) {
   if (!t.valid) return WLD_OK;
   WLD_CUDA(c, cudaEventSynchronize(t.end));
   WLD_CUDA(c, cudaEventElapsedTime(ms, t.beg, t.end));
+  *ms += t.carry_ms;
   return WLD_OK;
 }
 
 int wld_stage_launches(wld_ctx* c, int stage, int* launches) {
   WLD_CHECK_CTX(c);
   if (stage < 0 || stage >= WLD_STAGE_COUNT || !launches) return c->fail(WLD_ERR_INVALID, "bad stage id");
-  *launches = c->timers[stage].valid ? c->timers[stage].launches : 0;
+  *launches = c->timers[stage].valid ? c->timers[stage].launches + c->timers[stage].carry_launches : 0;
   return WLD_OK;
 }
 
