@@ -301,6 +301,12 @@ WLD_API uint64_t wld_pair_order_key(int64_t n_kept, uint32_t kept_a, uint32_t ke
 WLD_API int wld_plan_tiles(int64_t n_kept, int n_limbs, int cta_group, int part, int nparts, int sm_count, uint32_t* tiles,
                            uint64_t cap_tiles, uint64_t* n_tiles, uint64_t* n_pairs);
 
+/* The schedule of "screen + exact kernel on the flagged cells" (wld_set_screen), host only: given one flag per tile of
+ * the screen's schedule of this partition (wld_plan_tiles with n_limbs = 1, same order), the exact kernel's tiles of
+ * `n_limbs` limbs that cover the flagged tiles, windows clipped to them.  Same output convention as wld_plan_tiles. */
+WLD_API int wld_plan_cell_tiles(int64_t n_kept, int n_limbs, int cta_group, int part, int nparts, const uint8_t* flags,
+                                uint64_t n_flags, uint32_t* tiles, uint64_t cap_tiles, uint64_t* n_tiles, uint64_t* n_pairs);
+
 /* ---- introspection ------------------------------------------------------------------------- */
 /* Device time of the last run of a stage in milliseconds (CUDA events on the context's stream). */
 WLD_API int wld_stage_ms(wld_ctx* ctx, int stage, float* ms);

@@ -200,3 +200,33 @@ def test_sharded_input_broadcast_and_output_gather_gloo():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+
+
+@pytest.mark.parametrize("ctas", [1, 2])
+@pytest.mark.parametrize("n_limbs,tile_n", [(2, 64), (3, 42), (4, 32)])
+def test_cell_plan_covers_exactly_the_flagged_cells(n_limbs, tile_n, ctas):
+    """Screen + exact kernel on the flagged cells: the exact kernel's tiles cut out for a set of
+    flagged screen tiles must evaluate every pair of those tiles once and no other pair — for whole triangles and for
+    partitions."""
+    import weightedld_b200 as wld
+    n_kept, tile_m = 1500, 64 * ctas
+    rng = np.random.default_rng(n_limbs * 10 + ctas)
+    for nparts in (1, 3):
+        total_flagged_pairs = 0
+        seen_all = np.zeros((n_kept, n_kept), np.int32)
+        want_all = np.zeros((n_kept, n_kept), np.int32)
+        for part in range(nparts):
+            screen, _ = wld.plan_tiles(n_kept, 1, part, nparts, cta_group=ctas)
+            flags = (rng.random(len(screen)) < 0.3).astype(np.uint8)
+            want = pair_cover(screen[flags == 1], n_kept, tile_m, 128)
+            tiles, pairs = wld.plan_cell_tiles(n_kept, flags, n_limbs, part, nparts, cta_group=ctas)
+            got = pair_cover(tiles, n_kept, tile_m, tile_n)
+            assert np.array_equal(got, want) and got.max() <= 1 and got.sum() == pairs
+            seen_all += got
+            want_all += want
+            total_flagged_pairs += pairs
+        assert np.array_equal(seen_all, want_all) and seen_all.max() <= 1 and total_flagged_pairs == want_all.sum()
+    # nothing flagged, everything flagged
+    screen, pairs_all = wld.plan_tiles(n_kept, 1, cta_group=ctas)
+    assert wld.plan_cell_tiles(n_kept, np.zeros(len(screen), np.uint8), n_limbs, cta_group=ctas)[1] == 0
+    assert wld.plan_cell_tiles(n_kept, np.ones(len(screen), np.uint8), n_limbs, cta_group=ctas)[1] == pairs_all == n_kept * (n_kept - 1) // 2

@@ -8,13 +8,13 @@ from ._lib import (FETCH_DEVICE, FETCH_KEPT_INDEX, FETCH_PARENT_INDEX, FETCH_UNO
                    PAIR_KERNEL_UMMA, PAIR_KERNEL_UMMA_I8, STAGE_FILTER, STAGE_HENIKOFF, STAGE_HISTOGRAM, STAGE_LOAD, STAGE_NAMES, STAGE_ORDER,
                    STAGE_PAIR, STAGE_PAIR_PREP, WldError)
 from .api import (Context, MultiSequence, PairStore, SiteSet, all_weighted_ld_pairs, format_f3, henikoff_weights,
-                  merge_shards, pair_order_key, plan_tiles, read_fasta, single_weighted_ld_pair, write_henikoff_weights, write_pair_stats)
+                  merge_shards, pair_order_key, plan_cell_tiles, plan_tiles, read_fasta, single_weighted_ld_pair, write_henikoff_weights, write_pair_stats)
 
 from . import pycompat  # mirror of the reference's Python program (WeightedLD.py), WLD_COMPAT_PYTHON
 
 __all__ = [
     "pycompat",
     "Context", "MultiSequence", "PairStore", "SiteSet", "WldError", "all_weighted_ld_pairs", "format_f3",
-    "henikoff_weights", "merge_shards", "pair_order_key", "plan_tiles", "read_fasta", "single_weighted_ld_pair", "write_henikoff_weights",
+    "henikoff_weights", "merge_shards", "pair_order_key", "plan_cell_tiles", "plan_tiles", "read_fasta", "single_weighted_ld_pair", "write_henikoff_weights",
     "write_pair_stats", "PAIR_DTYPE",
 ]

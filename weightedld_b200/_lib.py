@@ -97,6 +97,7 @@ SIGNATURES = {
     "wld_append_pairs_from": (_int, [_vp, _vp]),
     "wld_pair_order_key": (_u64, [_i64, C.c_uint32, C.c_uint32]),
     "wld_plan_tiles": (_int, [_i64, _int, _int, _int, _int, _int, _vp, _u64, C.POINTER(_u64), C.POINTER(_u64)]),
+    "wld_plan_cell_tiles": (_int, [_i64, _int, _int, _int, _int, _vp, _u64, _vp, _u64, C.POINTER(_u64), C.POINTER(_u64)]),
     "wld_set_cta_group": (_int, [_vp, _int]),
     "wld_set_compat": (_int, [_vp, _int]),
     "wld_filter_sites_python": (_int, [_vp, C.c_double, C.c_double, C.POINTER(_i64)]),

@@ -385,6 +385,23 @@ def plan_tiles(n_kept: int, n_limbs: int = 3, part: int = 0, nparts: int = 1, sm
     return tiles, pairs.value
 
 
+def plan_cell_tiles(n_kept: int, flags, n_limbs: int = 3, part: int = 0, nparts: int = 1, cta_group: int = 2):
+    """Host-only schedule of the exact kernel over the flagged tiles of the screen's schedule (wld_plan_cell_tiles):
+    ((n_tiles, 4) uint32 {M tile, N tile, first site j, end site j}, site pairs covered)."""
+    lib = L.load()
+    flags = np.ascontiguousarray(flags, np.uint8)
+    n, pairs = C.c_uint64(), C.c_uint64()
+    rc = lib.wld_plan_cell_tiles(n_kept, n_limbs, cta_group, part, nparts, _ptr(flags), len(flags), None, 0, C.byref(n), C.byref(pairs))
+    if rc != L.WLD_OK:
+        raise WldError(rc, "bad cell plan arguments")
+    tiles = np.empty((n.value, 4), np.uint32)
+    rc = lib.wld_plan_cell_tiles(n_kept, n_limbs, cta_group, part, nparts, _ptr(flags), len(flags), _ptr(tiles), n.value,
+                                 C.byref(n), C.byref(pairs))
+    if rc != L.WLD_OK:
+        raise WldError(rc, "bad cell plan arguments")
+    return tiles, pairs.value
+
+
 def merge_shards(n_kept: int, shards: list[np.ndarray], site_map: np.ndarray | None = None) -> np.ndarray:
     """Host merge of per-GPU survivor shards (records with KEPT indices) into the reference's
     output order (lib.rs:623-679); maps to raw columns when site_map is given (lib.rs:662-663)."""

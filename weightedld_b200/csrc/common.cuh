@@ -265,5 +265,8 @@ struct TilePlan {
   int64_t tile_m = 64, tile_n = 42;
 };
 TilePlan plan_tiles(int64_t n_kept, int n_limbs, int part, int nparts, int sm_count, int ctas);
+// the exact kernel's tiles (n_limbs limbs) covering the flagged tiles of a screen schedule, windows clipped to them
+TilePlan cut_cell_plan(const std::vector<uint4>& screen_tiles, const uint8_t* flags, size_t n_flags, int64_t n_kept,
+                       int n_limbs, int ctas, int64_t* n_flagged);
 
 }  // namespace wld

@@ -942,29 +942,37 @@ int ensure_tile_plan(wld_ctx* c, int which) {
 // (a 128-site cell column window of one M tile) is covered by the exact kernel's N tiles with their windows clipped
 // to it.  Cells without a flag hold no pair that can pass the threshold (the screen's bound), so nothing is lost.
 // The list keeps the strip-major order of the screen's list.
-int build_cell_plan(wld_ctx* c, const std::vector<uint8_t>& flags, int64_t* n_flagged) {
-  const DevPlan& sp = c->plans[1];
-  DevPlan& dp = c->plans[2];
-  const int64_t tile_m = (kBlockM / 2) * c->cta_group;
-  const int64_t tile_n = 2 * (128 / (2 * c->geom.n_limbs));
-  std::vector<uint4> tiles;
-  uint64_t pairs = 0;
+TilePlan cut_cell_plan(const std::vector<uint4>& screen_tiles, const uint8_t* flags, size_t n_flags, int64_t n_kept,
+                       int n_limbs, int ctas, int64_t* n_flagged) {
+  TilePlan plan;
+  plan.tile_m = (kBlockM / 2) * ctas;
+  plan.tile_n = 2 * (128 / (2 * n_limbs));
+  const int64_t tile_m = plan.tile_m, tile_n = plan.tile_n;
   int64_t flagged = 0;
-  for (size_t k = 0; k < sp.host.size() && k < flags.size(); ++k) {
+  for (size_t k = 0; k < screen_tiles.size() && k < n_flags; ++k) {
     if (!flags[k]) continue;
     ++flagged;
-    const uint4 cell = sp.host[k];  // {M tile, cell column, j_lo, j_hi}
-    const int64_t i0 = (int64_t)cell.x * tile_m, i1 = std::min<int64_t>(c->n_kept, i0 + tile_m);
+    const uint4 cell = screen_tiles[k];  // {M tile, cell column, j_lo, j_hi}
+    const int64_t i0 = (int64_t)cell.x * tile_m, i1 = std::min<int64_t>(n_kept, i0 + tile_m);
     for (int64_t nj = (int64_t)cell.z / tile_n; nj * tile_n < (int64_t)cell.w; ++nj) {
       const int64_t w_lo = std::max<int64_t>(nj * tile_n, cell.z), w_hi = std::min<int64_t>((nj + 1) * tile_n, cell.w);
       if (w_lo >= w_hi || i0 >= w_hi - 1) continue;
-      tiles.push_back(make_uint4(cell.x, (unsigned)nj, (unsigned)w_lo, (unsigned)w_hi));
-      if (i1 <= w_lo) pairs += (uint64_t)((i1 - i0) * (w_hi - w_lo));
+      plan.tiles.push_back(make_uint4(cell.x, (unsigned)nj, (unsigned)w_lo, (unsigned)w_hi));
+      if (i1 <= w_lo) plan.pairs += (uint64_t)((i1 - i0) * (w_hi - w_lo));
       else
-        for (int64_t i = i0; i < i1; ++i) pairs += (uint64_t)std::max<int64_t>(0, w_hi - std::max(w_lo, i + 1));
+        for (int64_t i = i0; i < i1; ++i) plan.pairs += (uint64_t)std::max<int64_t>(0, w_hi - std::max(w_lo, i + 1));
     }
   }
-  *n_flagged = flagged;
+  if (n_flagged) *n_flagged = flagged;
+  return plan;
+}
+
+int build_cell_plan(wld_ctx* c, const std::vector<uint8_t>& flags, int64_t* n_flagged) {
+  DevPlan& dp = c->plans[2];
+  TilePlan cut = cut_cell_plan(c->plans[1].host, flags.data(), flags.size(), c->n_kept, c->geom.n_limbs, c->cta_group, n_flagged);
+  std::vector<uint4>& tiles = cut.tiles;
+  const uint64_t pairs = cut.pairs;
+  const int64_t tile_m = cut.tile_m, tile_n = cut.tile_n;
   WLD_CUDA(c, dp.tiles.ensure(sizeof(uint4) * std::max<size_t>(tiles.size(), 1)));
   if (!tiles.empty())
     WLD_CUDA(c, cudaMemcpyAsync(dp.tiles.p, tiles.data(), sizeof(uint4) * tiles.size(), cudaMemcpyHostToDevice, c->stream));

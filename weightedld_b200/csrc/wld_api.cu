@@ -795,6 +795,26 @@ int wld_plan_tiles(int64_t n_kept, int n_limbs, int cta_group, int part, int npa
   return WLD_OK;
 }
 
+int wld_plan_cell_tiles(int64_t n_kept, int n_limbs, int cta_group, int part, int nparts, const uint8_t* flags, uint64_t n_flags,
+                        uint32_t* tiles, uint64_t cap_tiles, uint64_t* n_tiles, uint64_t* n_pairs) {
+  if (cta_group != 1 && cta_group != 2) return WLD_ERR_INVALID;
+  if (n_kept < 0 || n_limbs < 1 || n_limbs > 4 || nparts < 1 || part < 0 || part >= nparts || (!flags && n_flags)) return WLD_ERR_INVALID;
+  const TilePlan screen = plan_tiles(n_kept, 1, part, nparts, kNumSMsB200, cta_group);
+  const TilePlan plan = cut_cell_plan(screen.tiles, flags, (size_t)n_flags, n_kept, n_limbs, cta_group, nullptr);
+  if (n_tiles) *n_tiles = plan.tiles.size();
+  if (n_pairs) *n_pairs = plan.pairs;
+  if (tiles) {
+    if (cap_tiles < plan.tiles.size()) return WLD_ERR_INVALID;
+    for (size_t i = 0; i < plan.tiles.size(); ++i) {
+      tiles[4 * i] = plan.tiles[i].x;
+      tiles[4 * i + 1] = plan.tiles[i].y;
+      tiles[4 * i + 2] = plan.tiles[i].z;
+      tiles[4 * i + 3] = plan.tiles[i].w;
+    }
+  }
+  return WLD_OK;
+}
+
 // ---- host <-> device copies of large pageable buffers ------------------------------------------------
 // A cudaMemcpy between device memory and PAGEABLE host memory (a Rust Vec<u8> / Vec<PairData>, a numpy array)
 // is staged by the driver through a small pinned buffer at a fraction of the PCIe rate.  Large copies are
