@@ -253,3 +253,17 @@ def test_block_ld_goes_through_the_screen_and_the_exact_kernel_on_flagged_cells(
         modes.append(r["info"].screen)
     assert done == a["done"] and modes == [2, 2]
     assert wld.merge_shards(a["n_kept"], shards, a["site_map"]).tobytes() == a["pairs"].tobytes()
+
+
+@pytest.mark.gpu
+def test_medium_candidate_lists_are_costed_after_the_screen():
+    """Between "a handful" and "too many": the refinement first declines a list that is not short, and the host then
+    picks the cheapest way to finish from the exact counts — here (weak LD spread over many cells) the pair-by-pair
+    refinement after all.  Same bytes as the exact kernel."""
+    chars = synth(1500, 6000, seed=61, founders=24, block=900)
+    a = run(chars, "never", thr=0.02)
+    b = run(chars, "auto", thr=0.02)
+    bi = b["info"]
+    assert a["pairs"].tobytes() == b["pairs"].tobytes() and len(a["pairs"]) > 1000
+    if bi.screen == 1 and bi.screen_candidates > 65536:
+        assert bi.screen_cells > 0          # it was costed on the host (flags were read back) and refined pair by pair

@@ -610,21 +610,31 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
     }
     unsigned long long progress_last = 0;
     bool cells_only = false;            // the exact kernel over the cells the screen flagged (plans[2])
+    bool refine_only = false;           // the screen has run and its candidate list is complete: refine it, whatever its length
     uint64_t screened_pairs = 0;        // pairs the screen went through before that
     for (int attempt = 0; attempt < 4; ++attempt) {
-      WLD_CUDA(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 8, c->stream));
+      if (refine_only) {  // keep the screen's counters (candidates, pairs); clear the survivor count and the "declined" word
+        WLD_CUDA(c, cudaMemsetAsync(c->counters.as<unsigned long long>(), 0, sizeof(unsigned long long), c->stream));
+        WLD_CUDA(c, cudaMemsetAsync(c->counters.as<unsigned long long>() + 6, 0, sizeof(unsigned long long), c->stream));
+      } else
+        WLD_CUDA(c, cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long) * 8, c->stream));
       c->die_used = 0;
-      if (use_screen) {
+      if (use_screen && !refine_only) {
         const size_t n_screen_tiles = (size_t)std::max<int64_t>(c->plans[1].n_tiles, 1);
         WLD_CUDA(c, c->cell_flags.ensure(n_screen_tiles));
         WLD_CUDA(c, cudaMemsetAsync(c->cell_flags.p, 0, n_screen_tiles, c->stream));
       }
       {
-        int rc = c->pair_kernel == WLD_PAIR_KERNEL_SIMT ? run_pair_simt(c, r2_threshold)
-                                                        : run_pair_umma(c, r2_threshold, use_screen ? 1 : cells_only ? 3 : 0);
-        // automatic mode: twice the candidate rate the screen is chosen at is the point of no return (pair_refine.cu)
-        if (rc == WLD_OK && use_screen)
-          rc = run_pair_refine(c, r2_threshold, c->screen_opt == 2 ? ~0ull : expect_cells ? 0ull : std::max<uint64_t>(c->plan_pairs / 128, 1ull << 16));
+        int rc = refine_only ? WLD_OK
+                 : c->pair_kernel == WLD_PAIR_KERNEL_SIMT ? run_pair_simt(c, r2_threshold)
+                                                          : run_pair_umma(c, r2_threshold, use_screen ? 1 : cells_only ? 3 : 0);
+        // Automatic mode: a short candidate list (recomputing it costs below 3 % of the exact kernel: 455/limbs per unit
+        // of candidate rate, see above) is refined at once; with a longer one the refinement declines on the device and
+        // the host chooses below, from the exact counts, how to finish.  (expect_cells: the sample already said so.)
+        if (rc == WLD_OK && use_screen) {
+          const uint64_t short_list = std::max<uint64_t>(1ull << 16, (uint64_t)((double)c->plan_pairs * 0.03 * c->geom.n_limbs / 455.0));
+          rc = run_pair_refine(c, r2_threshold, (c->screen_opt == 2 || refine_only) ? ~0ull : expect_cells ? 0ull : short_list);
+        }
         // pairs whose per-pair allele call may differ from the per-site call (WeightedLD.py:186-211)
         if (rc == WLD_OK && c->compat == WLD_COMPAT_PYTHON) rc = run_pair_python_fixup(c, r2_threshold);
         if (rc != WLD_OK) return rc;
@@ -664,16 +674,28 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
       if (use_screen) {
         c->info.screen_candidates = (int64_t)cnt[5];
         if (cnt[6]) {
-          // The refinement declined (too many candidates to recompute one by one).  The exact kernel takes over — on the
-          // cells in which the screen found a candidate when those are a minority (LD confined to a band or to blocks:
-          // every other cell is ruled out by the screen's bound), else on all of this partition's pairs.
-          use_screen = false;
+          // The refinement declined: the candidate list is not short.  Three ways to finish, costed with the exact
+          // numbers now at hand (units of the exact kernel over every pair): recompute the candidates one by one after
+          // all; run the exact kernel on the cells in which the screen found a candidate (LD confined to a band or to
+          // blocks: every other cell is ruled out by the screen's bound); or run it on all of this partition's pairs.
           std::vector<uint8_t> flags((size_t)c->plans[1].n_tiles);
           if (!flags.empty())
             WLD_CUDA(c, cudaMemcpyAsync(flags.data(), c->cell_flags.p, flags.size(), cudaMemcpyDeviceToHost, c->stream));
           WLD_CUDA(c, cudaStreamSynchronize(c->stream));
           int64_t n_flagged = 0;
           for (uint8_t f : flags) n_flagged += f != 0;
+          c->info.screen_cells = c->plans[1].n_tiles;
+          c->info.screen_cells_flagged = n_flagged;
+          {
+            const double limbs_d = (double)std::max(c->geom.n_limbs, 1);
+            const double cost_pairs = cnt[5] <= c->cand_cap ? 455.0 / limbs_d * (double)cnt[5] / (double)std::max<uint64_t>(c->plan_pairs, 1) : 1e9;
+            const double cost_cells = 1.3 * (double)n_flagged / (double)std::max<int64_t>(c->plans[1].n_tiles, 1) + 0.02;
+            if (cost_pairs <= std::min(cost_cells, 1.0)) {
+              refine_only = true;  // use_screen stays set: the survivors come from the candidate list
+              --attempt;
+              continue;
+            }
+          }
           {  // the screen's time stays part of the pair stage
             StageTimer& pt = c->timers[WLD_STAGE_PAIR];
             float ms = 0.f;
@@ -682,8 +704,7 @@ int wld_ld_pairs(wld_ctx* c, float r2_threshold, wld_progress_fn progress, void*
               pt.carry_launches += pt.launches;
             }
           }
-          c->info.screen_cells = c->plans[1].n_tiles;
-          c->info.screen_cells_flagged = n_flagged;
+          use_screen = false;
           ScopedStageTimer tm(c, WLD_STAGE_PAIR_PREP);
           int rc = run_expand_limbs(c, tm, false);
           if (rc == WLD_OK) rc = ensure_tile_plan(c, 0);
